@@ -1,0 +1,171 @@
+"""CPU: pin oracle/stellar_oracle.py against the reference's recorded outputs
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from the unmodified
+reference) and, when the checkout is present, against the live reference."""
+import numpy as np
+import pytest
+
+import ref_shim
+import stellar_oracle as so
+from helpers import first_divergence, golden, relerr, setup_from
+
+TOL = 1e-13  # the oracle follows the reference's operation order; expect ~1e-16
+
+
+def test_constants_match_survey():
+    S = so.Setup()
+    assert S.PSF_FWHM_pix == 3.4999999999999996
+    assert S.flux_to_count == 39.592934273456464
+    assert S.B_count == 24.98145266935892 == S.f_lim
+    assert (S.g0, S.g1, S.g2) == (0.035997054345069765, 0.4523523265306124, 0.008141675878296745)
+
+
+def test_psf_normalised_interior():
+    psf = so.gauss_psf(48, 48, 24.2, 23.7, 3.5)
+    assert abs(psf.sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["kat1", "kat2", "field_eval_204"])
+def test_l2_functions(name):
+    g = golden(name)
+    S = setup_from(g)
+    q, p = g["q"], g["p"]
+    assert relerr(so.potential(S, q, f_pos=True), g["V"]) < TOL
+    assert relerr(so.grad_potential(S, q), g["dVdq"]) < TOL
+    H, dH = so.metric(S, q, grad=True)
+    assert relerr(H, g["H"]) < TOL and relerr(dH, g["dH"]) < TOL
+    assert relerr(so.kinetic(p, H), g["T"]) < TOL
+    if "dphidq" in g:
+        assert relerr(so.dphidq(S, q), g["dphidq"]) < TOL
+    if "dtaudq" in g:
+        assert np.allclose(so.dtaudq(S, q, p), g["dtaudq"], rtol=TOL, atol=0)
+        assert relerr(so.dtaudp(S, q, p), g["dtaudp"]) < TOL
+
+
+def test_single_step_kat1():
+    g = golden("kat1")
+    S = setup_from(g)
+    q1, p1 = so.rhmc_step(S, g["q"], g["p"], 1e-6, 1000)
+    assert relerr(q1, g["q1"]) < TOL and relerr(p1, g["p1"]) < TOL
+    e0 = so.potential(S, g["q"], True) + so.kinetic(g["p"], so.metric(S, g["q"]))
+    assert relerr(e0, g["E0"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["kat1", "kat2"])
+def test_multi_step_trajectory(name):
+    g = golden(name)
+    S = setup_from(g)
+    q, p = g["q"], g["p"]
+    for i in range(1, len(g["q_traj"])):
+        q, p = so.rhmc_step(S, q, p, 1e-6, 1000)
+        assert relerr(q, g["q_traj"][i]) < 1e-12
+        assert relerr(p, g["p_traj"][i]) < 1e-11
+
+
+def test_step_204_stars():
+    g = golden("field_eval_204")
+    S = setup_from(g)
+    q1, p1 = so.rhmc_step(S, g["q"], g["p"], 1e-6, 1000)
+    assert relerr(q1, g["q1"]) < TOL and relerr(p1, g["p1"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["chain_one_star_m19", "chain_one_star_m21", "chain_one_star_m15", "chain_one_star_m20_sep1"])
+def test_run_rhmc_one_star(name):
+    g = golden(name)
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    out = so.run_rhmc(S, q0, g["normals"], g["lnu"], int(g["niter"]), int(g["nsteps"]), float(g["dt"]))
+    assert np.array_equal(out.A, g["A_chain"])
+    assert first_divergence(out.q, g["q_chain"], 1e-12) == -1
+    assert first_divergence(out.p, g["p_chain"], 1e-11) == -1
+    assert relerr(out.E, g["E_chain"]) < 1e-13 and relerr(out.V, g["V_chain"]) < 1e-13
+    assert 0 < out.A.sum() <= out.A.size
+
+
+@pytest.mark.parametrize("name", ["chain_multi30_vc", "chain_multi100"])
+def test_run_rhmc_crowded(name):
+    g = golden(name)
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    out = so.run_rhmc(S, q0, g["normals"], g["lnu"], int(g["niter"]), int(g["nsteps"]), float(g["dt"]),
+                      schedule_g_ff2=g["schedule_g_ff2"], schedule_beta=g["schedule_beta"])
+    assert np.array_equal(out.A, g["A_chain"])
+    n3 = q0.size
+    assert first_divergence(out.q, g["q_chain"][:, :n3], 1e-11) == -1
+    assert first_divergence(out.p, g["p_chain"][:, :n3], 1e-10) == -1
+    assert relerr(out.E, g["E_chain"]) < 1e-12
+
+
+def test_run_single_rhmc():
+    g = golden("single_traj")
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    out = so.run_single_rhmc(S, q0, g["p0"], int(g["nsteps"]), float(g["dt"]), f_pos=True)
+    assert first_divergence(out.q, g["q_chain"], 1e-11) == -1
+    assert first_divergence(out.p, g["p_chain"], 1e-10) == -1
+    assert np.allclose(out.V, g["V_chain"], rtol=0, atol=1e-8)
+    assert np.allclose(out.E, g["E_chain"], rtol=0, atol=1e-8)
+    # energy conservation property of RHMC-single-tests.py: drift stays tiny at dt=0.1
+    assert np.max(np.abs(out.E)) < 1.0
+
+
+def test_lightsource_functions():
+    g = golden("kat3")
+    L = so.LightSetup(num_rows=32, num_cols=32, D=g["D"], f_lim=0.0)
+    L.compute_factors()
+    q, p = g["q"], g["p"]
+    assert relerr([L.factor0, L.factor1, L.factor2], g["factors"]) < TOL
+    dqdt, dpdt, E = so.ls_efficient(L, q, p)
+    assert relerr(dqdt, g["dqdt"]) < TOL and relerr(dpdt, g["dpdt"]) < 1e-12 and relerr(E, g["E_eff"]) < TOL
+    assert relerr(so.ls_efficient(L, q, p, dVdqq_only=True), g["dVdqq"]) < TOL
+    M = so.ls_mass_matrix(L, q)
+    assert relerr(M, g["mass"]) < TOL
+    assert np.allclose(so.ls_dlndet(L, q), g["dlnDetdq"], rtol=TOL, atol=0)
+    assert np.allclose(so.ls_dpmp(L, q, p), g["dpMpdq"], rtol=TOL, atol=0)
+    assert relerr(so.ls_kinetic(p, M), g["K"]) < TOL and relerr(so.ls_energy(L, q, p, M), g["E"]) < TOL
+    assert relerr(so.ls_potential(L, q), g["V"]) < TOL and relerr(so.ls_grad(L, q), g["dVdq"]) < TOL
+
+
+def test_lightsource_chains():
+    g = golden("light_chains")
+    L = so.LightSetup(num_rows=32, num_cols=32, D=g["D"])
+    L.compute_factors()
+    niter = int(g["niter"])
+    out = so.ls_hmc_random(L, g["q0"], g["dt_vec"], g["hmc_normals"], g["hmc_steps"], g["hmc_lnu"], niter,
+                           f_lim=float(g["f_lim"]))
+    assert np.array_equal(out.A, g["hmc_A"])
+    assert first_divergence(out.q, g["hmc_q"], 1e-11) == -1
+    assert relerr(out.E, g["hmc_E"]) < 1e-12
+    out = so.ls_rhmc_random_diag(L, g["q0"], float(g["dt_global"]), g["diag_normals"], g["diag_steps"],
+                                 g["diag_lnu"], niter, f_lim=float(g["f_lim"]))
+    assert np.array_equal(out.A, g["diag_A"])
+    assert first_divergence(out.q, g["diag_q"], 1e-11) == -1
+    assert relerr(out.E, g["diag_E"]) < 1e-12
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_live_reference_random_states():
+    """Random (q, p) on random Poisson data: oracle == live reference."""
+    _, srhmc, _ = ref_shim.load()
+    rng = np.random.RandomState(123)
+    for trial in range(3):
+        n = [1, 5, 17][trial]
+        gym = srhmc.multi_gym(dt=0.01, g_xx=0.05, g_ff=4.0, g_ff2=3.0)
+        gym.num_rows = gym.num_cols = 24
+        gym.V_prior_const = 0.3
+        gym.use_prior, gym.alpha = True, 1.7
+        gym.use_Vc, gym.beta, gym.Vc_r_pow, gym.f_expnt = True, 1e-3, 3.0, np.zeros(n)
+        gym.Nobjs, gym.d = n, 3 * n
+        q = np.zeros(3 * n)
+        q[0::3] = gym.mag2flux_converter(rng.uniform(15, 22, n))
+        q[1::3] = rng.uniform(1, 23, n)
+        q[2::3] = rng.uniform(1, 23, n)
+        gym.D = rng.poisson(gym.gen_model(np.c_[gym.flux2mag_converter(q[0::3]), q[1::3], q[2::3]])).astype(float)
+        S = so.Setup(num_rows=24, num_cols=24, dt=0.01, g_xx=0.05, g_ff=4.0, g_ff2=3.0, use_prior=True, alpha=1.7,
+                     V_prior_const=0.3, use_Vc=True, beta=1e-3, Vc_r_pow=3.0, D=gym.D)
+        p = rng.randn(3 * n) * np.sqrt(gym.H(q))
+        assert relerr(so.potential(S, q, True), gym.V(q, f_pos=True)) < TOL
+        assert relerr(so.grad_potential(S, q), gym.dVdq(q)) < TOL
+        q1, p1 = so.rhmc_step(S, q, p)
+        qr, pr = gym.RHMC_single_step(np.copy(q), np.copy(p))
+        assert relerr(q1, qr) < TOL and relerr(p1, pr) < 1e-12
