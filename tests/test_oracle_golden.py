@@ -104,8 +104,12 @@ def test_run_single_rhmc():
     assert first_divergence(out.p, g["p_chain"], 1e-10) == -1
     assert np.allclose(out.V, g["V_chain"], rtol=0, atol=1e-8)
     assert np.allclose(out.E, g["E_chain"], rtol=0, atol=1e-8)
-    # energy conservation property of RHMC-single-tests.py: drift stays tiny at dt=0.1
-    assert np.max(np.abs(out.E)) < 1.0
+    # RHMC-single-tests.py plots the energy error against dt.  The reference flow (which drops the p_x, p_y
+    # and H_xx' terms of dtau/dq, sampler_RHMC.py:477-481) does not conserve V+T exactly, but the integrator
+    # converges: the end-of-trajectory energy at dt=0.1 and dt=0.01 over the same time span agree to ~1%.
+    coarse = so.run_single_rhmc(S, q0, g["p0"], 20, 0.1, f_pos=True)
+    fine = so.run_single_rhmc(S, q0, g["p0"], 200, 0.01, f_pos=True)
+    assert abs(coarse.E[-1] - fine.E[-1]) < 0.02 * abs(fine.E[-1])
 
 
 def test_lightsource_functions():
