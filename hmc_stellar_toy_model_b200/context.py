@@ -1,0 +1,207 @@
+"""RHMCContext: numpy-in / numpy-out wrapper over the C ABI for a batch of independent fields.
+
+The gym classes in sampler_RHMC.py / samplers.py (the reference's call surface) are built on this; it is also the
+batch API the reference lacks (`Nchain == 1` everywhere upstream): F fields or chains advance in one launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import Config, RunArgs, as_f64, bptr, check, dptr, iptr
+
+
+@dataclass
+class RunResult:
+    q_chain: np.ndarray | None
+    p_chain: np.ndarray | None
+    E_chain: np.ndarray | None
+    V_chain: np.ndarray | None
+    T_chain: np.ndarray | None
+    A_chain: np.ndarray | None
+    q_final: np.ndarray
+    accept_rate: np.ndarray
+    kernel_ms: float
+
+
+class RHMCContext:
+    """Device context holding `n_fields` fields of `num_rows x num_cols` pixels with up to `max_stars` stars."""
+
+    def __init__(self, *, n_fields, num_rows, num_cols, max_stars, psf_fwhm_pix, B_count, f_lim, f_low, g0, g1, g2,
+                 g_xx, g_ff, use_prior=False, alpha=2.0, V_prior_const=0.0, use_Vc=False, Vc_r_pow=1.0,
+                 precision=64, patch_radius=0, shared_data=False, fixed_point_mode=0, device=0):
+        self._lib = _capi.load_library()
+        cfg = Config(
+            abi_version=_capi.ABI_VERSION, device=device, precision=precision, n_fields=n_fields, num_rows=num_rows,
+            num_cols=num_cols, max_stars=max_stars, patch_radius=patch_radius, shared_data=int(bool(shared_data)),
+            fixed_point_mode=fixed_point_mode, use_prior=int(bool(use_prior)), use_Vc=int(bool(use_Vc)),
+            psf_fwhm_pix=psf_fwhm_pix, B_count=B_count, f_lim=f_lim, f_low=f_low, g0=g0, g1=g1, g2=g2, g_xx=g_xx,
+            g_ff=g_ff, alpha=alpha, V_prior_const=V_prior_const, Vc_r_pow=Vc_r_pow)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(self._lib.srhmc_create(C.byref(cfg), C.byref(self._h)))
+        self.F = n_fields
+        self.S = 3 * max_stars
+        self._run_args = None
+        self._keep = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.srhmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    # ------------------------------------------------------------------ plumbing
+    def set_stream(self, cuda_stream_ptr):
+        check(self._lib.srhmc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        check(self._lib.srhmc_synchronize(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(self._lib.srhmc_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.srhmc_launch_count(self._h))
+
+    def _nstars(self, nstars):
+        if nstars is None:
+            return None
+        return np.ascontiguousarray(nstars, dtype=np.int32).reshape(self.F)
+
+    # ------------------------------------------------------------------ data
+    def set_data(self, D):
+        D = as_f64(D)
+        n_img = 1 if self.cfg.shared_data else self.F
+        D = D.reshape(n_img, self.cfg.num_rows, self.cfg.num_cols)
+        check(self._lib.srhmc_set_data(self._h, dptr(D), n_img))
+
+    # ------------------------------------------------------------------ a2-a4: V, dVdq, H
+    def eval(self, q, nstars=None, f_pos=False, g_ff2=1.0, beta=1.0):
+        q = as_f64(q, (self.F, self.S))
+        ns = self._nstars(nstars)
+        V = np.empty(self.F)
+        grad = np.zeros((self.F, self.S))
+        H = np.zeros((self.F, self.S))
+        Hg = np.zeros((self.F, self.S))
+        check(self._lib.srhmc_eval(self._h, dptr(q), iptr(ns), int(bool(f_pos)), float(g_ff2), float(beta),
+                                   dptr(V), dptr(grad), dptr(H), dptr(Hg)))
+        return V, grad, H, Hg
+
+    # ------------------------------------------------------------------ a7: RHMC_single_step
+    def step(self, q, p, nsteps, dt, delta=1e-6, counter_max=1000, g_ff2=1.0, beta=1.0, nstars=None,
+             return_counts=False):
+        q = np.array(as_f64(q, (self.F, self.S)), copy=True)
+        p = np.array(as_f64(p, (self.F, self.S)), copy=True)
+        ns = self._nstars(nstars)
+        counts = np.zeros((self.F, 2), dtype=np.int32)
+        check(self._lib.srhmc_step(self._h, dptr(q), dptr(p), iptr(ns), int(nsteps), float(dt), float(delta),
+                                   int(counter_max), float(g_ff2), float(beta), iptr(counts)))
+        return (q, p, counts) if return_counts else (q, p)
+
+    # ------------------------------------------------------------------ a8: run_RHMC move-0 leg
+    def make_run_args(self, q0, niter, nsteps, dt, *, nstars=None, delta=1e-6, counter_max=1000, f_pos=True,
+                      g_ff2=1.0, beta=1.0, schedule_g_ff2=None, schedule_beta=None, normals=None, lnu=None, seed=0,
+                      chain_stride=1, want=("q", "p", "E", "V", "T", "A"), out=None):
+        """Build the argument block (and the host arrays it points at).  `out` may supply preallocated
+        (e.g. pinned) output arrays keyed like RunResult fields."""
+        F, S, L = self.F, self.S, int(niter) + 1
+        rows = (L + chain_stride - 1) // chain_stride
+        keep = {}
+        keep["q0"] = as_f64(q0, (F, S))
+        keep["nstars"] = self._nstars(nstars)
+        keep["sg"] = None if schedule_g_ff2 is None else as_f64(schedule_g_ff2).ravel()
+        keep["sb"] = None if schedule_beta is None else as_f64(schedule_beta).ravel()
+        keep["normals"] = None if normals is None else as_f64(normals, (F, L, S))
+        keep["lnu"] = None if lnu is None else as_f64(lnu, (F, L))
+        out = dict(out or {})
+
+        def buf(key, shape, dtype=np.float64):
+            if key in out and out[key] is not None:
+                a = out[key]
+                assert a.shape == shape and a.dtype == dtype and a.flags.c_contiguous
+                return a
+            return np.zeros(shape, dtype=dtype)
+
+        keep["q_chain"] = buf("q_chain", (F, rows, S)) if "q" in want else None
+        keep["p_chain"] = buf("p_chain", (F, rows, S)) if "p" in want else None
+        keep["E_chain"] = buf("E_chain", (F, rows)) if "E" in want else None
+        keep["V_chain"] = buf("V_chain", (F, rows)) if "V" in want else None
+        keep["T_chain"] = buf("T_chain", (F, rows)) if "T" in want else None
+        keep["A_chain"] = buf("A_chain", (F, rows), np.uint8) if "A" in want else None
+        keep["q_final"] = buf("q_final", (F, S))
+        keep["accept_rate"] = buf("accept_rate", (F,))
+        a = RunArgs(
+            q0=dptr(keep["q0"]), nstars=iptr(keep["nstars"]), niter=int(niter), nsteps=int(nsteps), dt=float(dt),
+            delta=float(delta), counter_max=int(counter_max), f_pos=int(bool(f_pos)), g_ff2=float(g_ff2),
+            beta=float(beta), g_ff2_schedule=dptr(keep["sg"]), n_g_ff2=0 if keep["sg"] is None else keep["sg"].size,
+            beta_schedule=dptr(keep["sb"]), n_beta=0 if keep["sb"] is None else keep["sb"].size,
+            normals=dptr(keep["normals"]), lnu=dptr(keep["lnu"]), seed=int(seed), chain_stride=int(chain_stride),
+            reserved=0, q_chain=dptr(keep["q_chain"]), p_chain=dptr(keep["p_chain"]), E_chain=dptr(keep["E_chain"]),
+            V_chain=dptr(keep["V_chain"]), T_chain=dptr(keep["T_chain"]), A_chain=bptr(keep["A_chain"]),
+            q_final=dptr(keep["q_final"]), accept_rate=dptr(keep["accept_rate"]))
+        return a, keep
+
+    def _result(self, keep):
+        return RunResult(keep["q_chain"], keep["p_chain"], keep["E_chain"], keep["V_chain"], keep["T_chain"],
+                         keep["A_chain"], keep["q_final"], keep["accept_rate"], self.last_kernel_ms())
+
+    def run(self, q0, niter, nsteps, dt, **kw):
+        """All (niter+1) x nsteps leapfrog steps of every field in ONE resident launch."""
+        a, keep = self.make_run_args(q0, niter, nsteps, dt, **kw)
+        check(self._lib.srhmc_run(self._h, C.byref(a)))
+        return self._result(keep)
+
+    # split phases, for callers that keep inputs resident (bench.py `value`)
+    def run_upload(self, a):
+        check(self._lib.srhmc_run_upload(self._h, C.byref(a)))
+
+    def run_launch(self, a):
+        check(self._lib.srhmc_run_launch(self._h, C.byref(a)))
+
+    def run_download(self, a):
+        check(self._lib.srhmc_run_download(self._h, C.byref(a)))
+
+    # ------------------------------------------------------------------ a9: run_single_RHMC(implicit)
+    def run_single(self, q0, p0, nsteps, dt, delta=1e-6, counter_max=100, f_pos=False, g_ff2=1.0, beta=1.0,
+                   nstars=None):
+        F, S, rows = self.F, self.S, int(nsteps) + 1
+        q0 = as_f64(q0, (F, S))
+        p0 = as_f64(p0, (F, S))
+        ns = self._nstars(nstars)
+        qc = np.zeros((F, rows, S))
+        pc = np.zeros((F, rows, S))
+        E = np.zeros((F, rows))
+        V = np.zeros((F, rows))
+        T = np.zeros((F, rows))
+        check(self._lib.srhmc_run_single(self._h, dptr(q0), dptr(p0), iptr(ns), int(nsteps), float(dt), float(delta),
+                                         int(counter_max), int(bool(f_pos)), float(g_ff2), float(beta), dptr(qc),
+                                         dptr(pc), dptr(E), dptr(V), dptr(T)))
+        return qc, pc, E, V, T
+
+    # ------------------------------------------------------------------ device RNG replay
+    def philox_draws(self, seed, niter):
+        L = int(niter) + 1
+        normals = np.zeros((self.F, L, self.S))
+        lnu = np.zeros((self.F, L))
+        check(self._lib.srhmc_philox_draws(self._h, int(seed), int(niter), dptr(normals), dptr(lnu)))
+        return normals, lnu

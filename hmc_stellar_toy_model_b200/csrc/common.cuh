@@ -1,0 +1,190 @@
+// Shared device helpers for the sm_100a RHMC kernels: parameter blocks, the metric of the reference
+// (sampler_RHMC.py:229-292), fast FP64 reciprocal, deterministic reductions and a Philox4x32-10 generator.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srhmc {
+
+constexpr int kWarp = 32;
+
+// Problem constants snapshot (host fills it from srhmc_config).
+struct FieldParams {
+    int R, C;          // image rows / cols
+    int Nmax;          // star slots per field
+    int Kc;            // stars per table chunk
+    int rad;           // PSF truncation radius in pixels, 0 = full image
+    int sx, sy;        // table strides (rows / cols rounded up to the warp-tile)
+    int fp_mode;       // 0 parity (field-wide stop rule), 1 per-star
+    int D_shared;      // all fields read image 0
+    int use_prior, use_Vc, vc_int;  // vc_int: Vc_r_pow as small non-negative integer, or -1
+    double inv2s2;     // 1/(2 sigma^2)
+    double inv_s2;     // 1/sigma^2
+    double norm;       // 1/(2 pi sigma^2)
+    double c2;         // exp(-1/sigma^2): second-order ratio of the Gaussian recurrence
+    double B, f_lim, f_low;
+    double g0, g1, g2, g_xx, g_ff;
+    double alpha, Vpc, vc_pow;
+};
+
+enum Mode : int { MODE_EVAL = 0, MODE_STEP = 1, MODE_RUN = 2, MODE_SINGLE = 3 };
+
+// Per-launch arguments (device pointers).
+struct LaunchArgs {
+    int mode;
+    int n_fields;
+    const void* D;          // [n_images, R*C] in the pixel type
+    const int* nstars;      // [F] or nullptr
+    // state in / out
+    const double* q_in;     // [F,S]
+    const double* p_in;     // [F,S] (STEP, SINGLE)
+    double* q_out;          // [F,S]
+    double* p_out;          // [F,S]
+    // integrator
+    int niter, nsteps, counter_max, f_pos;
+    double dt, delta, g_ff2, beta;
+    const double* gff2_sched; int n_gff2;
+    const double* beta_sched; int n_beta;
+    // draws
+    const double* normals;  // [F,L,S] or nullptr -> Philox
+    const double* lnu;      // [F,L] or nullptr -> Philox
+    unsigned long long seed;
+    // outputs
+    int chain_stride;
+    int n_rows;             // chain rows kept per field
+    double* q_chain; double* p_chain; double* E_chain; double* V_chain; double* T_chain;
+    unsigned char* A_chain;
+    double* accept_rate;    // [F]
+    // EVAL outputs
+    double* V_out; double* grad_out; double* H_out; double* Hgrad_out;
+    int* fp_counts;         // [F,2]
+    double* draws_normals;  // philox dump
+    double* draws_lnu;
+};
+
+// ------------------------------------------------------------------ metric (sampler_RHMC.py:229-292)
+struct Metric {
+    double Hff, dHff, Hxx, dHxx;
+};
+
+__device__ __forceinline__ Metric metric_of(const FieldParams& P, double f, double g_ff2) {
+    Metric m;
+    const double c = (P.B / P.g0) / P.g_ff;
+    m.Hff = 1.0 / (f / g_ff2 + c);
+    const double s = f + c;
+    m.dHff = -1.0 / (s * s);                 // reference formula: ignores g_ff2 (sampler_RHMC.py:292)
+    const bool low = f < P.f_low;            // faint clamp at mag mB+2 (sampler_RHMC.py:267-271)
+    const double fh = low ? P.f_low : f;
+    const double inner = 1.0 / (P.g1 * fh) + P.B / (P.g2 * fh * fh);
+    m.Hxx = P.g_xx * (1.0 / inner);
+    m.dHxx = low ? 0.0
+                 : P.g_xx * (1.0 / (P.g1 * fh * fh) + 2.0 * P.B / (P.g2 * fh * fh * fh)) * (1.0 / (inner * inner));
+    return m;
+}
+
+// ------------------------------------------------------------------ arithmetic helpers
+// 1/a for normal positive a: MUFU.RCP64H seed (~2^-20) + one cubic step -> ~2^-60 relative error.
+__device__ __forceinline__ double rcp_fast(double a) {
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
+    const double e = fma(-a, x0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(x0, t, x0);
+}
+__device__ __forceinline__ float rcp_fast(float a) { return __frcp_rn(a); }
+
+__device__ __forceinline__ double ipow(double b, int n) {  // b^n, small n >= 0
+    double r = 1.0;
+    while (n > 0) {
+        if (n & 1) r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic CTA-wide sum of NV doubles; result valid in every thread.  `red` holds >= NV*32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();  // protect `red` from the previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = (lane < nw) ? red[i * 32 + lane] : 0.0;
+        v[i] = warp_sum(x);
+    }
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 (Salmon et al. 2011)
+struct Philox {
+    uint32_t key[2];
+    __device__ __forceinline__ static void round(uint32_t (&c)[4], const uint32_t (&k)[2]) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+        const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ __forceinline__ static void block(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t (&out)[4]) {
+        uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, k);
+            k[0] += 0x9E3779B9u;
+            k[1] += 0xBB67AE85u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = c[i];
+    }
+};
+
+// uniform in (0,1) with 53 random bits from two words
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+    const unsigned long long m = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Three standard normals for (field, iteration, star); counter layout documented in DESIGN.md.
+__device__ __forceinline__ void philox_normals3(uint64_t seed, uint32_t field, uint32_t iter, uint32_t star,
+                                                double (&z)[3]) {
+    uint32_t r[4];
+    Philox::block(seed, star, iter, field, 0u, r);
+    double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+    double rad = sqrt(-2.0 * log(u1)), s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z[0] = rad * c;
+    z[1] = rad * s;
+    Philox::block(seed, star, iter, field, 1u, r);
+    u1 = u01(r[0], r[1]);
+    u2 = u01(r[2], r[3]);
+    rad = sqrt(-2.0 * log(u1));
+    sincospi(2.0 * u2, &s, &c);
+    z[2] = rad * c;
+}
+__device__ __forceinline__ double philox_lnu(uint64_t seed, uint32_t field, uint32_t iter) {
+    uint32_t r[4];
+    Philox::block(seed, 0xFFFFFFFFu, iter, field, 2u, r);
+    return log(u01(r[0], r[1]));
+}
+
+}  // namespace srhmc

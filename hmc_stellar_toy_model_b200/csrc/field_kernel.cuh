@@ -1,0 +1,686 @@
+// CTA-per-field resident RHMC kernel (sm_100a).
+//
+// One thread block owns one field (one chain): the data image D and the model/residual image stay in shared
+// memory for the whole launch, star state (q, p, cached pixel gradient) too, and every leapfrog step, momentum
+// refresh, energy and Metropolis test of the chain runs device-side (no host round trip).
+//
+// Pixel work per gradient evaluation (reference: base_class.dVdq, sampler_RHMC.py:365-425):
+//   sweep 1  tables  ex_k[i] = f_k exp(-(i+.5-x_k)^2/2s^2),  ey_k[j] = exp(-(j+.5-y_k)^2/2s^2)/(2 pi s^2)
+//                    (separable PSF; built with the exact two-term Gaussian recurrence, 3 exps per star-axis)
+//            render  Lambda = B + sum_k ex_k[i] ey_k[j]     register-tiled gather, MRxMC pixels per thread,
+//                    deterministic star order; rho = D/Lambda - 1 written back in place (+ V = sum(L - D ln L))
+//   sweep 2  grads   one warp per star: column sums c0_j = sum_i rho_ij ex_i, c1_j = sum_i rho_ij ex_i dx_i,
+//                    then g_f = -sum_j ey_j c0_j, g_x = -(f/s^2) sum_j ey_j c1_j, g_y = -(f/s^2) sum_j ey_j dy_j c0_j
+//                    finished with warp shuffles.
+// Scalar work (metric, implicit fixed points, reflections; sampler_RHMC.py:229-292, 448-492, 522-566) is one
+// thread per star with a CTA-wide vote per fixed-point iteration (the reference's field-wide stop rule).
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace srhmc {
+
+struct SmemLayout {
+    size_t q, p, g, a1, a2, red, D, L, tabx, taby, span, total;
+};
+
+template <typename T>
+__host__ __device__ inline SmemLayout make_layout(const FieldParams& P, bool d_in_smem) {
+    SmemLayout s;
+    size_t o = 0;
+    const size_t S = 3 * (size_t)P.Nmax * sizeof(double);
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o += (bytes + 15) & ~(size_t)15;
+        return at;
+    };
+    s.q = take(S);
+    s.p = take(S);
+    s.g = take(S);
+    s.a1 = take(S);
+    s.a2 = take(S);
+    s.red = take(8 * 32 * sizeof(double));
+    s.D = take(d_in_smem ? (size_t)P.R * P.C * sizeof(T) : 0);
+    s.L = take((size_t)P.R * P.C * sizeof(T));
+    s.tabx = take((size_t)P.Kc * P.sx * sizeof(T));
+    s.taby = take((size_t)P.Kc * P.sy * sizeof(T));
+    s.span = take((size_t)P.Kc * 4 * sizeof(short));
+    s.total = o;
+    return s;
+}
+
+template <typename T>
+struct Ctx {
+    const FieldParams* P;
+    T* sD;         // nullptr when D is read from global / L2
+    T* sL;
+    T* tabx;
+    T* taby;
+    const T* gD;   // this field's image in global memory
+    double *q, *p, *g, *a1, *a2, *red;
+    short* span;
+    int N;
+    double g_ff2, beta, h;
+};
+
+template <typename T, int N> struct VecLoad;
+template <> struct VecLoad<double, 1> { static __device__ __forceinline__ void ld(const double* p, double* o) { o[0] = p[0]; } };
+template <> struct VecLoad<double, 2> { static __device__ __forceinline__ void ld(const double* p, double* o) {
+    const double2 v = *reinterpret_cast<const double2*>(p); o[0] = v.x; o[1] = v.y; } };
+template <> struct VecLoad<double, 4> { static __device__ __forceinline__ void ld(const double* p, double* o) {
+    const double2 a = *reinterpret_cast<const double2*>(p); const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; } };
+template <> struct VecLoad<float, 1> { static __device__ __forceinline__ void ld(const float* p, float* o) { o[0] = p[0]; } };
+template <> struct VecLoad<float, 2> { static __device__ __forceinline__ void ld(const float* p, float* o) {
+    const float2 v = *reinterpret_cast<const float2*>(p); o[0] = v.x; o[1] = v.y; } };
+template <> struct VecLoad<float, 4> { static __device__ __forceinline__ void ld(const float* p, float* o) {
+    const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; } };
+
+// ---------------------------------------------------------------------------------------------- tables
+// One thread per (star, axis).  Exact recurrence: e(u+1) = e(u) r(u), r(u+1) = r(u) exp(-1/s^2), run outwards
+// from the pixel that contains the star so the rounding error stays at a few ulp where the PSF matters.
+template <typename T>
+__device__ void build_tables(const Ctx<T>& c, int k0, int nk, bool scale_f) {
+    const FieldParams& P = *c.P;
+    for (int t = threadIdx.x; t < 2 * nk; t += blockDim.x) {
+        const int kk = t >> 1, axis = t & 1, k = k0 + kk;
+        const double coord = c.q[3 * k + 1 + axis];
+        const int n = axis ? P.C : P.R;
+        const int stride = axis ? P.sy : P.sx;
+        T* tab = (axis ? c.taby : c.tabx) + (size_t)kk * stride;
+        const double scale = axis ? P.norm : (scale_f ? c.q[3 * k] : 1.0);
+        const double fl = floor(coord);
+        int m = 0;
+        if (fl > 0.0) m = (fl > (double)(n - 1)) ? n - 1 : (int)fl;
+        int lo = 0, hi = n - 1;
+        if (P.rad > 0) {
+            lo = max(0, m - P.rad);
+            hi = min(n - 1, m + P.rad);
+        }
+        for (int i = 0; i < lo; ++i) tab[i] = (T)0;
+        for (int i = hi + 1; i < stride; ++i) tab[i] = (T)0;
+        const double u = ((double)m + 0.5) - coord;
+        const double e0 = exp(-(u * u) * P.inv2s2) * scale;
+        tab[m] = (T)e0;
+        double e = e0, r = exp(-(2.0 * u + 1.0) * P.inv2s2);
+        for (int i = m + 1; i <= hi; ++i) {
+            e *= r;
+            r *= P.c2;
+            tab[i] = (T)e;
+        }
+        e = e0;
+        r = exp((2.0 * u - 1.0) * P.inv2s2);
+        for (int i = m - 1; i >= lo; --i) {
+            e *= r;
+            r *= P.c2;
+            tab[i] = (T)e;
+        }
+        c.span[4 * kk + 2 * axis] = (short)lo;
+        c.span[4 * kk + 2 * axis + 1] = (short)hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- render
+template <typename T, int MR, int MC>
+__device__ void render_chunk(const Ctx<T>& c, int nk, bool first, bool last, bool want_V, double& vacc) {
+    const FieldParams& P = *c.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    constexpr int TR = 8 * MR, TC = 4 * MC;
+    const int ntr = (P.R + TR - 1) / TR, ntc = (P.C + TC - 1) / TC;
+    for (int wt = warp; wt < ntr * ntc; wt += nwarps) {
+        const int ti = (wt / ntc) * TR, tj = (wt % ntc) * TC;
+        const int ib = ti + (lane >> 2) * MR, jb = tj + (lane & 3) * MC;
+        T acc[MR][MC];
+#pragma unroll
+        for (int r = 0; r < MR; ++r)
+#pragma unroll
+            for (int cc = 0; cc < MC; ++cc) {
+                const bool ok = (ib + r < P.R) && (jb + cc < P.C);
+                acc[r][cc] = first ? (T)P.B : (ok ? c.sL[(ib + r) * P.C + jb + cc] : (T)0);
+            }
+        auto accumulate = [&](int kk) {
+            T fx[MR], fy[MC];
+            VecLoad<T, MR>::ld(c.tabx + (size_t)kk * P.sx + ib, fx);
+            VecLoad<T, MC>::ld(c.taby + (size_t)kk * P.sy + jb, fy);
+#pragma unroll
+            for (int r = 0; r < MR; ++r)
+#pragma unroll
+                for (int cc = 0; cc < MC; ++cc) acc[r][cc] = fma(fx[r], fy[cc], acc[r][cc]);
+        };
+        if (P.rad == 0) {
+#pragma unroll 2
+            for (int kk = 0; kk < nk; ++kk) accumulate(kk);
+        } else {
+            for (int kb = 0; kb < nk; kb += 32) {
+                const int kk = kb + lane;
+                bool hit = false;
+                if (kk < nk) {
+                    const short4 sp = *reinterpret_cast<const short4*>(c.span + 4 * kk);
+                    hit = (sp.x <= ti + TR - 1) && (sp.y >= ti) && (sp.z <= tj + TC - 1) && (sp.w >= tj);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    accumulate(kb + b);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MR; ++r)
+#pragma unroll
+            for (int cc = 0; cc < MC; ++cc) {
+                const int i = ib + r, j = jb + cc;
+                if (i < P.R && j < P.C) {
+                    const int pix = i * P.C + j;
+                    if (!last) {
+                        c.sL[pix] = acc[r][cc];
+                    } else {
+                        const T lam = acc[r][cc];
+                        const T d = c.sD ? c.sD[pix] : c.gD[pix];
+                        c.sL[pix] = fma(d, rcp_fast(lam), (T)-1);  // rho = D/Lambda - 1
+                        if (want_V) {
+                            const double ld = (double)lam;
+                            vacc += ld - (double)d * log(ld);
+                        }
+                    }
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- gradients
+template <typename T>
+__device__ void grad_chunk(const Ctx<T>& c, int k0, int nk) {
+    const FieldParams& P = *c.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int kk = warp; kk < nk; kk += nwarps) {
+        const int k = k0 + kk;
+        const double f = c.q[3 * k], x = c.q[3 * k + 1], y = c.q[3 * k + 2];
+        const short4 sp = *reinterpret_cast<const short4*>(c.span + 4 * kk);
+        const int i0 = sp.x, i1 = sp.y, j0 = sp.z, j1 = sp.w;
+        const T* tx = c.tabx + (size_t)kk * P.sx;
+        const T* ty = c.taby + (size_t)kk * P.sy;
+        T gf = 0, gx = 0, gy = 0;
+        for (int jc = j0; jc <= j1; jc += 32) {
+            const int j = jc + lane;
+            const bool ok = j <= j1;
+            const int jj = ok ? j : j1;
+            const T ey = ok ? ty[jj] : (T)0;
+            const T eydy = ey * (T)(((double)jj + 0.5) - y);
+            const T* Lp = c.sL + jj;
+            T c0a = 0, c1a = 0, c0b = 0, c1b = 0;
+            int i = i0;
+            for (; i + 1 <= i1; i += 2) {
+                const T ra = Lp[i * P.C], rb = Lp[(i + 1) * P.C];
+                const T ea = tx[i], eb = tx[i + 1];
+                const T da = ea * (T)(((double)i + 0.5) - x), db = eb * (T)(((double)i + 1.5) - x);
+                c0a = fma(ra, ea, c0a);
+                c1a = fma(ra, da, c1a);
+                c0b = fma(rb, eb, c0b);
+                c1b = fma(rb, db, c1b);
+            }
+            if (i <= i1) {
+                const T ra = Lp[i * P.C];
+                const T ea = tx[i];
+                const T da = ea * (T)(((double)i + 0.5) - x);
+                c0a = fma(ra, ea, c0a);
+                c1a = fma(ra, da, c1a);
+            }
+            const T c0 = c0a + c0b, c1 = c1a + c1b;
+            gf = fma(ey, c0, gf);
+            gx = fma(ey, c1, gx);
+            gy = fma(eydy, c0, gy);
+        }
+        // lanes -> one value; accumulate the final reduction in double for both builds
+        double df = warp_sum((double)gf), dx = warp_sum((double)gx), dy = warp_sum((double)gy);
+        if (lane == 0) {
+            c.g[3 * k] = -df;
+            c.g[3 * k + 1] = -dx * f * P.inv_s2;
+            c.g[3 * k + 2] = -dy * f * P.inv_s2;
+        }
+    }
+}
+
+// Pixel part of V and dV/dq at the current c.q.  Returns sum(Lambda - D ln Lambda) in every thread when want_V.
+template <typename T, int MR, int MC>
+__device__ double eval_pixels(const Ctx<T>& c, bool want_V) {
+    const FieldParams& P = *c.P;
+    const int nchunks = c.N > 0 ? (c.N + P.Kc - 1) / P.Kc : 1;
+    double vacc = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
+        build_tables<T>(c, k0, nk, true);
+        __syncthreads();
+        render_chunk<T, MR, MC>(c, nk, ch == 0, ch == nchunks - 1, want_V, vacc);
+        __syncthreads();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
+        if (nk <= 0) break;
+        build_tables<T>(c, k0, nk, false);
+        __syncthreads();
+        grad_chunk<T>(c, k0, nk);
+        __syncthreads();
+    }
+    if (want_V) {
+        double v[1] = {vacc};
+        block_sum<1>(v, c.red);
+        return v[0];
+    }
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------- per-star scalars
+// dV/dq of star k = pixel part + prior + repulsion (sampler_RHMC.py:404-418)
+template <typename T>
+__device__ __forceinline__ void total_grad(const Ctx<T>& c, int k, double& gf, double& gx, double& gy) {
+    const FieldParams& P = *c.P;
+    gf = c.g[3 * k];
+    gx = c.g[3 * k + 1];
+    gy = c.g[3 * k + 2];
+    if (P.use_prior) gf += P.alpha / c.q[3 * k];
+    if (P.use_Vc) {
+        const double x = c.q[3 * k + 1], y = c.q[3 * k + 2];
+        double sx = 0.0, sy = 0.0;
+        for (int j = 0; j < c.N; ++j) {
+            const double dx = c.q[3 * j + 1] - x, dy = c.q[3 * j + 2] - y;
+            double r = sqrt(dx * dx + dy * dy);
+            if (fabs(r) < 1e-10) r = 1e32;
+            const double ir = 1.0 / r;
+            const double w = (P.vc_int >= 0) ? ipow(ir, P.vc_int + 2) : pow(ir, P.vc_pow + 2.0);
+            sx += w * dx;
+            sy += w * dy;
+        }
+        gx += c.beta * sx * P.vc_pow;
+        gy += c.beta * sy * P.vc_pow;
+    }
+}
+
+// sum_j R_kj^-pow for the repulsion potential (sampler_RHMC.py:340-349)
+template <typename T>
+__device__ __forceinline__ double vc_row(const Ctx<T>& c, int k) {
+    const FieldParams& P = *c.P;
+    const double x = c.q[3 * k + 1], y = c.q[3 * k + 2];
+    double s = 0.0;
+    for (int j = 0; j < c.N; ++j) {
+        const double dx = c.q[3 * j + 1] - x, dy = c.q[3 * j + 2] - y;
+        double r = sqrt(dx * dx + dy * dy);
+        if (fabs(r) < 1e-10) r = 1e32;
+        const double ir = 1.0 / r;
+        s += (P.vc_int >= 0) ? ipow(ir, P.vc_int) : pow(ir, P.vc_pow);
+    }
+    return s;
+}
+
+struct Energies {
+    double V, T;
+};
+
+// V(q, f_pos) and T(p, H(q)) from the cached pixel potential (sampler_RHMC.py:294-363).
+template <typename T>
+__device__ Energies energies(const Ctx<T>& c, double Vpix, int f_pos, bool with_T) {
+    const FieldParams& P = *c.P;
+    double v[5] = {0, 0, 0, 0, 0};  // sum p^2/H, sum ln|H|, prior, repulsion, bad-count
+    for (int k = threadIdx.x; k < c.N; k += blockDim.x) {
+        const double f = c.q[3 * k], x = c.q[3 * k + 1], y = c.q[3 * k + 2];
+        if (with_T) {
+            const Metric m = metric_of(P, f, c.g_ff2);
+            const double pf = c.p[3 * k], px = c.p[3 * k + 1], py = c.p[3 * k + 2];
+            v[0] += pf * pf / m.Hff + px * px / m.Hxx + py * py / m.Hxx;
+            v[1] += log(fabs(m.Hff)) + 2.0 * log(fabs(m.Hxx));
+        }
+        if (P.use_prior) v[2] += P.alpha * log(f) + P.Vpc;
+        if (P.use_Vc) v[3] += vc_row(c, k);
+        bool bad = (f_pos && f < P.f_lim) || (x < -1.0) || (x > P.R + 1.0) || (y < -1.0) || (y > P.C + 1.0);
+        v[4] += bad ? 1.0 : 0.0;
+    }
+    block_sum<5>(v, c.red);
+    Energies e;
+    e.T = (v[0] + v[1]) / 2.0;
+    double V = Vpix;
+    if (P.use_prior) V += v[2];
+    if (P.use_Vc) V += 0.5 * c.beta * v[3];
+    e.V = (v[4] > 0.0) ? CUDART_INF : V;
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------- one leapfrog step
+// base_class.RHMC_single_step (sampler_RHMC.py:522-566).  Requires c.g == pixel gradient at c.q on entry and
+// leaves it so on exit.  All threads of the CTA must call it.
+template <typename T, int MR, int MC>
+__device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool want_V, double& Vpix, int* counts) {
+    const FieldParams& P = *c.P;
+    const double h = c.h;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    // (1) p <- p - h dphi/dq(q); set up the p fixed point: a1 = anchor rho_f, a2 = -H_ff'/H_ff^2
+    for (int k = tid; k < c.N; k += nt) {
+        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        double gf, gx, gy;
+        total_grad(c, k, gf, gx, gy);
+        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        const double pf = c.p[3 * k] - h * gf;
+        c.p[3 * k] = pf;
+        c.p[3 * k + 1] -= h * gx;
+        c.p[3 * k + 2] -= h * gy;
+        c.a1[k] = pf;
+        c.a2[k] = -m.dHff / (m.Hff * m.Hff);
+    }
+    // (2) p' = rho - h dtau/dq(q, p)  until max|p - p'| <= delta   (only flux slots move)
+    int cnt_p = 0;
+    if (P.fp_mode == 0) {
+        while (cnt_p < counter_max) {
+            int more = 0;
+            for (int k = tid; k < c.N; k += nt) {
+                const double pf = c.p[3 * k];
+                const double pn = c.a1[k] - h * (((pf * pf) * c.a2[k]) / 2.0);
+                more |= (fabs(pf - pn) > delta);
+                c.p[3 * k] = pn;
+            }
+            ++cnt_p;
+            if (!__syncthreads_or(more)) break;
+        }
+    } else {
+        for (int k = tid; k < c.N; k += nt) {
+            double pf = c.p[3 * k];
+            int n = 0;
+            while (n < counter_max) {
+                const double pn = c.a1[k] - h * (((pf * pf) * c.a2[k]) / 2.0);
+                const bool more = fabs(pf - pn) > delta;
+                pf = pn;
+                ++n;
+                if (!more) break;
+            }
+            c.p[3 * k] = pf;
+            cnt_p = max(cnt_p, n);
+        }
+    }
+    // (3) q' = sigma + h (p/H(sigma) + p/H(q))  until max|q - q'| <= delta.  a1 = sigma, a2 = p/H(sigma)
+    __syncthreads();  // a1/a2 change meaning (per-star scalars -> per-component vectors)
+    for (int k = tid; k < c.N; k += nt) {
+        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        c.a1[3 * k] = c.q[3 * k];
+        c.a1[3 * k + 1] = c.q[3 * k + 1];
+        c.a1[3 * k + 2] = c.q[3 * k + 2];
+        c.a2[3 * k] = c.p[3 * k] / m.Hff;
+        c.a2[3 * k + 1] = c.p[3 * k + 1] / m.Hxx;
+        c.a2[3 * k + 2] = c.p[3 * k + 2] / m.Hxx;
+    }
+    int cnt_q = 0;
+    auto q_iter = [&](int k, double& qf, double& qx, double& qy) -> bool {
+        const Metric m = metric_of(P, qf, c.g_ff2);
+        const double nf = c.a1[3 * k] + h * (c.a2[3 * k] + c.p[3 * k] / m.Hff);
+        const double nx = c.a1[3 * k + 1] + h * (c.a2[3 * k + 1] + c.p[3 * k + 1] / m.Hxx);
+        const double ny = c.a1[3 * k + 2] + h * (c.a2[3 * k + 2] + c.p[3 * k + 2] / m.Hxx);
+        const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
+        qf = nf;
+        qx = nx;
+        qy = ny;
+        return d > delta;
+    };
+    if (P.fp_mode == 0) {
+        while (cnt_q < counter_max) {
+            int more = 0;
+            for (int k = tid; k < c.N; k += nt) {
+                double qf = c.q[3 * k], qx = c.q[3 * k + 1], qy = c.q[3 * k + 2];
+                more |= q_iter(k, qf, qx, qy);
+                c.q[3 * k] = qf;
+                c.q[3 * k + 1] = qx;
+                c.q[3 * k + 2] = qy;
+            }
+            ++cnt_q;
+            if (!__syncthreads_or(more)) break;
+        }
+    } else {
+        for (int k = tid; k < c.N; k += nt) {
+            double qf = c.q[3 * k], qx = c.q[3 * k + 1], qy = c.q[3 * k + 2];
+            int n = 0;
+            while (n < counter_max) {
+                const bool more = q_iter(k, qf, qx, qy);
+                ++n;
+                if (!more) break;
+            }
+            c.q[3 * k] = qf;
+            c.q[3 * k + 1] = qx;
+            c.q[3 * k + 2] = qy;
+            cnt_q = max(cnt_q, n);
+        }
+    }
+    // (4) p <- p - h dtau/dq(q, p) at the new q
+    for (int k = tid; k < c.N; k += nt) {
+        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        const double pf = c.p[3 * k];
+        c.p[3 * k] = pf - h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+    }
+    __syncthreads();
+    // (5) gradient at the new q, then p <- p - h dphi/dq(q)
+    const double v = eval_pixels<T, MR, MC>(c, want_V);
+    if (want_V) Vpix = v;
+    for (int k = tid; k < c.N; k += nt) {
+        const double f = c.q[3 * k], x = c.q[3 * k + 1], y = c.q[3 * k + 2];
+        const Metric m = metric_of(P, f, c.g_ff2);
+        double gf, gx, gy;
+        total_grad(c, k, gf, gx, gy);
+        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        double pf = c.p[3 * k] - h * gf, px = c.p[3 * k + 1] - h * gx, py = c.p[3 * k + 2] - h * gy;
+        // (6) reflections (sampler_RHMC.py:554-564); positions are not clamped
+        if (f < P.f_lim) pf *= -1.0;
+        if ((x < 0.0) || (x > P.R - 1.0)) px *= -1.0;
+        if ((y < 0.0) || (y > P.C - 1.0)) py *= -1.0;
+        c.p[3 * k] = pf;
+        c.p[3 * k + 1] = px;
+        c.p[3 * k + 2] = py;
+    }
+    __syncthreads();
+    if (counts) {
+        counts[0] = cnt_p;
+        counts[1] = cnt_q;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <typename T, int MR, int MC>
+__global__ void __launch_bounds__(512, 1)
+field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A, double* scratch, int d_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemLayout lay = make_layout<T>(P, d_in_smem != 0);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int S = 3 * P.Nmax;
+
+    for (int field = blockIdx.x; field < A.n_fields; field += gridDim.x) {
+        Ctx<T> c;
+        c.P = &P;
+        c.q = reinterpret_cast<double*>(smem_raw + lay.q);
+        c.p = reinterpret_cast<double*>(smem_raw + lay.p);
+        c.g = reinterpret_cast<double*>(smem_raw + lay.g);
+        c.a1 = reinterpret_cast<double*>(smem_raw + lay.a1);
+        c.a2 = reinterpret_cast<double*>(smem_raw + lay.a2);
+        c.red = reinterpret_cast<double*>(smem_raw + lay.red);
+        c.sD = d_in_smem ? reinterpret_cast<T*>(smem_raw + lay.D) : nullptr;
+        c.sL = reinterpret_cast<T*>(smem_raw + lay.L);
+        c.tabx = reinterpret_cast<T*>(smem_raw + lay.tabx);
+        c.taby = reinterpret_cast<T*>(smem_raw + lay.taby);
+        c.span = reinterpret_cast<short*>(smem_raw + lay.span);
+        c.gD = reinterpret_cast<const T*>(A.D) + (P.D_shared ? 0 : (size_t)field * P.R * P.C);
+        c.N = A.nstars ? A.nstars[field] : P.Nmax;
+        c.g_ff2 = A.g_ff2;
+        c.beta = A.beta;
+        c.h = A.dt / 2.0;
+
+        __syncthreads();  // previous field done with shared memory
+        if (c.sD)
+            for (int i = tid; i < P.R * P.C; i += nt) c.sD[i] = c.gD[i];
+        const double* q_in = A.q_in + (size_t)field * S;
+        for (int i = tid; i < 3 * c.N; i += nt) {
+            c.q[i] = q_in[i];
+            c.p[i] = (A.p_in != nullptr) ? A.p_in[(size_t)field * S + i] : 0.0;
+        }
+        __syncthreads();
+
+        if (A.mode == MODE_EVAL) {
+            const double Vpix = eval_pixels<T, MR, MC>(c, true);
+            const Energies e = energies(c, Vpix, A.f_pos, false);
+            for (int k = tid; k < c.N; k += nt) {
+                double gf, gx, gy;
+                total_grad(c, k, gf, gx, gy);
+                const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+                const size_t o = (size_t)field * S + 3 * k;
+                if (A.grad_out) { A.grad_out[o] = gf; A.grad_out[o + 1] = gx; A.grad_out[o + 2] = gy; }
+                if (A.H_out) { A.H_out[o] = m.Hff; A.H_out[o + 1] = m.Hxx; A.H_out[o + 2] = m.Hxx; }
+                if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
+            }
+            if (tid == 0 && A.V_out) A.V_out[field] = e.V;
+        } else if (A.mode == MODE_STEP) {
+            eval_pixels<T, MR, MC>(c, false);
+            double Vpix = 0.0;
+            int counts[2] = {0, 0};
+            for (int s = 0; s < A.nsteps; ++s) rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, false, Vpix, counts);
+            for (int i = tid; i < 3 * c.N; i += nt) {
+                A.q_out[(size_t)field * S + i] = c.q[i];
+                A.p_out[(size_t)field * S + i] = c.p[i];
+            }
+            if (A.fp_counts) {
+                // parity mode: every thread already holds the field-wide counts; per-star mode: take the CTA max
+                int cp = counts[0], cq = counts[1];
+                if (P.fp_mode != 0) {
+                    for (int o = 16; o > 0; o >>= 1) {
+                        cp = max(cp, __shfl_xor_sync(0xffffffffu, cp, o));
+                        cq = max(cq, __shfl_xor_sync(0xffffffffu, cq, o));
+                    }
+                    __syncthreads();
+                    if ((tid & 31) == 0) {
+                        c.red[tid >> 5] = (double)cp;
+                        c.red[32 + (tid >> 5)] = (double)cq;
+                    }
+                    __syncthreads();
+                    for (int w = 0; w < (nt >> 5); ++w) {
+                        cp = max(cp, (int)c.red[w]);
+                        cq = max(cq, (int)c.red[32 + w]);
+                    }
+                }
+                if (tid == 0) {
+                    A.fp_counts[2 * field] = cp;
+                    A.fp_counts[2 * field + 1] = cq;
+                }
+            }
+        } else if (A.mode == MODE_SINGLE) {
+            // single_gym.run_single_RHMC, solver="implicit" (sampler_RHMC.py:649-783)
+            const size_t rows = (size_t)A.nsteps + 1;
+            double Vpix = eval_pixels<T, MR, MC>(c, true);
+            const Energies e0 = energies(c, Vpix, A.f_pos, true);
+            for (int i = tid; i < 3 * c.N; i += nt) {
+                A.q_chain[((size_t)field * rows) * S + i] = c.q[i];
+                A.p_chain[((size_t)field * rows) * S + i] = c.p[i];
+            }
+            if (tid == 0) {
+                A.E_chain[field * rows] = 0.0;
+                A.V_chain[field * rows] = 0.0;
+                A.T_chain[field * rows] = 0.0;
+            }
+            for (int s = 1; s <= A.nsteps; ++s) {
+                rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, true, Vpix, nullptr);
+                const Energies e = energies(c, Vpix, A.f_pos, true);
+                for (int i = tid; i < 3 * c.N; i += nt) {
+                    A.q_chain[((size_t)field * rows + s) * S + i] = c.q[i];
+                    A.p_chain[((size_t)field * rows + s) * S + i] = c.p[i];
+                }
+                if (tid == 0) {
+                    const double dV = e.V - e0.V, dT = e.T - e0.T;
+                    A.V_chain[field * rows + s] = dV;
+                    A.T_chain[field * rows + s] = dT;
+                    A.E_chain[field * rows + s] = dV + dT;
+                }
+            }
+        } else {  // MODE_RUN: multi_gym.run_RHMC, move 0 (sampler_RHMC.py:1009-1083)
+            double* qs = scratch + (size_t)field * 2 * S;  // q and pixel gradient at the start of the iteration
+            double* gs = qs + S;
+            const size_t rows = (size_t)A.n_rows;
+            const int L = A.niter + 1;
+            double Vpix = eval_pixels<T, MR, MC>(c, true);
+            int n_acc = 0;
+            for (int l = 0; l < L; ++l) {
+                if (A.gff2_sched && l < A.n_gff2) c.g_ff2 = A.gff2_sched[l];
+                if (A.beta_sched && l < A.n_beta) c.beta = A.beta_sched[l];
+                // momentum refresh p = z sqrt(H)  (sampler_RHMC.py:1021-1022)
+                for (int k = tid; k < c.N; k += nt) {
+                    const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+                    double z[3];
+                    if (A.normals) {
+                        const double* zp = A.normals + ((size_t)field * L + l) * S + 3 * k;
+                        z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
+                    } else {
+                        philox_normals3(A.seed, (uint32_t)field, (uint32_t)l, (uint32_t)k, z);
+                    }
+                    c.p[3 * k] = z[0] * sqrt(m.Hff);
+                    c.p[3 * k + 1] = z[1] * sqrt(m.Hxx);
+                    c.p[3 * k + 2] = z[2] * sqrt(m.Hxx);
+                    qs[3 * k] = c.q[3 * k]; qs[3 * k + 1] = c.q[3 * k + 1]; qs[3 * k + 2] = c.q[3 * k + 2];
+                    gs[3 * k] = c.g[3 * k]; gs[3 * k + 1] = c.g[3 * k + 1]; gs[3 * k + 2] = c.g[3 * k + 2];
+                }
+                __syncthreads();
+                const Energies e0 = energies(c, Vpix, A.f_pos, true);
+                const double E0 = e0.V + e0.T;
+                const double Vpix0 = Vpix;
+                const bool keep = (l % A.chain_stride) == 0;
+                const size_t row = (size_t)field * rows + (size_t)(l / A.chain_stride);
+                if (keep) {
+                    if (A.q_chain)
+                        for (int i = tid; i < 3 * c.N; i += nt) A.q_chain[row * S + i] = c.q[i];
+                    if (A.p_chain)
+                        for (int i = tid; i < 3 * c.N; i += nt) A.p_chain[row * S + i] = c.p[i];
+                    if (tid == 0) {
+                        if (A.E_chain) A.E_chain[row] = E0;
+                        if (A.V_chain) A.V_chain[row] = e0.V;
+                        if (A.T_chain) A.T_chain[row] = e0.T;
+                    }
+                }
+                for (int s = 0; s < A.nsteps; ++s)
+                    rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, s == A.nsteps - 1, Vpix, nullptr);
+                const Energies e1 = energies(c, Vpix, A.f_pos, true);
+                const double dE = (e1.V + e1.T) - E0;
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)field, (uint32_t)l);
+                const bool accept = (dE < 0.0) || (lnu < -dE);
+                if (keep && tid == 0 && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
+                if (accept) {
+                    ++n_acc;
+                } else {
+                    __syncthreads();
+                    for (int i = tid; i < 3 * c.N; i += nt) {
+                        c.q[i] = qs[i];
+                        c.g[i] = gs[i];
+                    }
+                    Vpix = Vpix0;
+                }
+                __syncthreads();
+            }
+            if (A.q_out)
+                for (int i = tid; i < 3 * c.N; i += nt) A.q_out[(size_t)field * S + i] = c.q[i];
+            if (tid == 0 && A.accept_rate) A.accept_rate[field] = (double)n_acc / (double)L;
+        }
+    }
+}
+
+// Device normals / log-uniforms exactly as MODE_RUN consumes them (for replay through another implementation).
+__global__ void philox_dump_kernel(unsigned long long seed, int n_fields, int L, int Nmax, double* normals, double* lnu) {
+    const size_t total = (size_t)n_fields * L * Nmax;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % Nmax);
+        const int l = (int)((t / Nmax) % L);
+        const int f = (int)(t / ((size_t)Nmax * L));
+        double z[3];
+        philox_normals3(seed, (uint32_t)f, (uint32_t)l, (uint32_t)k, z);
+        double* o = normals + (((size_t)f * L + l) * Nmax + k) * 3;
+        o[0] = z[0]; o[1] = z[1]; o[2] = z[2];
+        if (k == 0) lnu[(size_t)f * L + l] = philox_lnu(seed, (uint32_t)f, (uint32_t)l);
+    }
+}
+
+template <typename T>
+__global__ void convert_image_kernel(const double* src, T* dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (T)src[i];
+}
+
+}  // namespace srhmc

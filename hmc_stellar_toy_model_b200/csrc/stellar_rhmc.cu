@@ -1,0 +1,616 @@
+// libstellar_rhmc.so -- C ABI (include/stellar_rhmc.h) over the sm_100a RHMC kernels.
+// Host logic only: context / buffer ownership, launch configuration, copies.  No CPU compute path exists.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/stellar_rhmc.h"
+#include "common.cuh"
+#include "field_kernel.cuh"
+#include "chain_kernel.cuh"
+
+using namespace srhmc;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                        \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fail(SRHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) return fail(SRHMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(ptr); }
+};
+
+typedef void (*FieldKernelFn)(const FieldParams, const LaunchArgs, double*, int);
+
+struct KernelChoice {
+    FieldKernelFn fn;
+    int mr, mc;
+};
+
+}  // namespace
+
+struct srhmc_ctx {
+    srhmc_config cfg;
+    FieldParams P;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_data = false, timed = false;
+    int64_t launches = 0;
+    int sm_count = 0;
+    // launch configuration of the CTA-per-field kernel
+    KernelChoice kc{};
+    int threads = 256;
+    size_t smem = 0;
+    int d_in_smem = 1;
+    bool use_chain_kernel = false;  // warp-per-chain one-star kernel
+    size_t pix_bytes = 8;
+    // device buffers
+    DevBuf D, Dstage, q, p, nstars, normals, lnu, sg, sb, qchain, pchain, E, V, T, A, acc, scratch, qout, pout, Vout,
+        grad, H, Hg, counts;
+    // sizes of the last uploaded run
+    int run_L = 0, run_rows = 0;
+    bool run_has_nstars = false, run_has_normals = false, run_has_lnu = false;
+};
+
+namespace {
+
+template <typename T>
+KernelChoice pick_kernel(int R, int C, int nwarps) {
+    auto tiles = [&](int mr, int mc) { return ((R + 8 * mr - 1) / (8 * mr)) * ((C + 4 * mc - 1) / (4 * mc)); };
+    if (tiles(2, 4) >= nwarps) return {field_kernel<T, 2, 4>, 2, 4};
+    if (tiles(2, 2) >= nwarps) return {field_kernel<T, 2, 2>, 2, 2};
+    return {field_kernel<T, 1, 2>, 1, 2};
+}
+
+constexpr size_t kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+template <typename T>
+int configure(srhmc_ctx* c) {
+    const srhmc_config& g = c->cfg;
+    FieldParams& P = c->P;
+    const int R = g.num_rows, C = g.num_cols, N = g.max_stars;
+    int threads = 256;
+    if ((size_t)R * C >= 4096 || N > 256) threads = 512;
+    if ((size_t)R * C <= 256 && N <= 64) threads = 128;
+    c->threads = threads;
+    c->kc = pick_kernel<T>(R, C, threads / 32);
+    P.sx = ((R + 8 * c->kc.mr - 1) / (8 * c->kc.mr)) * 8 * c->kc.mr;
+    P.sy = ((C + 4 * c->kc.mc - 1) / (4 * c->kc.mc)) * 4 * c->kc.mc;
+    const int nwant = std::max(1, N);
+    auto fit = [&](size_t budget, bool dsm) -> int {
+        FieldParams Q = P;
+        Q.Kc = 0;
+        const size_t base = make_layout<T>(Q, dsm).total;
+        const size_t per = (size_t)(P.sx + P.sy) * sizeof(T) + 4 * sizeof(short);
+        if (base + per + 64 > budget) return 0;
+        return (int)std::min<size_t>((size_t)nwant, (budget - base - 64) / per);
+    };
+    int kc = fit(112 * 1024, true);
+    bool dsm = true;
+    if (kc < std::min(nwant, 24)) kc = fit(kSmemMax, true);
+    if (kc < std::min(nwant, 8)) {
+        const int kg = fit(kSmemMax, false);
+        if (kg > kc) {
+            kc = kg;
+            dsm = false;
+        }
+    }
+    if (kc < 1)
+        return fail(SRHMC_ERR_TOO_LARGE, "a %dx%d field with %d stars does not fit the CTA-resident kernel (%zu B shared memory)",
+                    R, C, N, kSmemMax);
+    P.Kc = kc;
+    c->d_in_smem = dsm ? 1 : 0;
+    c->smem = make_layout<T>(P, dsm).total;
+    CU_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    return 0;
+}
+
+int launch_field(srhmc_ctx* c, const LaunchArgs& A) {
+    if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (c->use_chain_kernel) {
+        int rc = c->cfg.precision == 64 ? launch_chain_kernel<double>(c->P, A, c->scratch.as<double>(), c->sm_count, c->stream)
+                                        : launch_chain_kernel<float>(c->P, A, c->scratch.as<double>(), c->sm_count, c->stream);
+        if (rc != 0) return fail(SRHMC_ERR_CUDA, "chain kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    } else {
+        const int grid = std::max(1, A.n_fields);
+        c->kc.fn<<<grid, c->threads, c->smem, c->stream>>>(c->P, A, c->scratch.as<double>(), c->d_in_smem);
+    }
+    CU_TRY(cudaGetLastError());
+    if (c->timed) CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    return 0;
+}
+
+int upload(srhmc_ctx* c, DevBuf& b, const void* src, size_t bytes) {
+    if (int rc = b.ensure(bytes)) return rc;
+    CU_TRY(cudaMemcpyAsync(b.ptr, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int download(srhmc_ctx* c, void* dst, const DevBuf& b, size_t bytes) {
+    CU_TRY(cudaMemcpyAsync(dst, b.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+bool chain_kernel_eligible(const srhmc_config& g) {
+    return false && g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc && !g.shared_data &&
+           g.patch_radius == 0 && g.fixed_point_mode == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srhmc_abi_version(void) { return SRHMC_ABI_VERSION; }
+const char* srhmc_last_error(void) { return g_err; }
+
+int srhmc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void* srhmc_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        fail(SRHMC_ERR_CUDA, "cudaMallocHost(%llu) failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+int srhmc_host_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return 0;
+}
+
+int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
+    if (!cfg || !out) return fail(SRHMC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SRHMC_ABI_VERSION)
+        return fail(SRHMC_ERR_INVALID, "ABI version mismatch: caller %d, library %d", cfg->abi_version, SRHMC_ABI_VERSION);
+    if (cfg->precision != 64 && cfg->precision != 32) return fail(SRHMC_ERR_INVALID, "precision must be 64 or 32");
+    if (cfg->n_fields < 1 || cfg->num_rows < 1 || cfg->num_cols < 1 || cfg->max_stars < 0)
+        return fail(SRHMC_ERR_INVALID, "n_fields, num_rows, num_cols must be >= 1 and max_stars >= 0");
+    if (cfg->num_rows > 16384 || cfg->num_cols > 16384) return fail(SRHMC_ERR_INVALID, "image dimension too large");
+    if (!(cfg->psf_fwhm_pix > 0.0)) return fail(SRHMC_ERR_INVALID, "psf_fwhm_pix must be positive");
+    if (cfg->patch_radius < 0 || cfg->patch_radius > 15)
+        return fail(SRHMC_ERR_INVALID, "patch_radius must be 0 (full image) or 1..15");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRHMC_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SRHMC_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+    CU_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(SRHMC_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    srhmc_ctx* c = new (std::nothrow) srhmc_ctx();
+    if (!c) return fail(SRHMC_ERR_INVALID, "out of host memory");
+    c->cfg = *cfg;
+    c->sm_count = prop.multiProcessorCount;
+    FieldParams& P = c->P;
+    std::memset(&P, 0, sizeof(P));
+    P.R = cfg->num_rows;
+    P.C = cfg->num_cols;
+    P.Nmax = cfg->max_stars;
+    P.rad = cfg->patch_radius;
+    P.fp_mode = cfg->fixed_point_mode;
+    P.D_shared = cfg->shared_data ? 1 : 0;
+    P.use_prior = cfg->use_prior ? 1 : 0;
+    P.use_Vc = cfg->use_Vc ? 1 : 0;
+    const double sigma = cfg->psf_fwhm_pix / 2.354;  // utils.py:480
+    P.inv2s2 = 1.0 / (2.0 * sigma * sigma);
+    P.inv_s2 = 1.0 / (sigma * sigma);
+    P.norm = 1.0 / (M_PI * 2.0 * sigma * sigma);
+    P.c2 = std::exp(-1.0 / (sigma * sigma));
+    P.B = cfg->B_count;
+    P.f_lim = cfg->f_lim;
+    P.f_low = cfg->f_low;
+    P.g0 = cfg->g0; P.g1 = cfg->g1; P.g2 = cfg->g2;
+    P.g_xx = cfg->g_xx; P.g_ff = cfg->g_ff;
+    P.alpha = cfg->alpha;
+    P.Vpc = cfg->V_prior_const;
+    P.vc_pow = cfg->Vc_r_pow;
+    const double rp = std::floor(cfg->Vc_r_pow);
+    P.vc_int = (rp == cfg->Vc_r_pow && rp >= 0.0 && rp <= 32.0) ? (int)rp : -1;
+    c->pix_bytes = cfg->precision == 64 ? 8 : 4;
+
+    int rc = 0;
+    c->use_chain_kernel = chain_kernel_eligible(*cfg);
+    if (c->use_chain_kernel) {
+        rc = cfg->precision == 64 ? configure_chain_kernel<double>(P) : configure_chain_kernel<float>(P);
+        if (rc != 0) rc = fail(SRHMC_ERR_CUDA, "chain kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
+    } else {
+        rc = cfg->precision == 64 ? configure<double>(c) : configure<float>(c);
+    }
+    if (rc != 0) {
+        delete c;
+        return rc;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(SRHMC_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    c->timed = true;
+    *out = c;
+    return 0;
+}
+
+int srhmc_destroy(srhmc_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = {&c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
+                     &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout,
+                     &c->grad, &c->H, &c->Hg, &c->counts};
+    for (DevBuf* b : all) b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int srhmc_set_stream(srhmc_ctx* c, void* s) {
+    if (!c) return fail(SRHMC_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+    return 0;
+}
+
+int srhmc_synchronize(srhmc_ctx* c) {
+    if (!c) return fail(SRHMC_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_last_kernel_ms(srhmc_ctx* c, float* ms) {
+    if (!c || !ms) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (c->launches == 0) return fail(SRHMC_ERR_STATE, "no kernel launched yet");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaEventSynchronize(c->ev1));
+    CU_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+int64_t srhmc_launch_count(srhmc_ctx* c) { return c ? c->launches : 0; }
+
+int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
+    if (!c || !D) return fail(SRHMC_ERR_INVALID, "null argument");
+    const int64_t want = c->cfg.shared_data ? 1 : c->cfg.n_fields;
+    if (n_images != want) return fail(SRHMC_ERR_INVALID, "expected %lld image(s), got %lld", (long long)want, (long long)n_images);
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)n_images * c->P.R * c->P.C;
+    if (c->cfg.precision == 64) {
+        if (int rc = upload(c, c->D, D, n * 8)) return rc;
+    } else {
+        if (int rc = upload(c, c->Dstage, D, n * 8)) return rc;
+        if (int rc = c->D.ensure(n * 4)) return rc;
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+        convert_image_kernel<float><<<blocks, 256, 0, c->stream>>>(c->Dstage.as<double>(), c->D.as<float>(), n);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->have_data = true;
+    return 0;
+}
+
+static int upload_nstars(srhmc_ctx* c, const int32_t* nstars) {
+    if (!nstars) return 0;
+    for (int f = 0; f < c->cfg.n_fields; ++f)
+        if (nstars[f] < 0 || nstars[f] > c->cfg.max_stars)
+            return fail(SRHMC_ERR_INVALID, "nstars[%d] = %d outside [0, %d]", f, nstars[f], c->cfg.max_stars);
+    return upload(c, c->nstars, nstars, (size_t)c->cfg.n_fields * sizeof(int32_t));
+}
+
+int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_pos, double g_ff2, double beta,
+               double* V, double* grad, double* H, double* Hgrad) {
+    if (!c || !q) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = F * S * 8;
+    if (int rc = upload(c, c->q, q, std::max<size_t>(FS, 8))) return rc;
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    if (int rc = c->Vout.ensure(F * 8)) return rc;
+    if (int rc = c->grad.ensure(std::max<size_t>(FS, 8))) return rc;
+    if (int rc = c->H.ensure(std::max<size_t>(FS, 8))) return rc;
+    if (int rc = c->Hg.ensure(std::max<size_t>(FS, 8))) return rc;
+    if (int rc = c->scratch.ensure(std::max<size_t>(2 * FS, 8))) return rc;
+    LaunchArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.mode = MODE_EVAL;
+    A.n_fields = (int)F;
+    A.D = c->D.ptr;
+    A.nstars = nstars ? c->nstars.as<int>() : nullptr;
+    A.q_in = c->q.as<double>();
+    A.f_pos = f_pos;
+    A.g_ff2 = g_ff2;
+    A.beta = beta;
+    A.chain_stride = 1;
+    A.V_out = c->Vout.as<double>();
+    A.grad_out = c->grad.as<double>();
+    A.H_out = c->H.as<double>();
+    A.Hgrad_out = c->Hg.as<double>();
+    CU_TRY(cudaMemsetAsync(c->grad.ptr, 0, std::max<size_t>(FS, 8), c->stream));
+    CU_TRY(cudaMemsetAsync(c->H.ptr, 0, std::max<size_t>(FS, 8), c->stream));
+    CU_TRY(cudaMemsetAsync(c->Hg.ptr, 0, std::max<size_t>(FS, 8), c->stream));
+    if (int rc = launch_field(c, A)) return rc;
+    if (V) if (int rc = download(c, V, c->Vout, F * 8)) return rc;
+    if (grad && FS) if (int rc = download(c, grad, c->grad, FS)) return rc;
+    if (H && FS) if (int rc = download(c, H, c->H, FS)) return rc;
+    if (Hgrad && FS) if (int rc = download(c, Hgrad, c->Hg, FS)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_step(srhmc_ctx* c, double* q, double* p, const int32_t* nstars, int32_t nsteps, double dt, double delta,
+               int32_t counter_max, double g_ff2, double beta, int32_t* fp_counts) {
+    if (!c || !q || !p) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    if (nsteps < 0 || counter_max < 0) return fail(SRHMC_ERR_INVALID, "nsteps and counter_max must be >= 0");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = std::max<size_t>(F * S * 8, 8);
+    if (int rc = upload(c, c->q, q, FS)) return rc;
+    if (int rc = upload(c, c->p, p, FS)) return rc;
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    if (int rc = c->qout.ensure(FS)) return rc;
+    if (int rc = c->pout.ensure(FS)) return rc;
+    if (int rc = c->counts.ensure(F * 2 * sizeof(int))) return rc;
+    if (int rc = c->scratch.ensure(2 * FS)) return rc;
+    CU_TRY(cudaMemcpyAsync(c->qout.ptr, c->q.ptr, FS, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->pout.ptr, c->p.ptr, FS, cudaMemcpyDeviceToDevice, c->stream));
+    LaunchArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.mode = MODE_STEP;
+    A.n_fields = (int)F;
+    A.D = c->D.ptr;
+    A.nstars = nstars ? c->nstars.as<int>() : nullptr;
+    A.q_in = c->q.as<double>();
+    A.p_in = c->p.as<double>();
+    A.q_out = c->qout.as<double>();
+    A.p_out = c->pout.as<double>();
+    A.nsteps = nsteps;
+    A.dt = dt;
+    A.delta = delta;
+    A.counter_max = counter_max;
+    A.g_ff2 = g_ff2;
+    A.beta = beta;
+    A.chain_stride = 1;
+    A.fp_counts = c->counts.as<int>();
+    if (int rc = launch_field(c, A)) return rc;
+    if (F * S) {
+        if (int rc = download(c, q, c->qout, F * S * 8)) return rc;
+        if (int rc = download(c, p, c->pout, F * S * 8)) return rc;
+    }
+    if (fp_counts) if (int rc = download(c, fp_counts, c->counts, F * 2 * sizeof(int))) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int check_run_args(srhmc_ctx* c, const srhmc_run_args* a) {
+    if (!c || !a) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    if (a->niter < 0 || a->nsteps < 0 || a->counter_max < 0) return fail(SRHMC_ERR_INVALID, "niter, nsteps, counter_max must be >= 0");
+    if (a->chain_stride < 1) return fail(SRHMC_ERR_INVALID, "chain_stride must be >= 1");
+    if ((a->g_ff2_schedule && a->n_g_ff2 < 0) || (a->beta_schedule && a->n_beta < 0)) return fail(SRHMC_ERR_INVALID, "negative schedule length");
+    return 0;
+}
+
+int srhmc_run_upload(srhmc_ctx* c, const srhmc_run_args* a) {
+    if (int rc = check_run_args(c, a)) return rc;
+    if (!a->q0) return fail(SRHMC_ERR_INVALID, "q0 is null");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, L = (size_t)a->niter + 1;
+    const size_t FS = std::max<size_t>(F * S * 8, 8);
+    if (int rc = upload(c, c->q, a->q0, FS)) return rc;
+    if (int rc = upload_nstars(c, a->nstars)) return rc;
+    c->run_has_nstars = a->nstars != nullptr;
+    c->run_has_normals = a->normals != nullptr;
+    c->run_has_lnu = a->lnu != nullptr;
+    if (a->normals) if (int rc = upload(c, c->normals, a->normals, std::max<size_t>(F * L * S * 8, 8))) return rc;
+    if (a->lnu) if (int rc = upload(c, c->lnu, a->lnu, F * L * 8)) return rc;
+    if (a->g_ff2_schedule && a->n_g_ff2 > 0) if (int rc = upload(c, c->sg, a->g_ff2_schedule, (size_t)a->n_g_ff2 * 8)) return rc;
+    if (a->beta_schedule && a->n_beta > 0) if (int rc = upload(c, c->sb, a->beta_schedule, (size_t)a->n_beta * 8)) return rc;
+    c->run_L = (int)L;
+    return 0;
+}
+
+int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
+    if (int rc = check_run_args(c, a)) return rc;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, L = (size_t)a->niter + 1;
+    if ((int)L != c->run_L) return fail(SRHMC_ERR_STATE, "srhmc_run_launch: niter differs from the uploaded run");
+    const size_t rows = (L + a->chain_stride - 1) / a->chain_stride;
+    c->run_rows = (int)rows;
+    const size_t FS = std::max<size_t>(F * S * 8, 8);
+    if (a->q_chain) if (int rc = c->qchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
+    if (a->p_chain) if (int rc = c->pchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
+    if (a->E_chain) if (int rc = c->E.ensure(F * rows * 8)) return rc;
+    if (a->V_chain) if (int rc = c->V.ensure(F * rows * 8)) return rc;
+    if (a->T_chain) if (int rc = c->T.ensure(F * rows * 8)) return rc;
+    if (a->A_chain) if (int rc = c->A.ensure(F * rows)) return rc;
+    if (int rc = c->acc.ensure(F * 8)) return rc;
+    if (int rc = c->qout.ensure(FS)) return rc;
+    if (int rc = c->scratch.ensure(2 * FS)) return rc;
+    // unused star slots of the chains read back as zeros, like the reference's np.zeros allocation
+    if (a->q_chain && c->cfg.max_stars > 0 && c->run_has_nstars) CU_TRY(cudaMemsetAsync(c->qchain.ptr, 0, F * rows * S * 8, c->stream));
+    if (a->p_chain && c->cfg.max_stars > 0 && c->run_has_nstars) CU_TRY(cudaMemsetAsync(c->pchain.ptr, 0, F * rows * S * 8, c->stream));
+    if (c->run_has_nstars) CU_TRY(cudaMemsetAsync(c->qout.ptr, 0, FS, c->stream));
+    LaunchArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.mode = MODE_RUN;
+    A.n_fields = (int)F;
+    A.D = c->D.ptr;
+    A.nstars = c->run_has_nstars ? c->nstars.as<int>() : nullptr;
+    A.q_in = c->q.as<double>();
+    A.q_out = c->qout.as<double>();
+    A.niter = a->niter;
+    A.nsteps = a->nsteps;
+    A.counter_max = a->counter_max;
+    A.f_pos = a->f_pos;
+    A.dt = a->dt;
+    A.delta = a->delta;
+    A.g_ff2 = a->g_ff2;
+    A.beta = a->beta;
+    A.gff2_sched = (a->g_ff2_schedule && a->n_g_ff2 > 0) ? c->sg.as<double>() : nullptr;
+    A.n_gff2 = a->n_g_ff2;
+    A.beta_sched = (a->beta_schedule && a->n_beta > 0) ? c->sb.as<double>() : nullptr;
+    A.n_beta = a->n_beta;
+    A.normals = c->run_has_normals ? c->normals.as<double>() : nullptr;
+    A.lnu = c->run_has_lnu ? c->lnu.as<double>() : nullptr;
+    A.seed = a->seed;
+    A.chain_stride = a->chain_stride;
+    A.n_rows = (int)rows;
+    A.q_chain = a->q_chain ? c->qchain.as<double>() : nullptr;
+    A.p_chain = a->p_chain ? c->pchain.as<double>() : nullptr;
+    A.E_chain = a->E_chain ? c->E.as<double>() : nullptr;
+    A.V_chain = a->V_chain ? c->V.as<double>() : nullptr;
+    A.T_chain = a->T_chain ? c->T.as<double>() : nullptr;
+    A.A_chain = a->A_chain ? c->A.as<unsigned char>() : nullptr;
+    A.accept_rate = c->acc.as<double>();
+    return launch_field(c, A);
+}
+
+int srhmc_run_download(srhmc_ctx* c, const srhmc_run_args* a) {
+    if (int rc = check_run_args(c, a)) return rc;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, rows = (size_t)c->run_rows;
+    if (rows == 0) return fail(SRHMC_ERR_STATE, "srhmc_run_download before srhmc_run_launch");
+    if (a->q_chain && S) if (int rc = download(c, a->q_chain, c->qchain, F * rows * S * 8)) return rc;
+    if (a->p_chain && S) if (int rc = download(c, a->p_chain, c->pchain, F * rows * S * 8)) return rc;
+    if (a->E_chain) if (int rc = download(c, a->E_chain, c->E, F * rows * 8)) return rc;
+    if (a->V_chain) if (int rc = download(c, a->V_chain, c->V, F * rows * 8)) return rc;
+    if (a->T_chain) if (int rc = download(c, a->T_chain, c->T, F * rows * 8)) return rc;
+    if (a->A_chain) if (int rc = download(c, a->A_chain, c->A, F * rows)) return rc;
+    if (a->q_final && S) if (int rc = download(c, a->q_final, c->qout, F * S * 8)) return rc;
+    if (a->accept_rate) if (int rc = download(c, a->accept_rate, c->acc, F * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_run(srhmc_ctx* c, const srhmc_run_args* a) {
+    if (int rc = srhmc_run_upload(c, a)) return rc;
+    if (int rc = srhmc_run_launch(c, a)) return rc;
+    return srhmc_run_download(c, a);
+}
+
+int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int32_t* nstars, int32_t nsteps, double dt,
+                     double delta, int32_t counter_max, int32_t f_pos, double g_ff2, double beta, double* q_chain,
+                     double* p_chain, double* E_chain, double* V_chain, double* T_chain) {
+    if (!c || !q0 || !p0) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    if (nsteps < 0 || counter_max < 0) return fail(SRHMC_ERR_INVALID, "nsteps and counter_max must be >= 0");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, rows = (size_t)nsteps + 1;
+    const size_t FS = std::max<size_t>(F * S * 8, 8);
+    if (int rc = upload(c, c->q, q0, FS)) return rc;
+    if (int rc = upload(c, c->p, p0, FS)) return rc;
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    if (int rc = c->qchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
+    if (int rc = c->pchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
+    if (int rc = c->E.ensure(F * rows * 8)) return rc;
+    if (int rc = c->V.ensure(F * rows * 8)) return rc;
+    if (int rc = c->T.ensure(F * rows * 8)) return rc;
+    if (int rc = c->scratch.ensure(2 * FS)) return rc;
+    if (S) {
+        CU_TRY(cudaMemsetAsync(c->qchain.ptr, 0, F * rows * S * 8, c->stream));
+        CU_TRY(cudaMemsetAsync(c->pchain.ptr, 0, F * rows * S * 8, c->stream));
+    }
+    LaunchArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.mode = MODE_SINGLE;
+    A.n_fields = (int)F;
+    A.D = c->D.ptr;
+    A.nstars = nstars ? c->nstars.as<int>() : nullptr;
+    A.q_in = c->q.as<double>();
+    A.p_in = c->p.as<double>();
+    A.nsteps = nsteps;
+    A.counter_max = counter_max;
+    A.f_pos = f_pos;
+    A.dt = dt;
+    A.delta = delta;
+    A.g_ff2 = g_ff2;
+    A.beta = beta;
+    A.chain_stride = 1;
+    A.n_rows = (int)rows;
+    A.q_chain = c->qchain.as<double>();
+    A.p_chain = c->pchain.as<double>();
+    A.E_chain = c->E.as<double>();
+    A.V_chain = c->V.as<double>();
+    A.T_chain = c->T.as<double>();
+    if (int rc = launch_field(c, A)) return rc;
+    if (q_chain && S) if (int rc = download(c, q_chain, c->qchain, F * rows * S * 8)) return rc;
+    if (p_chain && S) if (int rc = download(c, p_chain, c->pchain, F * rows * S * 8)) return rc;
+    if (E_chain) if (int rc = download(c, E_chain, c->E, F * rows * 8)) return rc;
+    if (V_chain) if (int rc = download(c, V_chain, c->V, F * rows * 8)) return rc;
+    if (T_chain) if (int rc = download(c, T_chain, c->T, F * rows * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* normals, double* lnu) {
+    if (!c || !normals || !lnu || niter < 0) return fail(SRHMC_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, N = (size_t)c->cfg.max_stars, L = (size_t)niter + 1;
+    if (N == 0) return fail(SRHMC_ERR_INVALID, "max_stars is 0");
+    if (int rc = c->normals.ensure(F * L * N * 3 * 8)) return rc;
+    if (int rc = c->lnu.ensure(F * L * 8)) return rc;
+    const int blocks = (int)std::min<size_t>((F * L * N + 255) / 256, 8192);
+    philox_dump_kernel<<<blocks, 256, 0, c->stream>>>(seed, (int)F, (int)L, (int)N, c->normals.as<double>(), c->lnu.as<double>());
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    if (int rc = download(c, normals, c->normals, F * L * N * 3 * 8)) return rc;
+    if (int rc = download(c, lnu, c->lnu, F * L * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->run_has_normals = false;  // the staging buffers were overwritten
+    c->run_has_lnu = false;
+    return 0;
+}
+
+}  // extern "C"

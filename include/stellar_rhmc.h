@@ -1,0 +1,165 @@
+/*
+ * stellar_rhmc.h  --  C ABI of libstellar_rhmc.so: the B200-native (sm_100a) RHMC leapfrog hot path of the
+ * stellar toy model.
+ *
+ * The reference (jaekor91/HMC-stellar-toy-model) has no FFI of its own: its seam is the Python method surface of
+ * the gym classes.  Each entry point below replaces the reference methods named in its comment (file:line into the
+ * reference checkout); hmc_stellar_toy_model_b200/_capi.py is the ctypes binding and INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative srhmc_status; nothing throws or aborts across the ABI;
+ *     srhmc_last_error() returns a thread-local, human-readable message for the last failure.
+ *   - the caller owns every host pointer; the library copies in/out and owns all device memory inside the context.
+ *   - a context is bound to one CUDA device and one stream and is NOT thread-safe (one context per host thread;
+ *     ctypes releases the GIL so N contexts drive N GPUs from N threads).
+ *   - star state: q and p are float64, flat [f, x, y] per star with f in counts, x along image rows (axis 0);
+ *     per field they occupy 3*max_stars slots, of which the first 3*nstars[field] are live.
+ *   - images are float64 [rows, cols] C-order on the host whatever the device precision.
+ *   - there is no CPU fallback: every entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef STELLAR_RHMC_H
+#define STELLAR_RHMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRHMC_ABI_VERSION 1
+
+typedef enum srhmc_status {
+    SRHMC_OK = 0,
+    SRHMC_ERR_INVALID = -1,   /* bad argument */
+    SRHMC_ERR_CUDA = -2,      /* CUDA runtime error (message in srhmc_last_error) */
+    SRHMC_ERR_NO_DEVICE = -3, /* no usable sm_100 device */
+    SRHMC_ERR_TOO_LARGE = -4, /* field does not fit the resident kernel's shared memory */
+    SRHMC_ERR_STATE = -5      /* call order (e.g. run before set_data) */
+} srhmc_status;
+
+typedef struct srhmc_ctx srhmc_ctx;
+
+/* Snapshot of the gym attributes the path reads at call time (SURVEY.md 8b "state read at call time").
+ * Reference: base_class.__init__/default_exp_setup, sampler_RHMC.py:28-75,169-201. */
+typedef struct srhmc_config {
+    int32_t abi_version;     /* SRHMC_ABI_VERSION */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t precision;       /* 64: float64 pixels (parity build); 32: float32 pixels, float64 star state */
+    int32_t n_fields;        /* independent fields / chains held by this context */
+    int32_t num_rows;        /* gym.num_rows */
+    int32_t num_cols;        /* gym.num_cols */
+    int32_t max_stars;       /* N_max: star slots per field */
+    int32_t patch_radius;    /* 0: full-image PSF (reference semantics); r>0: PSF truncated to (2r+1)^2 pixels */
+    int32_t shared_data;     /* 1: one data image shared by all fields (many chains on the same D) */
+    int32_t fixed_point_mode;/* 0: reference stop rule (max over the whole field); 1: per-star early exit */
+    int32_t use_prior;       /* gym.use_prior */
+    int32_t use_Vc;          /* gym.use_Vc */
+    double psf_fwhm_pix;     /* gym.PSF_FWHM_pix; sigma = fwhm/2.354 (utils.py:480) */
+    double B_count;          /* gym.B_count */
+    double f_lim;            /* gym.f_lim */
+    double f_low;            /* mag2flux_converter(mB+2): clamp of H_xx (sampler_RHMC.py:267) */
+    double g0, g1, g2;       /* utils.factors constants (frozen at 48x48 by the reference) */
+    double g_xx, g_ff;       /* metric scale factors */
+    double alpha;            /* prior exponent (sampler_RHMC.py:326,409) */
+    double V_prior_const;    /* gym.V_prior_const (sampler_RHMC.py:320-321) */
+    double Vc_r_pow;         /* repulsion exponent (sampler_RHMC.py:349,417) */
+} srhmc_config;
+
+/* Arguments of one resident chain run.  Replaces the move-0 leg of multi_gym.run_RHMC
+ * (sampler_RHMC.py:1009-1083): all (niter+1) x nsteps leapfrog steps, the momentum refresh, the energies and the
+ * Metropolis test execute inside ONE kernel launch with no host round trip.
+ * Array shapes (F = n_fields, S = 3*max_stars, L = niter+1):
+ *   q0 [F,S]; nstars [F] or NULL (= max_stars everywhere);
+ *   normals [F,L,S] standard-normal draws replacing np.random.randn (NULL -> device Philox4x32-10, `seed`);
+ *   lnu [F,L] log-uniform draws replacing log(np.random.random(1)) (NULL -> device Philox);
+ *   g_ff2_schedule [n_g_ff2] / beta_schedule [n_beta] or NULL (sampler_RHMC.py:1011-1016);
+ *   outputs (any may be NULL): q_chain, p_chain [F,Ls,S]; E_chain, V_chain, T_chain [F,Ls]; A_chain [F,Ls] uint8
+ *   where Ls = ceil(L / chain_stride) rows are kept (row r = iteration r*chain_stride; stride 1 = reference). */
+typedef struct srhmc_run_args {
+    const double* q0;
+    const int32_t* nstars;
+    int32_t niter;
+    int32_t nsteps;
+    double dt;
+    double delta;
+    int32_t counter_max;
+    int32_t f_pos;
+    double g_ff2;
+    double beta;
+    const double* g_ff2_schedule;
+    int32_t n_g_ff2;
+    const double* beta_schedule;
+    int32_t n_beta;
+    const double* normals;
+    const double* lnu;
+    uint64_t seed;
+    int32_t chain_stride;
+    int32_t reserved;
+    double* q_chain;
+    double* p_chain;
+    double* E_chain;
+    double* V_chain;
+    double* T_chain;
+    uint8_t* A_chain;
+    double* q_final;       /* [F,S] state after the last iteration (accepted or restored), may be NULL */
+    double* accept_rate;   /* [F] fraction of accepted iterations, may be NULL */
+} srhmc_run_args;
+
+int srhmc_abi_version(void);
+const char* srhmc_last_error(void);
+int srhmc_device_count(void);
+
+int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out);
+int srhmc_destroy(srhmc_ctx* ctx);
+
+/* Adopt an external CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores the context's own. */
+int srhmc_set_stream(srhmc_ctx* ctx, void* cuda_stream);
+int srhmc_synchronize(srhmc_ctx* ctx);
+/* Device time (ms, CUDA events on the launching stream) of the most recent kernel launch of this context. */
+int srhmc_last_kernel_ms(srhmc_ctx* ctx, float* ms);
+/* Number of kernels this context has launched since creation. */
+int64_t srhmc_launch_count(srhmc_ctx* ctx);
+
+/* Pinned host memory helpers for callers that want asynchronous copies. */
+void* srhmc_host_alloc(uint64_t bytes);
+int srhmc_host_free(void* p);
+
+/* gym.D: n_images = n_fields, or 1 when cfg.shared_data. */
+int srhmc_set_data(srhmc_ctx* ctx, const double* D, int64_t n_images);
+
+/* One evaluation per field.  Replaces base_class.V (sampler_RHMC.py:294-351), dVdq (:365-425), H with grad
+ * (:229-292) and, composed by the caller, dphidq/dtaudq/dtaudp (:448-492); also lightsource_gym.V/dVdq
+ * (samplers.py:1108-1150) with use_prior = use_Vc = 0.
+ * q [F,S]; outputs (any may be NULL): V [F] (inf outside the support when f_pos / bounds apply),
+ * grad [F,S] = dV/dq incl. prior and repulsion, H [F,S], Hgrad [F,S]. */
+int srhmc_eval(srhmc_ctx* ctx, const double* q, const int32_t* nstars, int32_t f_pos, double g_ff2, double beta,
+               double* V, double* grad, double* H, double* Hgrad);
+
+/* nsteps generalised-leapfrog steps in place.  Replaces base_class.RHMC_single_step (sampler_RHMC.py:522-566).
+ * fp_counts, if not NULL, receives [F,2]: the two fixed-point iteration counts of the LAST step. */
+int srhmc_step(srhmc_ctx* ctx, double* q, double* p, const int32_t* nstars, int32_t nsteps, double dt,
+               double delta, int32_t counter_max, double g_ff2, double beta, int32_t* fp_counts);
+
+/* Full chain (see srhmc_run_args).  srhmc_run = upload + launch + download + synchronize.  The three phases are
+ * also exported so a caller can keep inputs resident and time the launch alone. */
+int srhmc_run(srhmc_ctx* ctx, const srhmc_run_args* args);
+int srhmc_run_upload(srhmc_ctx* ctx, const srhmc_run_args* args);
+int srhmc_run_launch(srhmc_ctx* ctx, const srhmc_run_args* args);
+int srhmc_run_download(srhmc_ctx* ctx, const srhmc_run_args* args);
+
+/* One long trajectory per field recording V-V0, T-T0 and their sum after every step.  Replaces
+ * single_gym.run_single_RHMC(solver="implicit") (sampler_RHMC.py:649-783).
+ * q0, p0 [F,S]; q_chain, p_chain [F,nsteps+1,S]; E_chain, V_chain, T_chain [F,nsteps+1] (row 0: q0,p0, zeros). */
+int srhmc_run_single(srhmc_ctx* ctx, const double* q0, const double* p0, const int32_t* nstars, int32_t nsteps,
+                     double dt, double delta, int32_t counter_max, int32_t f_pos, double g_ff2, double beta,
+                     double* q_chain, double* p_chain, double* E_chain, double* V_chain, double* T_chain);
+
+/* Draws of the device generator, for replaying a Philox run through another implementation:
+ * normals [F,L,S], lnu [F,L] exactly as srhmc_run would consume them for `seed`. */
+int srhmc_philox_draws(srhmc_ctx* ctx, uint64_t seed, int32_t niter, double* normals, double* lnu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STELLAR_RHMC_H */
