@@ -96,20 +96,38 @@ def test_run_rhmc_one_star_chain(name):
 
 @pytest.mark.parametrize("name", ["chain_multi30_vc", "chain_multi100"])
 def test_run_rhmc_crowded_chain(name):
+    """Crowded field with prior, repulsion and both schedules (RHMC-big-sim2/3.py).
+
+    The 30-star repulsive system is chaotic: a ONE-ulp perturbation of two inputs of the NumPy oracle grows by
+    ~1e3 per accepted trajectory (2e-16 -> 2e-13 -> 5e-10 over this fixture; scripts/dbg_chain.py).  So the
+    whole-chain comparison checks the accept decisions exactly and the energies to 1e-9, bounds the state error
+    loosely, and the 1e-10-class check is done per trajectory, restarting every iteration from the reference's
+    own recorded (q, p)."""
     g = golden(name)
     S = setup_from(g)
     q0 = so.format_q(S, g["q_model"])
     n = q0.size // 3
-    niter = int(g["niter"])
+    niter, nsteps, dt = int(g["niter"]), int(g["nsteps"]), float(g["dt"])
     with make_ctx(S, max_stars=n) as ctx:
         ctx.set_data(S.D)
-        r = ctx.run(q0[None], niter, int(g["nsteps"]), float(g["dt"]), normals=g["normals"][None], lnu=g["lnu"][None],
+        r = ctx.run(q0[None], niter, nsteps, dt, normals=g["normals"][None], lnu=g["lnu"][None],
                     g_ff2=S.g_ff2, beta=S.beta, f_pos=True, schedule_g_ff2=g["schedule_g_ff2"],
                     schedule_beta=g["schedule_beta"])
-    assert np.array_equal(r.A_chain[0].astype(bool), g["A_chain"])
-    assert first_divergence(r.q_chain[0], g["q_chain"][:, : 3 * n], 1e-8) == -1
-    assert relerr(r.E_chain[0], g["E_chain"]) < RTOL
-    assert relerr(r.V_chain[0], g["V_chain"]) < RTOL
+        assert np.array_equal(r.A_chain[0].astype(bool), g["A_chain"])
+        assert first_divergence(r.q_chain[0], g["q_chain"][:, : 3 * n], 1e-6) == -1
+        first_accept = int(np.argmax(g["A_chain"])) + 1
+        assert first_divergence(r.q_chain[0][: first_accept + 1], g["q_chain"][: first_accept + 1, : 3 * n], RTOL) == -1
+        assert relerr(r.E_chain[0], g["E_chain"]) < 1e-9
+        assert relerr(r.V_chain[0], g["V_chain"]) < 1e-9
+        # per-trajectory restart parity from the reference's recorded states
+        for l in range(0, niter + 1, 3):
+            Sl = S.clone(dt=dt, g_ff2=float(g["schedule_g_ff2"][l]), beta=float(g["schedule_beta"][l]))
+            q, p = g["q_chain"][l, : 3 * n].copy(), g["p_chain"][l, : 3 * n].copy()
+            qg, pg = ctx.step(q[None], p[None], nsteps, dt, g_ff2=Sl.g_ff2, beta=Sl.beta)
+            for _ in range(nsteps):
+                q, p = so.rhmc_step(Sl, q, p)
+            assert relerr(qg[0], q) < 1e-9, l
+            assert grad_relerr(pg[0], p) < 1e-7, l
 
 
 def test_run_single_rhmc():
