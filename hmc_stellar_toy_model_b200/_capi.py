@@ -117,7 +117,17 @@ SIGNATURES = {
                                    C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_philox_draws": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, c_double_p, c_double_p]),
+    "srhmc_measure_fma_peak": (C.c_int, [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_float)]),
 }
+
+
+def measure_fma_peak(device=0, precision=64):
+    """(TFLOP/s, ms) of the register-resident FMA-chain microbenchmark on `device`."""
+    lib = load_library()
+    tf = C.c_double()
+    ms = C.c_float()
+    check(lib.srhmc_measure_fma_peak(int(device), int(precision), C.byref(tf), C.byref(ms)))
+    return float(tf.value), float(ms.value)
 
 _lib = None
 

@@ -171,6 +171,10 @@ class RHMCContext:
         check(self._lib.srhmc_run(self._h, C.byref(a)))
         return self._result(keep)
 
+    def run_prepared(self, a):
+        """srhmc_run on an argument block from make_run_args (upload + launch + download + synchronize)."""
+        check(self._lib.srhmc_run(self._h, C.byref(a)))
+
     # split phases, for callers that keep inputs resident (bench.py `value`)
     def run_upload(self, a):
         check(self._lib.srhmc_run_upload(self._h, C.byref(a)))

@@ -17,6 +17,22 @@
 
 using namespace srhmc;
 
+namespace srhmc {
+// FMA-chain microbenchmark: 8 independent dependent chains per thread, ITERS iterations.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace srhmc
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -173,6 +189,34 @@ int download(srhmc_ctx* c, void* dst, const DevBuf& b, size_t bytes) {
 bool chain_kernel_eligible(const srhmc_config& g) {
     return false && g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc && !g.shared_data &&
            g.patch_radius == 0 && g.fixed_point_mode == 0;
+}
+
+template <typename T>
+int run_fma_peak(int sms, double* tflops, float* ms) {
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    T* out = nullptr;
+    CU_TRY(cudaMalloc(&out, (size_t)blocks * threads * sizeof(T)));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(e0, 0));
+        fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)0.999, (T)0.001);
+        CU_TRY(cudaEventRecord(e1, 0));
+        CU_TRY(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CU_TRY(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < best) best = t;
+    }
+    CU_TRY(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    return 0;
 }
 
 }  // namespace
@@ -611,6 +655,19 @@ int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* norma
     c->run_has_normals = false;  // the staging buffers were overwritten
     c->run_has_lnu = false;
     return 0;
+}
+
+int srhmc_measure_fma_peak(int32_t device, int32_t precision, double* tflops, float* ms) {
+    if (!tflops) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (precision != 64 && precision != 32) return fail(SRHMC_ERR_INVALID, "precision must be 64 or 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SRHMC_ERR_NO_DEVICE, "no CUDA device visible");
+    if (device < 0 || device >= ndev) return fail(SRHMC_ERR_INVALID, "device out of range");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    return precision == 64 ? run_fma_peak<double>(prop.multiProcessorCount, tflops, ms)
+                           : run_fma_peak<float>(prop.multiProcessorCount, tflops, ms);
 }
 
 }  // extern "C"
