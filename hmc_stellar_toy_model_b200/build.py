@@ -12,9 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libstellar_rhmc.so")
-SOURCES = [os.path.join(CSRC, "stellar_rhmc.cu")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+SOURCES = ["stellar_rhmc.cu", "field_kernels_f64.cu", "field_kernels_f32.cu", "chain_kernels.cu", "misc_kernels.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMPILE_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c"]
+LINK_FLAGS = ARCH + ["-shared", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _deps():
@@ -30,21 +32,50 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in _deps())
 
 
+def _stale(obj, src):
+    if not os.path.isfile(obj):
+        return True
+    t = os.path.getmtime(obj)
+    heads = [d for d in _deps() if d.endswith((".cuh", ".h"))]
+    return any(os.path.getmtime(d) > t for d in heads + [src])
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit for sm_100a (in parallel) and link libstellar_rhmc.so in-tree."""
     if not force and up_to_date():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
         raise RuntimeError("nvcc not found; cannot build libstellar_rhmc.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT + ".tmp"] + SOURCES
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs = []
+    for name in SOURCES:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(OBJ_DIR, name[:-3] + ".o")
+        if force or _stale(obj, src):
+            cmd = [nvcc] + COMPILE_FLAGS + ["-o", obj, src]
+            jobs.append((name, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log_lines = []
+    failed = []
+    for name, cmd, proc in jobs:
+        out, _ = proc.communicate()
+        log_lines.append(" ".join(cmd) + "\n" + out)
+        if proc.returncode != 0:
+            failed.append((name, out))
+    objs = [os.path.join(OBJ_DIR, n[:-3] + ".o") for n in SOURCES]
+    if not failed:
+        cmd = [nvcc] + LINK_FLAGS + ["-o", OUT + ".tmp"] + objs
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log_lines.append(" ".join(cmd) + "\n" + proc.stdout)
+        if proc.returncode != 0:
+            failed.append(("link", proc.stdout))
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + proc.stdout)
+        fh.write("\n".join(log_lines))
     if verbose:
-        print(proc.stdout)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (see %s):\n%s" % (log, proc.stdout[-4000:]))
+        print("\n".join(log_lines))
+    if failed:
+        raise RuntimeError("nvcc failed for %s (see %s):\n%s" % (failed[0][0], log, failed[0][1][-4000:]))
     os.replace(OUT + ".tmp", OUT)
     return OUT
 

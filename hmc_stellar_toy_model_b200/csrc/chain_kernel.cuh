@@ -1,8 +1,323 @@
-// Warp-per-chain one-star kernel (placeholder until the specialised kernel lands; the CTA-per-field kernel
-// handles every configuration).
+// Warp-resident one-star chain kernel (sm_100a): BASELINE.json configs[0..1] -- thousands of independent
+// one-star RHMC chains on small images (C <= 32 columns, R <= 64 rows).
+//
+// LPC lanes own one chain (LPC = 16: two chains per warp).  A lane owns the image columns sub, sub+LPC, ...;
+// the chain's data image sits in shared memory for the whole launch; the star state, momenta, cached gradient
+// and energies live in registers (every lane of the group holds the same copy), so a full
+// (niter+1) x nsteps chain runs without any block-level barrier, global traffic (except chain rows written out)
+// or host involvement.  Blocks are single warps; the grid is sized to a balanced number of warps per SM and each
+// warp walks its share of the chains.
+//
+// Per gradient evaluation (reference: base_class.dVdq, sampler_RHMC.py:365-425, one star, full-image PSF):
+//   lanes compute ex_i = exp(-(i+.5-x)^2/2s^2) for their rows -> shared row table {ex_i, ex_i*(i+.5-x)};
+//   lanes compute ey_j/(2 pi s^2) for their columns (registers);
+//   row loop: Lambda = B + ex_i * (f ey_j); rho = D/Lambda - 1 (MUFU.RCP64H + cubic Newton step);
+//             c0_j += rho ex_i; c1_j += rho ex_i dx_i;      [+ V += Lambda - D ln Lambda on request]
+//   g_f = -sum_j ey_j c0_j,  g_x = -(f/s^2) sum_j ey_j c1_j,  g_y = -(f/s^2) sum_j ey_j dy_j c0_j  via shuffles.
 #pragma once
+#include <math_constants.h>
+
 #include "common.cuh"
+
 namespace srhmc {
-template <typename T> inline int configure_chain_kernel(const FieldParams&) { return (int)cudaErrorNotSupported; }
-template <typename T> inline int launch_chain_kernel(const FieldParams&, const LaunchArgs&, double*, int, cudaStream_t) { return (int)cudaErrorNotSupported; }
+
+constexpr int kChainCS = 32;  // column stride of a chain image in shared memory
+
+struct ChainState {
+    double f, x, y, pf, px, py;  // q, p
+    double gf, gx, gy;           // pixel part of dV/dq at (f, x, y)
+    double Vpix;                 // sum(Lambda - D ln Lambda) at (f, x, y)
+};
+
+template <int LPC>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Pixel part of the gradient (and of V) for one chain; all lanes of the warp must call it together.
+template <int LPC, bool WANT_V>
+__device__ __forceinline__ void chain_eval(const FieldParams& P, const double* __restrict__ sD, double2* __restrict__ rt,
+                                           int sub, ChainState& s) {
+    constexpr int CPL = 32 / LPC;
+    const int R = P.R, C = P.C;
+    const double f = s.f, x = s.x, y = s.y;
+    for (int i = sub; i < R; i += LPC) {
+        const double u = ((double)i + 0.5) - x;
+        const double e = exp(-(u * u) * P.inv2s2);
+        rt[i] = make_double2(e, e * u);
+    }
+    double ey[CPL], fey[CPL], eydy[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        const int j = sub + LPC * c;
+        const double v = ((double)j + 0.5) - y;
+        const double e = (j < C) ? exp(-(v * v) * P.inv2s2) * P.norm : 0.0;
+        ey[c] = e;
+        fey[c] = f * e;
+        eydy[c] = e * v;
+    }
+    __syncwarp();
+    double c0[CPL], c1[CPL], vacc = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < R; ++i) {
+        const double2 re = rt[i];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const double lam = fma(re.x, fey[c], P.B);
+            const double d = sD[i * kChainCS + sub + LPC * c];
+            const double rho = fma(d, rcp_fast(lam), -1.0);
+            c0[c] = fma(rho, re.x, c0[c]);
+            c1[c] = fma(rho, re.y, c1[c]);
+            if (WANT_V) {
+                if (sub + LPC * c < C) vacc += lam - d * log(lam);
+            }
+        }
+    }
+    __syncwarp();  // row table is rewritten by the next evaluation
+    double sf = 0.0, sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        sf = fma(ey[c], c0[c], sf);
+        sx = fma(ey[c], c1[c], sx);
+        sy = fma(eydy[c], c0[c], sy);
+    }
+    sf = group_sum<LPC>(sf);
+    sx = group_sum<LPC>(sx);
+    sy = group_sum<LPC>(sy);
+    s.gf = -sf;
+    s.gx = -sx * f * P.inv_s2;
+    s.gy = -sy * f * P.inv_s2;
+    if (WANT_V) s.Vpix = group_sum<LPC>(vacc);
+}
+
+// V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential (sampler_RHMC.py:294-363).
+__device__ __forceinline__ void chain_energies(const FieldParams& P, const ChainState& s, double g_ff2, int f_pos,
+                                               double& V, double& T) {
+    const Metric m = metric_of(P, s.f, g_ff2);
+    const double v0 = s.pf * s.pf / m.Hff + s.px * s.px / m.Hxx + s.py * s.py / m.Hxx;
+    const double v1 = log(fabs(m.Hff)) + 2.0 * log(fabs(m.Hxx));
+    T = (v0 + v1) / 2.0;
+    double v = s.Vpix;
+    if (P.use_prior) v += P.alpha * log(s.f) + P.Vpc;
+    const bool bad = (f_pos && s.f < P.f_lim) || (s.x < -1.0) || (s.x > P.R + 1.0) || (s.y < -1.0) || (s.y > P.C + 1.0);
+    V = bad ? CUDART_INF : v;
+}
+
+// base_class.RHMC_single_step for a one-star field, state in registers (sampler_RHMC.py:522-566).
+template <int LPC>
+__device__ __forceinline__ void chain_step(const FieldParams& P, const double* sD, double2* rt, int sub, ChainState& s,
+                                           double h, double g_ff2, double delta, int counter_max, bool want_V,
+                                           int& cnt_p, int& cnt_q) {
+    // (1) first half kick
+    Metric m = metric_of(P, s.f, g_ff2);
+    {
+        double gf = s.gf;
+        if (P.use_prior) gf += P.alpha / s.f;
+        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        s.pf -= h * gf;
+        s.px -= h * s.gx;
+        s.py -= h * s.gy;
+    }
+    // (2) implicit momentum update (flux slot only)
+    {
+        const double rho = s.pf, kap = -m.dHff / (m.Hff * m.Hff);
+        double pf = s.pf;
+        cnt_p = 0;
+        while (cnt_p < counter_max) {
+            const double pn = rho - h * (((pf * pf) * kap) / 2.0);
+            const bool more = fabs(pf - pn) > delta;
+            pf = pn;
+            ++cnt_p;
+            if (!more) break;
+        }
+        s.pf = pf;
+    }
+    // (3) implicit position update
+    {
+        const double sf = s.f, sx = s.x, sy = s.y;
+        const double af = s.pf / m.Hff, ax = s.px / m.Hxx, ay = s.py / m.Hxx;
+        double qf = sf, qx = sx, qy = sy;
+        cnt_q = 0;
+        while (cnt_q < counter_max) {
+            const Metric mq = metric_of(P, qf, g_ff2);
+            const double nf = sf + h * (af + s.pf / mq.Hff);
+            const double nx = sx + h * (ax + s.px / mq.Hxx);
+            const double ny = sy + h * (ay + s.py / mq.Hxx);
+            const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
+            qf = nf;
+            qx = nx;
+            qy = ny;
+            ++cnt_q;
+            if (!(d > delta)) break;
+        }
+        s.f = qf;
+        s.x = qx;
+        s.y = qy;
+    }
+    // (4) second implicit half kick at the new q
+    m = metric_of(P, s.f, g_ff2);
+    s.pf = s.pf - h * (((s.pf * s.pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+    // (5) gradient at the new q and last half kick
+    if (want_V)
+        chain_eval<LPC, true>(P, sD, rt, sub, s);
+    else
+        chain_eval<LPC, false>(P, sD, rt, sub, s);
+    {
+        double gf = s.gf;
+        if (P.use_prior) gf += P.alpha / s.f;
+        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        s.pf -= h * gf;
+        s.px -= h * s.gx;
+        s.py -= h * s.gy;
+    }
+    // (6) reflections
+    if (s.f < P.f_lim) s.pf *= -1.0;
+    if ((s.x < 0.0) || (s.x > P.R - 1.0)) s.px *= -1.0;
+    if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py *= -1.0;
+}
+
+template <int LPC>
+__global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GPW = 32 / LPC;  // chains per warp
+    const int lane = threadIdx.x, grp = lane / LPC, sub = lane % LPC;
+    const int R = P.R, C = P.C;
+    const size_t img_elems = (size_t)R * kChainCS;
+    double* sD = reinterpret_cast<double*>(smem_raw) + (size_t)grp * img_elems;
+    double2* rt = reinterpret_cast<double2*>(smem_raw + (size_t)GPW * img_elems * sizeof(double)) + (size_t)grp * R;
+    const double h = A.dt / 2.0;
+
+    for (int base = blockIdx.x * GPW; base < A.n_fields; base += gridDim.x * GPW) {
+        const bool live = base + grp < A.n_fields;
+        const int field = live ? base + grp : A.n_fields - 1;  // idle group shadows a valid chain, writes nothing
+        constexpr int n = 1;  // the host routes only exactly-one-star batches to this kernel
+        const double* gD = reinterpret_cast<const double*>(A.D) + (size_t)field * R * C;
+        __syncwarp();
+        for (int i = 0; i < R; ++i)
+            for (int j = sub; j < kChainCS; j += LPC) sD[i * kChainCS + j] = (j < C) ? gD[i * C + j] : 0.0;
+        ChainState s;
+        const double* q_in = A.q_in + (size_t)field * 3;
+        s.f = n ? q_in[0] : 0.0;
+        s.x = n ? q_in[1] : 0.0;
+        s.y = n ? q_in[2] : 0.0;
+        s.pf = s.px = s.py = 0.0;
+        if (A.p_in && n) {
+            s.pf = A.p_in[(size_t)field * 3];
+            s.px = A.p_in[(size_t)field * 3 + 1];
+            s.py = A.p_in[(size_t)field * 3 + 2];
+        }
+        __syncwarp();
+        const bool writer = live && sub == 0;
+        double g_ff2 = A.g_ff2;
+        int cp = 0, cq = 0;
+
+        if (A.mode == MODE_EVAL) {
+            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            double V, T;
+            chain_energies(P, s, g_ff2, A.f_pos, V, T);
+            const Metric m = metric_of(P, s.f, g_ff2);
+            if (writer) {
+                const size_t o = (size_t)field * 3;
+                if (A.V_out) A.V_out[field] = V;
+                if (A.grad_out) {
+                    A.grad_out[o] = s.gf + (P.use_prior ? P.alpha / s.f : 0.0);
+                    A.grad_out[o + 1] = s.gx;
+                    A.grad_out[o + 2] = s.gy;
+                }
+                if (A.H_out) { A.H_out[o] = m.Hff; A.H_out[o + 1] = m.Hxx; A.H_out[o + 2] = m.Hxx; }
+                if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
+            }
+        } else if (A.mode == MODE_STEP) {
+            chain_eval<LPC, false>(P, sD, rt, sub, s);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, false, cp, cq);
+            if (writer) {
+                const size_t o = (size_t)field * 3;
+                A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
+                A.p_out[o] = s.pf; A.p_out[o + 1] = s.px; A.p_out[o + 2] = s.py;
+                if (A.fp_counts) { A.fp_counts[2 * field] = cp; A.fp_counts[2 * field + 1] = cq; }
+            }
+        } else if (A.mode == MODE_SINGLE) {
+            const size_t rows = (size_t)A.nsteps + 1;
+            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            double V0, T0;
+            chain_energies(P, s, g_ff2, A.f_pos, V0, T0);
+            if (writer) {
+                const size_t o = (size_t)field * rows * 3;
+                A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
+                A.p_chain[o] = s.pf; A.p_chain[o + 1] = s.px; A.p_chain[o + 2] = s.py;
+                A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
+            }
+            for (int t = 1; t <= A.nsteps; ++t) {
+                chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, true, cp, cq);
+                double V, T;
+                chain_energies(P, s, g_ff2, A.f_pos, V, T);
+                if (writer) {
+                    const size_t o = ((size_t)field * rows + t) * 3;
+                    A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
+                    A.p_chain[o] = s.pf; A.p_chain[o + 1] = s.px; A.p_chain[o + 2] = s.py;
+                    const double dV = V - V0, dT = T - T0;
+                    A.V_chain[field * rows + t] = dV;
+                    A.T_chain[field * rows + t] = dT;
+                    A.E_chain[field * rows + t] = dV + dT;
+                }
+            }
+        } else {  // MODE_RUN
+            const size_t rows = (size_t)A.n_rows;
+            const int L = A.niter + 1;
+            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            int n_acc = 0;
+            for (int l = 0; l < L; ++l) {
+                if (A.gff2_sched && l < A.n_gff2) g_ff2 = A.gff2_sched[l];
+                const Metric m = metric_of(P, s.f, g_ff2);
+                double z[3];
+                if (A.normals) {
+                    const double* zp = A.normals + ((size_t)field * L + l) * 3;
+                    z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
+                } else {
+                    philox_normals3(A.seed, (uint32_t)field, (uint32_t)l, 0u, z);
+                }
+                s.pf = z[0] * sqrt(m.Hff);
+                s.px = z[1] * sqrt(m.Hxx);
+                s.py = z[2] * sqrt(m.Hxx);
+                const ChainState s0 = s;
+                double V0, T0;
+                chain_energies(P, s, g_ff2, A.f_pos, V0, T0);
+                const double E0 = V0 + T0;
+                const bool keep = (l % A.chain_stride) == 0;
+                const size_t row = (size_t)field * rows + (size_t)(l / A.chain_stride);
+                if (keep && writer) {
+                    if (A.q_chain) { A.q_chain[row * 3] = s.f; A.q_chain[row * 3 + 1] = s.x; A.q_chain[row * 3 + 2] = s.y; }
+                    if (A.p_chain) { A.p_chain[row * 3] = s.pf; A.p_chain[row * 3 + 1] = s.px; A.p_chain[row * 3 + 2] = s.py; }
+                    if (A.E_chain) A.E_chain[row] = E0;
+                    if (A.V_chain) A.V_chain[row] = V0;
+                    if (A.T_chain) A.T_chain[row] = T0;
+                }
+                for (int t = 0; t < A.nsteps; ++t)
+                    chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, t == A.nsteps - 1, cp, cq);
+                double V1, T1;
+                chain_energies(P, s, g_ff2, A.f_pos, V1, T1);
+                const double dE = (V1 + T1) - E0;
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)field, (uint32_t)l);
+                const bool accept = (dE < 0.0) || (lnu < -dE);
+                if (keep && writer && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
+                if (accept) {
+                    ++n_acc;
+                } else {
+                    s.f = s0.f; s.x = s0.x; s.y = s0.y;
+                    s.gf = s0.gf; s.gx = s0.gx; s.gy = s0.gy;
+                    s.Vpix = s0.Vpix;
+                }
+            }
+            if (writer) {
+                if (A.q_out) { A.q_out[(size_t)field * 3] = s.f; A.q_out[(size_t)field * 3 + 1] = s.x; A.q_out[(size_t)field * 3 + 2] = s.y; }
+                if (A.accept_rate) A.accept_rate[field] = (double)n_acc / (double)L;
+            }
+        }
+    }
+}
+
 }  // namespace srhmc

@@ -662,25 +662,4 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
     }
 }
 
-// Device normals / log-uniforms exactly as MODE_RUN consumes them (for replay through another implementation).
-__global__ void philox_dump_kernel(unsigned long long seed, int n_fields, int L, int Nmax, double* normals, double* lnu) {
-    const size_t total = (size_t)n_fields * L * Nmax;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(t % Nmax);
-        const int l = (int)((t / Nmax) % L);
-        const int f = (int)(t / ((size_t)Nmax * L));
-        double z[3];
-        philox_normals3(seed, (uint32_t)f, (uint32_t)l, (uint32_t)k, z);
-        double* o = normals + (((size_t)f * L + l) * Nmax + k) * 3;
-        o[0] = z[0]; o[1] = z[1]; o[2] = z[2];
-        if (k == 0) lnu[(size_t)f * L + l] = philox_lnu(seed, (uint32_t)f, (uint32_t)l);
-    }
-}
-
-template <typename T>
-__global__ void convert_image_kernel(const double* src, T* dst, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = (T)src[i];
-}
-
 }  // namespace srhmc

@@ -7,31 +7,15 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "../../include/stellar_rhmc.h"
 #include "common.cuh"
-#include "field_kernel.cuh"
-#include "chain_kernel.cuh"
+#include "kernels_api.h"
 
 using namespace srhmc;
-
-namespace srhmc {
-// FMA-chain microbenchmark: 8 independent dependent chains per thread, ITERS iterations.
-template <typename T>
-__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
-    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-}
-}  // namespace srhmc
 
 namespace {
 
@@ -74,10 +58,7 @@ struct DevBuf {
     template <typename U> U* as() const { return reinterpret_cast<U*>(ptr); }
 };
 
-typedef void (*FieldKernelFn)(const FieldParams, const LaunchArgs, double*, int);
-
 struct KernelChoice {
-    FieldKernelFn fn;
     int mr, mc;
 };
 
@@ -96,30 +77,31 @@ struct srhmc_ctx {
     int threads = 256;
     size_t smem = 0;
     int d_in_smem = 1;
-    bool use_chain_kernel = false;  // warp-per-chain one-star kernel
+    bool chain_ok = false;          // warp-resident one-star kernel configured for this context
+    ChainLaunchPlan chain_plan;
     size_t pix_bytes = 8;
     // device buffers
     DevBuf D, Dstage, q, p, nstars, normals, lnu, sg, sb, qchain, pchain, E, V, T, A, acc, scratch, qout, pout, Vout,
         grad, H, Hg, counts;
     // sizes of the last uploaded run
     int run_L = 0, run_rows = 0;
-    bool run_has_nstars = false, run_has_normals = false, run_has_lnu = false;
+    bool run_has_nstars = false, run_has_normals = false, run_has_lnu = false, run_one_star = false;
 };
 
 namespace {
 
-template <typename T>
 KernelChoice pick_kernel(int R, int C, int nwarps) {
     auto tiles = [&](int mr, int mc) { return ((R + 8 * mr - 1) / (8 * mr)) * ((C + 4 * mc - 1) / (4 * mc)); };
-    if (tiles(2, 4) >= nwarps) return {field_kernel<T, 2, 4>, 2, 4};
-    if (tiles(2, 2) >= nwarps) return {field_kernel<T, 2, 2>, 2, 2};
-    return {field_kernel<T, 1, 2>, 1, 2};
+    if (tiles(2, 4) >= nwarps) return {2, 4};
+    if (tiles(2, 2) >= nwarps) return {2, 2};
+    return {1, 2};
 }
 
 constexpr size_t kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-template <typename T>
 int configure(srhmc_ctx* c) {
+    const int prec = c->cfg.precision;
+    const size_t elem = prec == 64 ? 8 : 4;
     const srhmc_config& g = c->cfg;
     FieldParams& P = c->P;
     const int R = g.num_rows, C = g.num_cols, N = g.max_stars;
@@ -127,15 +109,15 @@ int configure(srhmc_ctx* c) {
     if ((size_t)R * C >= 4096 || N > 256) threads = 512;
     if ((size_t)R * C <= 256 && N <= 64) threads = 128;
     c->threads = threads;
-    c->kc = pick_kernel<T>(R, C, threads / 32);
+    c->kc = pick_kernel(R, C, threads / 32);
     P.sx = ((R + 8 * c->kc.mr - 1) / (8 * c->kc.mr)) * 8 * c->kc.mr;
     P.sy = ((C + 4 * c->kc.mc - 1) / (4 * c->kc.mc)) * 4 * c->kc.mc;
     const int nwant = std::max(1, N);
     auto fit = [&](size_t budget, bool dsm) -> int {
         FieldParams Q = P;
         Q.Kc = 0;
-        const size_t base = make_layout<T>(Q, dsm).total;
-        const size_t per = (size_t)(P.sx + P.sy) * sizeof(T) + 4 * sizeof(short);
+        const size_t base = field_layout_total(prec, Q, dsm);
+        const size_t per = (size_t)(P.sx + P.sy) * elem + 4 * sizeof(short);
         if (base + per + 64 > budget) return 0;
         return (int)std::min<size_t>((size_t)nwant, (budget - base - 64) / per);
     };
@@ -154,22 +136,23 @@ int configure(srhmc_ctx* c) {
                     R, C, N, kSmemMax);
     P.Kc = kc;
     c->d_in_smem = dsm ? 1 : 0;
-    c->smem = make_layout<T>(P, dsm).total;
-    CU_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    c->smem = field_layout_total(prec, P, dsm);
+    const int e = field_kernel_configure(prec, c->kc.mr, c->kc.mc, c->smem);
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B shared) failed: %s", c->smem, cudaGetErrorString((cudaError_t)e));
     return 0;
 }
 
-int launch_field(srhmc_ctx* c, const LaunchArgs& A) {
+int launch_field(srhmc_ctx* c, const LaunchArgs& A, bool one_star_everywhere) {
     if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
-    if (c->use_chain_kernel) {
-        int rc = c->cfg.precision == 64 ? launch_chain_kernel<double>(c->P, A, c->scratch.as<double>(), c->sm_count, c->stream)
-                                        : launch_chain_kernel<float>(c->P, A, c->scratch.as<double>(), c->sm_count, c->stream);
+    if (c->chain_ok && one_star_everywhere) {
+        int rc = chain_kernel_launch(c->P, A, c->chain_plan, c->sm_count, c->stream);
         if (rc != 0) return fail(SRHMC_ERR_CUDA, "chain kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     } else {
         const int grid = std::max(1, A.n_fields);
-        c->kc.fn<<<grid, c->threads, c->smem, c->stream>>>(c->P, A, c->scratch.as<double>(), c->d_in_smem);
+        int rc = field_kernel_launch(c->cfg.precision, c->kc.mr, c->kc.mc, grid, c->threads, c->smem, c->stream, c->P, A,
+                                     c->scratch.as<double>(), c->d_in_smem);
+        if (rc != 0) return fail(SRHMC_ERR_CUDA, "field kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     }
-    CU_TRY(cudaGetLastError());
     if (c->timed) CU_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
     return 0;
@@ -187,36 +170,17 @@ int download(srhmc_ctx* c, void* dst, const DevBuf& b, size_t bytes) {
 }
 
 bool chain_kernel_eligible(const srhmc_config& g) {
-    return false && g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc && !g.shared_data &&
-           g.patch_radius == 0 && g.fixed_point_mode == 0;
+    const char* off = std::getenv("SRHMC_DISABLE_CHAIN_KERNEL");
+    if (off && off[0] == '1') return false;
+    return g.precision == 64 && g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc &&
+           !g.shared_data && g.patch_radius == 0;
 }
 
-template <typename T>
-int run_fma_peak(int sms, double* tflops, float* ms) {
-    const int blocks = sms * 8, threads = 256, iters = 4096;
-    T* out = nullptr;
-    CU_TRY(cudaMalloc(&out, (size_t)blocks * threads * sizeof(T)));
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
-        CU_TRY(cudaEventRecord(e0, 0));
-        fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)0.999, (T)0.001);
-        CU_TRY(cudaEventRecord(e1, 0));
-        CU_TRY(cudaEventSynchronize(e1));
-        float t = 0.f;
-        CU_TRY(cudaEventElapsedTime(&t, e0, e1));
-        if (rep > 0 && t < best) best = t;
-    }
-    CU_TRY(cudaGetLastError());
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(out);
-    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
-    *tflops = flops / (best * 1e-3) / 1e12;
-    if (ms) *ms = best;
-    return 0;
+bool all_one_star(const srhmc_ctx* c, const int32_t* nstars) {
+    if (!nstars) return c->cfg.max_stars == 1;
+    for (int f = 0; f < c->cfg.n_fields; ++f)
+        if (nstars[f] != 1) return false;
+    return true;
 }
 
 }  // namespace
@@ -298,13 +262,11 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.vc_int = (rp == cfg->Vc_r_pow && rp >= 0.0 && rp <= 32.0) ? (int)rp : -1;
     c->pix_bytes = cfg->precision == 64 ? 8 : 4;
 
-    int rc = 0;
-    c->use_chain_kernel = chain_kernel_eligible(*cfg);
-    if (c->use_chain_kernel) {
-        rc = cfg->precision == 64 ? configure_chain_kernel<double>(P) : configure_chain_kernel<float>(P);
-        if (rc != 0) rc = fail(SRHMC_ERR_CUDA, "chain kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
-    } else {
-        rc = cfg->precision == 64 ? configure<double>(c) : configure<float>(c);
+    int rc = configure(c);
+    if (rc == 0 && chain_kernel_eligible(*cfg)) {
+        const int e = chain_kernel_configure(P, c->chain_plan);
+        if (e != 0) rc = fail(SRHMC_ERR_CUDA, "chain kernel configuration failed: %s", cudaGetErrorString((cudaError_t)e));
+        c->chain_ok = (e == 0);
     }
     if (rc != 0) {
         delete c;
@@ -375,9 +337,8 @@ int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
     } else {
         if (int rc = upload(c, c->Dstage, D, n * 8)) return rc;
         if (int rc = c->D.ensure(n * 4)) return rc;
-        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
-        convert_image_kernel<float><<<blocks, 256, 0, c->stream>>>(c->Dstage.as<double>(), c->D.as<float>(), n);
-        CU_TRY(cudaGetLastError());
+        const int e = convert_image_launch(c->stream, c->Dstage.as<double>(), c->D.as<float>(), n);
+        if (e != 0) return fail(SRHMC_ERR_CUDA, "image conversion failed: %s", cudaGetErrorString((cudaError_t)e));
         c->launches += 1;
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -424,7 +385,7 @@ int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_p
     CU_TRY(cudaMemsetAsync(c->grad.ptr, 0, std::max<size_t>(FS, 8), c->stream));
     CU_TRY(cudaMemsetAsync(c->H.ptr, 0, std::max<size_t>(FS, 8), c->stream));
     CU_TRY(cudaMemsetAsync(c->Hg.ptr, 0, std::max<size_t>(FS, 8), c->stream));
-    if (int rc = launch_field(c, A)) return rc;
+    if (int rc = launch_field(c, A, all_one_star(c, nstars))) return rc;
     if (V) if (int rc = download(c, V, c->Vout, F * 8)) return rc;
     if (grad && FS) if (int rc = download(c, grad, c->grad, FS)) return rc;
     if (H && FS) if (int rc = download(c, H, c->H, FS)) return rc;
@@ -467,7 +428,7 @@ int srhmc_step(srhmc_ctx* c, double* q, double* p, const int32_t* nstars, int32_
     A.beta = beta;
     A.chain_stride = 1;
     A.fp_counts = c->counts.as<int>();
-    if (int rc = launch_field(c, A)) return rc;
+    if (int rc = launch_field(c, A, all_one_star(c, nstars))) return rc;
     if (F * S) {
         if (int rc = download(c, q, c->qout, F * S * 8)) return rc;
         if (int rc = download(c, p, c->pout, F * S * 8)) return rc;
@@ -495,6 +456,7 @@ int srhmc_run_upload(srhmc_ctx* c, const srhmc_run_args* a) {
     if (int rc = upload(c, c->q, a->q0, FS)) return rc;
     if (int rc = upload_nstars(c, a->nstars)) return rc;
     c->run_has_nstars = a->nstars != nullptr;
+    c->run_one_star = all_one_star(c, a->nstars);
     c->run_has_normals = a->normals != nullptr;
     c->run_has_lnu = a->lnu != nullptr;
     if (a->normals) if (int rc = upload(c, c->normals, a->normals, std::max<size_t>(F * L * S * 8, 8))) return rc;
@@ -558,7 +520,7 @@ int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
     A.T_chain = a->T_chain ? c->T.as<double>() : nullptr;
     A.A_chain = a->A_chain ? c->A.as<unsigned char>() : nullptr;
     A.accept_rate = c->acc.as<double>();
-    return launch_field(c, A);
+    return launch_field(c, A, c->run_one_star);
 }
 
 int srhmc_run_download(srhmc_ctx* c, const srhmc_run_args* a) {
@@ -628,7 +590,7 @@ int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int
     A.E_chain = c->E.as<double>();
     A.V_chain = c->V.as<double>();
     A.T_chain = c->T.as<double>();
-    if (int rc = launch_field(c, A)) return rc;
+    if (int rc = launch_field(c, A, all_one_star(c, nstars))) return rc;
     if (q_chain && S) if (int rc = download(c, q_chain, c->qchain, F * rows * S * 8)) return rc;
     if (p_chain && S) if (int rc = download(c, p_chain, c->pchain, F * rows * S * 8)) return rc;
     if (E_chain) if (int rc = download(c, E_chain, c->E, F * rows * 8)) return rc;
@@ -645,9 +607,8 @@ int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* norma
     if (N == 0) return fail(SRHMC_ERR_INVALID, "max_stars is 0");
     if (int rc = c->normals.ensure(F * L * N * 3 * 8)) return rc;
     if (int rc = c->lnu.ensure(F * L * 8)) return rc;
-    const int blocks = (int)std::min<size_t>((F * L * N + 255) / 256, 8192);
-    philox_dump_kernel<<<blocks, 256, 0, c->stream>>>(seed, (int)F, (int)L, (int)N, c->normals.as<double>(), c->lnu.as<double>());
-    CU_TRY(cudaGetLastError());
+    const int e = philox_dump_launch(c->stream, seed, (int)F, (int)L, (int)N, c->normals.as<double>(), c->lnu.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "philox dump failed: %s", cudaGetErrorString((cudaError_t)e));
     c->launches += 1;
     if (int rc = download(c, normals, c->normals, F * L * N * 3 * 8)) return rc;
     if (int rc = download(c, lnu, c->lnu, F * L * 8)) return rc;
@@ -666,8 +627,9 @@ int srhmc_measure_fma_peak(int32_t device, int32_t precision, double* tflops, fl
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
-    return precision == 64 ? run_fma_peak<double>(prop.multiProcessorCount, tflops, ms)
-                           : run_fma_peak<float>(prop.multiProcessorCount, tflops, ms);
+    const int e = fma_peak_run(precision, prop.multiProcessorCount, tflops, ms);
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "FMA peak microbenchmark failed: %s", cudaGetErrorString((cudaError_t)e));
+    return 0;
 }
 
 }  // extern "C"

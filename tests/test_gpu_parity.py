@@ -240,3 +240,41 @@ def test_fp32_build_within_1e4():
     a, b = grad[0].reshape(-1, 3), g["dVdq"].reshape(-1, 3)
     assert np.max(np.abs(a - b) / np.max(np.abs(b), axis=0, keepdims=True)) < 1e-4
     assert relerr(H[0], g["H"]) < 1e-12
+
+
+def test_chain_kernel_matches_field_kernel_and_oracle(monkeypatch):
+    """The warp-resident one-star kernel and the generic CTA-per-field kernel are two implementations of the same
+    path: run an odd-sized batch of one-star chains through both (and two of them through the oracle)."""
+    import bench
+    wl = bench.workload_c2(3, seed=5)  # 33 chains, 11 magnitudes
+    F = wl["D"].shape[0] - 2           # 31: leaves one half-warp idle
+    D, q0 = wl["D"][:F], wl["q0"][:F]
+    q0 = q0 + np.random.RandomState(1).uniform(-0.4, 0.4, q0.shape) * np.array([0.0, 1.0, 1.0])
+    cfg = dict(wl["cfg"], n_fields=F)
+    niter, nsteps, dt = 30, 10, 0.2
+    from hmc_stellar_toy_model_b200 import RHMCContext
+    res = {}
+    for name, off in (("chain", "0"), ("field", "1")):
+        monkeypatch.setenv("SRHMC_DISABLE_CHAIN_KERNEL", off)
+        with RHMCContext(**cfg) as ctx:
+            ctx.set_data(D)
+            normals, lnu = ctx.philox_draws(99, niter)
+            r = ctx.run(q0, niter, nsteps, dt, seed=99, g_ff2=1.0, f_pos=True)
+            V, grad, H, Hg = ctx.eval(q0, f_pos=True, g_ff2=1.0)
+            q1, p1, cnt = ctx.step(q0, normals[:, 0] * np.sqrt(H), 3, dt, g_ff2=1.0, return_counts=True)
+            res[name] = (r, V, grad, H, Hg, q1, p1, cnt, normals, lnu)
+    a, b = res["chain"], res["field"]
+    assert np.array_equal(a[0].A_chain, b[0].A_chain)
+    assert relerr(a[0].q_chain, b[0].q_chain) < 1e-9
+    assert relerr(a[0].E_chain, b[0].E_chain) < 1e-11
+    assert relerr(a[1], b[1]) < 1e-12 and grad_relerr(a[2], b[2]) < 1e-10
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert relerr(a[5], b[5]) < 1e-10 and np.array_equal(a[7], b[7])
+    assert np.array_equal(a[8], b[8]) and np.array_equal(a[9], b[9])
+    k = exp = None
+    for f in (0, F - 1):
+        S = so.Setup(num_rows=32, num_cols=32, g_xx=1.0, g_ff=1.0, g_ff2=1.0, V_prior_const=0.0, D=D[f])
+        out = so.run_rhmc(S, q0[f], a[8][f], a[9][f], niter, nsteps, dt)
+        assert np.array_equal(a[0].A_chain[f].astype(bool), out.A)
+        assert first_divergence(a[0].q_chain[f], out.q, 1e-9) == -1
+        assert relerr(a[0].E_chain[f], out.E) < RTOL
