@@ -27,7 +27,57 @@ struct ChainState {
     double f, x, y, pf, px, py;  // q, p
     double gf, gx, gy;           // pixel part of dV/dq at (f, x, y)
     double Vpix;                 // sum(Lambda - D ln Lambda) at (f, x, y)
+    // metric cache at f (see ChainConst): u = 1/H_ff, kap = -H_ff'/H_ff^2, ihxx = 1/H_xx,
+    // tphi = (H_ff'/H_ff + 2 H_xx'/H_xx)/2
+    double u, kap, ihxx, tphi;
 };
+
+// Division-free form of the reference metric (sampler_RHMC.py:229-292) for the hot loop.  With
+//   c = (B/g0)/g_ff, u = f/g_ff2 + c, w = 1/(f + c), fh = max(f, f_low), v = 1/fh, t = 1/g1 + (B/g2) v :
+//   H_ff = 1/u,  H_ff' = -w^2,  H_ff'/H_ff = -u w^2,  -H_ff'/H_ff^2 = (u w)^2,
+//   1/H_xx = v t / g_xx,  H_xx'/H_xx = v (t + (B/g2) v) / t   (0 below the faint clamp).
+// Every reciprocal is MUFU.RCP64H + one cubic Newton step (rcp_fast, ~2^-60 relative error).
+struct ChainConst {
+    double c, ig2, ig1, Bg2, igxx, g_xx, f_low;
+    double h, hh, delta;
+};
+
+__device__ __forceinline__ ChainConst make_chain_const(const FieldParams& P, double g_ff2, double h, double delta) {
+    ChainConst K;
+    K.c = (P.B / P.g0) / P.g_ff;
+    K.ig2 = 1.0 / g_ff2;
+    K.ig1 = 1.0 / P.g1;
+    K.Bg2 = P.B / P.g2;
+    K.igxx = 1.0 / P.g_xx;
+    K.g_xx = P.g_xx;
+    K.f_low = P.f_low;
+    K.h = h;
+    K.hh = h / 2.0;
+    K.delta = delta;
+    return K;
+}
+
+__device__ __forceinline__ double inv_hxx(const ChainConst& K, double f) {
+    const double v = rcp_fast(fmax(f, K.f_low));
+    return (v * fma(K.Bg2, v, K.ig1)) * K.igxx;
+}
+
+// full metric cache at s.f
+__device__ __forceinline__ void refresh_metric(const ChainConst& K, ChainState& s) {
+    const double f = s.f;
+    const double u = fma(f, K.ig2, K.c);
+    const double w = rcp_fast(f + K.c);
+    const double uw = u * w;
+    const bool low = f < K.f_low;
+    const double v = rcp_fast(low ? K.f_low : f);
+    const double bv = K.Bg2 * v;
+    const double t = bv + K.ig1;
+    s.u = u;
+    s.kap = uw * uw;
+    s.ihxx = (v * t) * K.igxx;
+    const double dxx = low ? 0.0 : (v * (t + bv)) * rcp_fast(t);
+    s.tphi = fma(-0.5 * uw, w, dxx);
+}
 
 template <int LPC>
 __device__ __forceinline__ double group_sum(double v) {
@@ -94,12 +144,12 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const double* _
     if (WANT_V) s.Vpix = group_sum<LPC>(vacc);
 }
 
-// V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential (sampler_RHMC.py:294-363).
-__device__ __forceinline__ void chain_energies(const FieldParams& P, const ChainState& s, double g_ff2, int f_pos,
+// V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential and metric
+// (sampler_RHMC.py:294-363).
+__device__ __forceinline__ void chain_energies(const FieldParams& P, const ChainConst& K, const ChainState& s, int f_pos,
                                                double& V, double& T) {
-    const Metric m = metric_of(P, s.f, g_ff2);
-    const double v0 = s.pf * s.pf / m.Hff + s.px * s.px / m.Hxx + s.py * s.py / m.Hxx;
-    const double v1 = log(fabs(m.Hff)) + 2.0 * log(fabs(m.Hxx));
+    const double v0 = (s.pf * s.pf) * s.u + (s.px * s.px + s.py * s.py) * s.ihxx;
+    const double v1 = -(log(fabs(s.u)) + 2.0 * log(fabs(s.ihxx)));   // ln|H_ff| + 2 ln|H_xx|
     T = (v0 + v1) / 2.0;
     double v = s.Vpix;
     if (P.use_prior) v += P.alpha * log(s.f) + P.Vpc;
@@ -108,76 +158,75 @@ __device__ __forceinline__ void chain_energies(const FieldParams& P, const Chain
 }
 
 // base_class.RHMC_single_step for a one-star field, state in registers (sampler_RHMC.py:522-566).
+// Requires s.g*, s.u, s.kap, s.ihxx, s.tphi valid at s.f on entry; leaves them valid on exit.
 template <int LPC>
-__device__ __forceinline__ void chain_step(const FieldParams& P, const double* sD, double2* rt, int sub, ChainState& s,
-                                           double h, double g_ff2, double delta, int counter_max, bool want_V,
-                                           int& cnt_p, int& cnt_q) {
-    // (1) first half kick
-    Metric m = metric_of(P, s.f, g_ff2);
+__device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const double* sD, double2* rt, int sub,
+                                           ChainState& s, int counter_max, bool want_V, int& cnt_p, int& cnt_q) {
+    const double h = K.h;
+    // (1) p <- p - h dphi/dq(q)
     {
-        double gf = s.gf;
-        if (P.use_prior) gf += P.alpha / s.f;
-        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
-        s.pf -= h * gf;
-        s.px -= h * s.gx;
-        s.py -= h * s.gy;
+        double gf = s.gf + s.tphi;
+        if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
+        s.pf = fma(-h, gf, s.pf);
+        s.px = fma(-h, s.gx, s.px);
+        s.py = fma(-h, s.gy, s.py);
     }
-    // (2) implicit momentum update (flux slot only)
+    // (2) p' = rho - h dtau/dq(q, p): only the flux slot moves, dtau/dq_f = p_f^2 kap / 2
     {
-        const double rho = s.pf, kap = -m.dHff / (m.Hff * m.Hff);
+        const double rho = s.pf, hk = K.hh * s.kap;
         double pf = s.pf;
         cnt_p = 0;
         while (cnt_p < counter_max) {
-            const double pn = rho - h * (((pf * pf) * kap) / 2.0);
-            const bool more = fabs(pf - pn) > delta;
+            const double pn = fma(-hk, pf * pf, rho);
+            const bool more = fabs(pf - pn) > K.delta;
             pf = pn;
             ++cnt_p;
             if (!more) break;
         }
         s.pf = pf;
     }
-    // (3) implicit position update
+    // (3) q' = sigma + h (p/H(sigma) + p/H(q)).  With u = 1/H_ff, ih = 1/H_xx:
+    //     f_k = sigma_f + h p_f (u0 + u(f_{k-1})),  x_k = sigma_x + h p_x g_k,  g_k = ih0 + ih(f_{k-1}),  g_0 := 0
     {
-        const double sf = s.f, sx = s.x, sy = s.y;
-        const double af = s.pf / m.Hff, ax = s.px / m.Hxx, ay = s.py / m.Hxx;
-        double qf = sf, qx = sx, qy = sy;
+        const double sf = s.f, u0 = s.u, ih0 = s.ihxx;
+        const double hpf = h * s.pf, hpx = h * s.px, hpy = h * s.py;
+        const double hpm = fmax(fabs(hpx), fabs(hpy));
+        double qf = sf, uq = u0, ihq = ih0, g = 0.0;
         cnt_q = 0;
         while (cnt_q < counter_max) {
-            const Metric mq = metric_of(P, qf, g_ff2);
-            const double nf = sf + h * (af + s.pf / mq.Hff);
-            const double nx = sx + h * (ax + s.px / mq.Hxx);
-            const double ny = sy + h * (ay + s.py / mq.Hxx);
-            const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
+            const double gn = ih0 + ihq;
+            const double nf = fma(hpf, u0 + uq, sf);
+            const double d = fmax(fabs(qf - nf), hpm * fabs(gn - g));
             qf = nf;
-            qx = nx;
-            qy = ny;
+            g = gn;
             ++cnt_q;
-            if (!(d > delta)) break;
+            if (!(d > K.delta)) break;
+            uq = fma(qf, K.ig2, K.c);
+            ihq = inv_hxx(K, qf);
         }
         s.f = qf;
-        s.x = qx;
-        s.y = qy;
+        s.x = fma(hpx, g, s.x);
+        s.y = fma(hpy, g, s.y);
     }
-    // (4) second implicit half kick at the new q
-    m = metric_of(P, s.f, g_ff2);
-    s.pf = s.pf - h * (((s.pf * s.pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+    // (4) p <- p - h dtau/dq(q, p) at the new q;  metric cache at the new f
+    refresh_metric(K, s);
+    s.pf = fma(-(K.hh * s.kap), s.pf * s.pf, s.pf);
     // (5) gradient at the new q and last half kick
     if (want_V)
         chain_eval<LPC, true>(P, sD, rt, sub, s);
     else
         chain_eval<LPC, false>(P, sD, rt, sub, s);
     {
-        double gf = s.gf;
-        if (P.use_prior) gf += P.alpha / s.f;
-        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
-        s.pf -= h * gf;
-        s.px -= h * s.gx;
-        s.py -= h * s.gy;
+        double gf = s.gf + s.tphi;
+        if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
+        s.pf = fma(-h, gf, s.pf);
+        s.px = fma(-h, s.gx, s.px);
+        s.py = fma(-h, s.gy, s.py);
     }
     // (6) reflections
-    if (s.f < P.f_lim) s.pf *= -1.0;
-    if ((s.x < 0.0) || (s.x > P.R - 1.0)) s.px *= -1.0;
-    if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py *= -1.0;
+    if (s.f < P.f_lim) s.pf = -s.pf;
+    if ((s.x < 0.0) || (s.x > P.R - 1.0)) s.px = -s.px;
+    if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py = -s.py;
 }
 
 template <int LPC>
@@ -213,13 +262,15 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
         __syncwarp();
         const bool writer = live && sub == 0;
         double g_ff2 = A.g_ff2;
+        ChainConst K = make_chain_const(P, g_ff2, h, A.delta);
         int cp = 0, cq = 0;
 
         if (A.mode == MODE_EVAL) {
             chain_eval<LPC, true>(P, sD, rt, sub, s);
+            refresh_metric(K, s);
             double V, T;
-            chain_energies(P, s, g_ff2, A.f_pos, V, T);
-            const Metric m = metric_of(P, s.f, g_ff2);
+            chain_energies(P, K, s, A.f_pos, V, T);
+            const Metric m = metric_of(P, s.f, g_ff2);  // reference-order formulas for the reported H, H'
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 if (A.V_out) A.V_out[field] = V;
@@ -233,7 +284,8 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
             }
         } else if (A.mode == MODE_STEP) {
             chain_eval<LPC, false>(P, sD, rt, sub, s);
-            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, false, cp, cq);
+            refresh_metric(K, s);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, false, cp, cq);
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
@@ -243,8 +295,9 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
         } else if (A.mode == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
             chain_eval<LPC, true>(P, sD, rt, sub, s);
+            refresh_metric(K, s);
             double V0, T0;
-            chain_energies(P, s, g_ff2, A.f_pos, V0, T0);
+            chain_energies(P, K, s, A.f_pos, V0, T0);
             if (writer) {
                 const size_t o = (size_t)field * rows * 3;
                 A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
@@ -252,9 +305,9 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                 A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
             }
             for (int t = 1; t <= A.nsteps; ++t) {
-                chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, true, cp, cq);
+                chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, true, cp, cq);
                 double V, T;
-                chain_energies(P, s, g_ff2, A.f_pos, V, T);
+                chain_energies(P, K, s, A.f_pos, V, T);
                 if (writer) {
                     const size_t o = ((size_t)field * rows + t) * 3;
                     A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
@@ -271,8 +324,11 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
             chain_eval<LPC, true>(P, sD, rt, sub, s);
             int n_acc = 0;
             for (int l = 0; l < L; ++l) {
-                if (A.gff2_sched && l < A.n_gff2) g_ff2 = A.gff2_sched[l];
-                const Metric m = metric_of(P, s.f, g_ff2);
+                if (A.gff2_sched && l < A.n_gff2) {
+                    g_ff2 = A.gff2_sched[l];
+                    K = make_chain_const(P, g_ff2, h, A.delta);
+                }
+                refresh_metric(K, s);
                 double z[3];
                 if (A.normals) {
                     const double* zp = A.normals + ((size_t)field * L + l) * 3;
@@ -280,12 +336,15 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                 } else {
                     philox_normals3(A.seed, (uint32_t)field, (uint32_t)l, 0u, z);
                 }
-                s.pf = z[0] * sqrt(m.Hff);
-                s.px = z[1] * sqrt(m.Hxx);
-                s.py = z[2] * sqrt(m.Hxx);
+                {
+                    const double sxx = sqrt(rcp_fast(s.ihxx));
+                    s.pf = z[0] * sqrt(rcp_fast(s.u));
+                    s.px = z[1] * sxx;
+                    s.py = z[2] * sxx;
+                }
                 const ChainState s0 = s;
                 double V0, T0;
-                chain_energies(P, s, g_ff2, A.f_pos, V0, T0);
+                chain_energies(P, K, s, A.f_pos, V0, T0);
                 const double E0 = V0 + T0;
                 const bool keep = (l % A.chain_stride) == 0;
                 const size_t row = (size_t)field * rows + (size_t)(l / A.chain_stride);
@@ -297,9 +356,9 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                     if (A.T_chain) A.T_chain[row] = T0;
                 }
                 for (int t = 0; t < A.nsteps; ++t)
-                    chain_step<LPC>(P, sD, rt, sub, s, h, g_ff2, A.delta, A.counter_max, t == A.nsteps - 1, cp, cq);
+                    chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
-                chain_energies(P, s, g_ff2, A.f_pos, V1, T1);
+                chain_energies(P, K, s, A.f_pos, V1, T1);
                 const double dE = (V1 + T1) - E0;
                 const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)field, (uint32_t)l);
                 const bool accept = (dE < 0.0) || (lnu < -dE);

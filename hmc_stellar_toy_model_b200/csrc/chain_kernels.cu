@@ -16,6 +16,8 @@ int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
     plan.smem = chain_smem_bytes(P, plan.lpc);
     cudaError_t e = cudaFuncSetAttribute(chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(chain_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<16>, 32, plan.smem);
     if (e != cudaSuccess) return (int)e;
