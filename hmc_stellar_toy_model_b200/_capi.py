@@ -117,6 +117,7 @@ SIGNATURES = {
                                    C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_philox_draws": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, c_double_p, c_double_p]),
+    "srhmc_test_device_math": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32]),
     "srhmc_measure_fma_peak": (C.c_int, [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_float)]),
 }
 

@@ -202,6 +202,13 @@ class RHMCContext:
                                          dptr(pc), dptr(E), dptr(V), dptr(T)))
         return qc, pc, E, V, T
 
+    def device_math(self, which, x):
+        """Diagnostic: the kernels' exp_neg (0), log_pos (1) or rcp_fast (2) evaluated on the device."""
+        x = as_f64(x).ravel()
+        y = np.empty_like(x)
+        check(self._lib.srhmc_test_device_math(self._h, int(which), dptr(x), dptr(y), x.size))
+        return y
+
     # ------------------------------------------------------------------ device RNG replay
     def philox_draws(self, seed, niter):
         L = int(niter) + 1

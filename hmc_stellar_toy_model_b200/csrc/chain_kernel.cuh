@@ -18,6 +18,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace srhmc {
 
@@ -79,6 +80,12 @@ __device__ __forceinline__ void refresh_metric(const ChainConst& K, ChainState& 
     s.tphi = fma(-0.5 * uw, w, dxx);
 }
 
+// data pixel as double: plain load, or exact uint32 count through the 2^52 trick (one DADD, no conversion unit)
+__device__ __forceinline__ double ld_pix(const double* p) { return *p; }
+__device__ __forceinline__ double ld_pix(const unsigned int* p) {
+    return __hiloint2double(0x43300000, (int)*p) - 4503599627370496.0;
+}
+
 template <int LPC>
 __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
@@ -87,15 +94,15 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // Pixel part of the gradient (and of V) for one chain; all lanes of the warp must call it together.
-template <int LPC, bool WANT_V>
-__device__ __forceinline__ void chain_eval(const FieldParams& P, const double* __restrict__ sD, double2* __restrict__ rt,
-                                           int sub, ChainState& s) {
+template <int LPC, bool WANT_V, typename DT>
+__device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
+                                           const double2* __restrict__ ltab, int sub, ChainState& s) {
     constexpr int CPL = 32 / LPC;
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
     for (int i = sub; i < R; i += LPC) {
         const double u = ((double)i + 0.5) - x;
-        const double e = exp(-(u * u) * P.inv2s2);
+        const double e = exp_neg(-(u * u) * P.inv2s2);
         rt[i] = make_double2(e, e * u);
     }
     double ey[CPL], fey[CPL], eydy[CPL];
@@ -103,13 +110,14 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const double* _
     for (int c = 0; c < CPL; ++c) {
         const int j = sub + LPC * c;
         const double v = ((double)j + 0.5) - y;
-        const double e = (j < C) ? exp(-(v * v) * P.inv2s2) * P.norm : 0.0;
+        const double e = (j < C) ? exp_neg(-(v * v) * P.inv2s2) * P.norm : 0.0;
         ey[c] = e;
         fey[c] = f * e;
         eydy[c] = e * v;
     }
     __syncwarp();
     double c0[CPL], c1[CPL], vacc = 0.0;
+    int bad = 0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
 #pragma unroll 4
@@ -118,15 +126,17 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const double* _
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const double lam = fma(re.x, fey[c], P.B);
-            const double d = sD[i * kChainCS + sub + LPC * c];
+            const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
             const double rho = fma(d, rcp_fast(lam), -1.0);
             c0[c] = fma(rho, re.x, c0[c]);
             c1[c] = fma(rho, re.y, c1[c]);
             if (WANT_V) {
-                if (sub + LPC * c < C) vacc += lam - d * log(lam);
+                bad |= (__double2hiint(lam) < 0x00100000);  // Lambda <= 0 or subnormal: ln undefined -> NaN below
+                if (sub + LPC * c < C) vacc += fma(-d, log_pos(lam, ltab), lam);
             }
         }
     }
+    if (WANT_V && bad) vacc = CUDART_NAN;
     __syncwarp();  // row table is rewritten by the next evaluation
     double sf = 0.0, sx = 0.0, sy = 0.0;
 #pragma unroll
@@ -159,9 +169,10 @@ __device__ __forceinline__ void chain_energies(const FieldParams& P, const Chain
 
 // base_class.RHMC_single_step for a one-star field, state in registers (sampler_RHMC.py:522-566).
 // Requires s.g*, s.u, s.kap, s.ihxx, s.tphi valid at s.f on entry; leaves them valid on exit.
-template <int LPC>
-__device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const double* sD, double2* rt, int sub,
-                                           ChainState& s, int counter_max, bool want_V, int& cnt_p, int& cnt_q) {
+template <int LPC, typename DT>
+__device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const DT* sD, double2* rt,
+                                           const double2* ltab, int sub, ChainState& s, int counter_max, bool want_V,
+                                           int& cnt_p, int& cnt_q) {
     const double h = K.h;
     // (1) p <- p - h dphi/dq(q)
     {
@@ -213,9 +224,9 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     s.pf = fma(-(K.hh * s.kap), s.pf * s.pf, s.pf);
     // (5) gradient at the new q and last half kick
     if (want_V)
-        chain_eval<LPC, true>(P, sD, rt, sub, s);
+        chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
     else
-        chain_eval<LPC, false>(P, sD, rt, sub, s);
+        chain_eval<LPC, false>(P, sD, rt, ltab, sub, s);
     {
         double gf = s.gf + s.tphi;
         if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
@@ -229,25 +240,32 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py = -s.py;
 }
 
-template <int LPC>
-__global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
+template <int LPC, typename DT>
+__global__ void __launch_bounds__(128, 4) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
-    const int lane = threadIdx.x, grp = lane / LPC, sub = lane % LPC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int grp = lane / LPC, sub = lane % LPC;
     const int R = P.R, C = P.C;
     const size_t img_elems = (size_t)R * kChainCS;
-    double* sD = reinterpret_cast<double*>(smem_raw) + (size_t)grp * img_elems;
-    double2* rt = reinterpret_cast<double2*>(smem_raw + (size_t)GPW * img_elems * sizeof(double)) + (size_t)grp * R;
+    const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * sizeof(double2));
+    double2* ltab = reinterpret_cast<double2*>(smem_raw);
+    unsigned char* wbase = smem_raw + kLogTableSize * sizeof(double2) + (size_t)warp * warp_bytes;
+    DT* sD = reinterpret_cast<DT*>(wbase) + (size_t)grp * img_elems;
+    double2* rt = reinterpret_cast<double2*>(wbase + (size_t)GPW * img_elems * sizeof(DT)) + (size_t)grp * R;
     const double h = A.dt / 2.0;
+    for (int i = threadIdx.x; i < kLogTableSize; i += blockDim.x) ltab[i] = A.log_table[i];
+    __syncthreads();
 
-    for (int base = blockIdx.x * GPW; base < A.n_fields; base += gridDim.x * GPW) {
+    const int chains_per_block = nw * GPW;
+    for (int base = blockIdx.x * chains_per_block + warp * GPW; base < A.n_fields; base += gridDim.x * chains_per_block) {
         const bool live = base + grp < A.n_fields;
         const int field = live ? base + grp : A.n_fields - 1;  // idle group shadows a valid chain, writes nothing
         constexpr int n = 1;  // the host routes only exactly-one-star batches to this kernel
-        const double* gD = reinterpret_cast<const double*>(A.D) + (size_t)field * R * C;
+        const DT* gD = reinterpret_cast<const DT*>(sizeof(DT) == 8 ? A.D : (const void*)A.D_u32) + (size_t)field * R * C;
         __syncwarp();
         for (int i = 0; i < R; ++i)
-            for (int j = sub; j < kChainCS; j += LPC) sD[i * kChainCS + j] = (j < C) ? gD[i * C + j] : 0.0;
+            for (int j = sub; j < kChainCS; j += LPC) sD[i * kChainCS + j] = (j < C) ? gD[i * C + j] : (DT)0;
         ChainState s;
         const double* q_in = A.q_in + (size_t)field * 3;
         s.f = n ? q_in[0] : 0.0;
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
         int cp = 0, cq = 0;
 
         if (A.mode == MODE_EVAL) {
-            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
             refresh_metric(K, s);
             double V, T;
             chain_energies(P, K, s, A.f_pos, V, T);
@@ -283,9 +301,9 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
         } else if (A.mode == MODE_STEP) {
-            chain_eval<LPC, false>(P, sD, rt, sub, s);
+            chain_eval<LPC, false>(P, sD, rt, ltab, sub, s);
             refresh_metric(K, s);
-            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, false, cp, cq);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, false, cp, cq);
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
             }
         } else if (A.mode == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
-            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
             refresh_metric(K, s);
             double V0, T0;
             chain_energies(P, K, s, A.f_pos, V0, T0);
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                 A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
             }
             for (int t = 1; t <= A.nsteps; ++t) {
-                chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, true, cp, cq);
+                chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, true, cp, cq);
                 double V, T;
                 chain_energies(P, K, s, A.f_pos, V, T);
                 if (writer) {
@@ -321,7 +339,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
         } else {  // MODE_RUN
             const size_t rows = (size_t)A.n_rows;
             const int L = A.niter + 1;
-            chain_eval<LPC, true>(P, sD, rt, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
             int n_acc = 0;
             for (int l = 0; l < L; ++l) {
                 if (A.gff2_sched && l < A.n_gff2) {
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const __grid_constant__ Field
                     if (A.T_chain) A.T_chain[row] = T0;
                 }
                 for (int t = 0; t < A.nsteps; ++t)
-                    chain_step<LPC>(P, K, sD, rt, sub, s, A.counter_max, t == A.nsteps - 1, cp, cq);
+                    chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, V1, T1);
                 const double dE = (V1 + T1) - E0;

@@ -1,42 +1,48 @@
-// Warp-resident one-star chain kernel: instantiation, occupancy plan and launcher.
+// Warp-resident one-star chain kernel: instantiations, occupancy plan, launcher, and the device-math test hook.
 #include <algorithm>
+#include <cmath>
 
 #include "chain_kernel.cuh"
 #include "kernels_api.h"
 
 namespace srhmc {
 
-static size_t chain_smem_bytes(const FieldParams& P, int lpc) {
+namespace {
+
+constexpr int kLPC = 16;
+constexpr int kWarpsPerBlock = 4;
+
+size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     const size_t gpw = 32 / lpc;
-    return gpw * ((size_t)P.R * kChainCS * sizeof(double) + (size_t)P.R * sizeof(double2));
+    const size_t per_warp = gpw * ((size_t)P.R * kChainCS * elem + (size_t)P.R * sizeof(double2));
+    return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
-    plan.lpc = 16;
-    plan.smem = chain_smem_bytes(P, plan.lpc);
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+template <typename DT>
+int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
+    smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT));
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<16>, 32, plan.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT>, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
-    plan.max_warps_per_sm = nb;
+    blocks_per_sm = nb;
     return 0;
 }
 
-// Grid = (warps per SM) x SMs with the warps-per-SM count chosen so that every SM runs the same number of equally
-// long rounds (chains of one launch all take the same number of iterations).
-static int chain_grid(const ChainLaunchPlan& plan, int n_fields, int sms) {
-    const int gpw = 32 / plan.lpc;
-    const long long warps = ((long long)n_fields + gpw - 1) / gpw;
-    const long long cap = (long long)plan.max_warps_per_sm * sms;
-    if (warps <= cap) return (int)warps;
-    int best_k = plan.max_warps_per_sm;
+// Grid = (blocks per SM) x SMs with the per-SM count chosen so that every SM runs the same number of equally long
+// rounds (all chains of one launch run the same number of iterations).
+int balanced_grid(int max_blocks_per_sm, long long blocks_needed, int sms) {
+    const long long cap = (long long)max_blocks_per_sm * sms;
+    if (blocks_needed <= cap) return (int)std::max<long long>(1, blocks_needed);
+    int best_k = max_blocks_per_sm;
     long long best_cost = -1;
-    for (int k = plan.max_warps_per_sm; k >= std::max(1, plan.max_warps_per_sm / 2); --k) {
-        const long long rounds = (warps + (long long)k * sms - 1) / ((long long)k * sms);
+    for (int k = max_blocks_per_sm; k >= std::max(1, (max_blocks_per_sm + 1) / 2); --k) {
+        const long long rounds = (blocks_needed + (long long)k * sms - 1) / ((long long)k * sms);
         const long long cost = rounds * k;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
@@ -46,10 +52,70 @@ static int chain_grid(const ChainLaunchPlan& plan, int n_fields, int sms) {
     return best_k * sms;
 }
 
-int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms,
-                               cudaStream_t stream) {
-    const int grid = chain_grid(plan, A.n_fields, sms);
-    chain_kernel<16><<<grid, 32, plan.smem, stream>>>(P, A);
+__global__ void math_test_kernel(int which, const double* x, double* y, int n, const double2* log_table) {
+    __shared__ double2 tab[kLogTableSize];
+    for (int i = threadIdx.x; i < kLogTableSize; i += blockDim.x) tab[i] = log_table[i];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double v = x[i];
+        y[i] = which == 0 ? exp_neg(v) : (which == 1 ? log_pos(v, tab) : rcp_fast(v));
+    }
+}
+
+// exact-count image check + conversion (1 flag word: set when a pixel is not a uint32-representable integer)
+__global__ void to_u32_kernel(const double* src, unsigned int* dst, size_t n, int* not_exact) {
+    int bad = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = src[i];
+        const bool ok = (v >= 0.0) && (v <= 4294967295.0) && (v == floor(v));
+        bad |= !ok;
+        dst[i] = ok ? (unsigned int)v : 0u;
+    }
+    if (bad) atomicOr(not_exact, 1);
+}
+
+}  // namespace
+
+void fill_log_table(double* host_table /* [kLogTableSize*2] */) {
+    for (int k = 0; k < kLogTableSize; ++k) {
+        const long double c = 1.0L + ((long double)k + 0.5L) / (long double)kLogTableSize;
+        const double rc = (double)(1.0L / c);
+        host_table[2 * k] = rc;
+        host_table[2 * k + 1] = (double)(-logl((long double)rc));
+    }
+}
+
+int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
+    plan.lpc = kLPC;
+    plan.nw = kWarpsPerBlock;
+    int rc = configure_one<double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
+    if (rc != 0) return rc;
+    rc = configure_one<unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
+    return rc;
+}
+
+int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, cudaStream_t stream) {
+    const int chains_per_block = plan.nw * (32 / plan.lpc);
+    const long long blocks = ((long long)A.n_fields + chains_per_block - 1) / chains_per_block;
+    if (A.D_u32 != nullptr) {
+        const int grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
+        chain_kernel<kLPC, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
+    } else {
+        const int grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
+        chain_kernel<kLPC, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
+    }
+    return (int)cudaGetLastError();
+}
+
+int math_test_launch(cudaStream_t stream, int which, const double* x, double* y, int n, const double* log_table) {
+    math_test_kernel<<<std::max(1, std::min(1024, (n + 255) / 256)), 256, 0, stream>>>(
+        which, x, y, n, reinterpret_cast<const double2*>(log_table));
+    return (int)cudaGetLastError();
+}
+
+int to_u32_launch(cudaStream_t stream, const double* src, unsigned int* dst, size_t n, int* not_exact_flag) {
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 4096));
+    to_u32_kernel<<<blocks, 256, 0, stream>>>(src, dst, n, not_exact_flag);
     return (int)cudaGetLastError();
 }
 

@@ -34,6 +34,8 @@ struct LaunchArgs {
     int mode;
     int n_fields;
     const void* D;          // [n_images, R*C] in the pixel type
+    const unsigned int* D_u32;  // same images as exact uint32 counts, or nullptr (chain kernel, lossless)
+    const double2* log_table;   // fastmath.cuh reciprocal/log table [128]
     const int* nstars;      // [F] or nullptr
     // state in / out
     const double* q_in;     // [F,S]

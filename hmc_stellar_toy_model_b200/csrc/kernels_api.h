@@ -9,9 +9,10 @@
 namespace srhmc {
 
 struct ChainLaunchPlan {
-    int lpc = 16;
-    int max_warps_per_sm = 0;
-    size_t smem = 0;
+    int lpc = 16;   // lanes per chain
+    int nw = 4;     // warps per block
+    size_t smem_f64 = 0, smem_u32 = 0;
+    int blocks_per_sm_f64 = 0, blocks_per_sm_u32 = 0;
 };
 
 // CTA-per-field kernel (field_kernel.cuh); precision 64|32, (mr, mc) in {(2,4), (2,2), (1,2)}
@@ -26,6 +27,10 @@ int convert_image_launch(cudaStream_t stream, const double* src, float* dst, siz
 // warp-resident one-star kernel (chain_kernel.cuh), FP64
 int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan);
 int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, cudaStream_t stream);
+
+void fill_log_table(double* host_table /* [256]: (rc_k, lc_k) pairs */);
+int math_test_launch(cudaStream_t stream, int which, const double* x, double* y, int n, const double* log_table);
+int to_u32_launch(cudaStream_t stream, const double* src, unsigned int* dst, size_t n, int* not_exact_flag);
 
 // FMA-chain roofline microbenchmark
 int fma_peak_run(int precision, int sms, double* tflops, float* ms);

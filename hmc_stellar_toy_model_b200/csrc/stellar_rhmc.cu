@@ -81,6 +81,8 @@ struct srhmc_ctx {
     ChainLaunchPlan chain_plan;
     size_t pix_bytes = 8;
     // device buffers
+    DevBuf D32, logtab, flag;       // exact uint32 copy of the images, fastmath log table, scratch flag
+    bool d_u32_ok = false;
     DevBuf D, Dstage, q, p, nstars, normals, lnu, sg, sb, qchain, pchain, E, V, T, A, acc, scratch, qout, pout, Vout,
         grad, H, Hg, counts;
     // sizes of the last uploaded run
@@ -281,6 +283,18 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     }
     c->stream = c->own_stream;
     c->timed = true;
+    {
+        double tab[256];
+        fill_log_table(tab);
+        int rc2 = c->logtab.ensure(sizeof(tab));
+        if (rc2 == 0 && cudaMemcpy(c->logtab.ptr, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc2 = fail(SRHMC_ERR_CUDA, "log table upload failed");
+        if (rc2 == 0) rc2 = c->flag.ensure(16);
+        if (rc2 != 0) {
+            srhmc_destroy(c);
+            return rc2;
+        }
+    }
     *out = c;
     return 0;
 }
@@ -289,7 +303,7 @@ int srhmc_destroy(srhmc_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
+    DevBuf* all[] = {&c->D32, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
                      &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout,
                      &c->grad, &c->H, &c->Hg, &c->counts};
     for (DevBuf* b : all) b->release();
@@ -341,6 +355,20 @@ int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
         if (e != 0) return fail(SRHMC_ERR_CUDA, "image conversion failed: %s", cudaGetErrorString((cudaError_t)e));
         c->launches += 1;
     }
+    c->d_u32_ok = false;
+    if (c->chain_ok && c->cfg.precision == 64) {
+        // lossless compact copy for the warp-resident kernel when every pixel is an integer count (Poisson data)
+        if (int rc = c->D32.ensure(n * 4)) return rc;
+        CU_TRY(cudaMemsetAsync(c->flag.ptr, 0, 4, c->stream));
+        const int e = to_u32_launch(c->stream, c->D.as<double>(), c->D32.as<unsigned int>(), n, c->flag.as<int>());
+        if (e != 0) return fail(SRHMC_ERR_CUDA, "count conversion failed: %s", cudaGetErrorString((cudaError_t)e));
+        c->launches += 1;
+        int not_exact = 1;
+        CU_TRY(cudaMemcpyAsync(&not_exact, c->flag.ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        const char* off = std::getenv("SRHMC_DISABLE_U32_IMAGES");
+        c->d_u32_ok = (not_exact == 0) && !(off && off[0] == '1');
+    }
     CU_TRY(cudaStreamSynchronize(c->stream));
     c->have_data = true;
     return 0;
@@ -372,6 +400,8 @@ int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_p
     A.mode = MODE_EVAL;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
+    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
     A.f_pos = f_pos;
@@ -415,6 +445,8 @@ int srhmc_step(srhmc_ctx* c, double* q, double* p, const int32_t* nstars, int32_
     A.mode = MODE_STEP;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
+    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
     A.p_in = c->p.as<double>();
@@ -493,6 +525,8 @@ int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
     A.mode = MODE_RUN;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
+    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = c->run_has_nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
     A.q_out = c->qout.as<double>();
@@ -573,6 +607,8 @@ int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int
     A.mode = MODE_SINGLE;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
+    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
     A.p_in = c->p.as<double>();
@@ -615,6 +651,19 @@ int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* norma
     CU_TRY(cudaStreamSynchronize(c->stream));
     c->run_has_normals = false;  // the staging buffers were overwritten
     c->run_has_lnu = false;
+    return 0;
+}
+
+int srhmc_test_device_math(srhmc_ctx* c, int32_t which, const double* x, double* y, int32_t n) {
+    if (!c || !x || !y || n < 0 || which < 0 || which > 2) return fail(SRHMC_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    if (int rc = upload(c, c->Dstage, x, std::max<size_t>((size_t)n * 8, 8))) return rc;
+    if (int rc = c->grad.ensure(std::max<size_t>((size_t)n * 8, 8))) return rc;
+    const int e = math_test_launch(c->stream, which, c->Dstage.as<double>(), c->grad.as<double>(), n, c->logtab.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "math test kernel failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (n) if (int rc = download(c, y, c->grad, (size_t)n * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -159,6 +159,10 @@ int srhmc_run_single(srhmc_ctx* ctx, const double* q0, const double* p0, const i
  * normals [F,L,S], lnu [F,L] exactly as srhmc_run would consume them for `seed`. */
 int srhmc_philox_draws(srhmc_ctx* ctx, uint64_t seed, int32_t niter, double* normals, double* lnu);
 
+/* Diagnostic: evaluate the kernels' own device math on n values (which = 0: exp_neg(x), x <= 0; 1: log_pos(x), x > 0;
+ * 2: rcp_fast(x)) so the test-suite can bound its error against libm. */
+int srhmc_test_device_math(srhmc_ctx* ctx, int32_t which, const double* x, double* y, int32_t n);
+
 /* Roofline denominator measured on the device itself: a register-resident FMA chain (8 independent chains per
  * thread, all SMs filled) in the given precision (64 or 32).  Returns TFLOP/s (2 flop per FMA) and the launch time. */
 int srhmc_measure_fma_peak(int32_t device, int32_t precision, double* tflops, float* ms);

@@ -278,3 +278,37 @@ def test_chain_kernel_matches_field_kernel_and_oracle(monkeypatch):
         assert np.array_equal(a[0].A_chain[f].astype(bool), out.A)
         assert first_divergence(a[0].q_chain[f], out.q, 1e-9) == -1
         assert relerr(a[0].E_chain[f], out.E) < RTOL
+
+
+def test_device_math_accuracy():
+    """The kernels' own exp / log / reciprocal against libm."""
+    g = golden("kat1")
+    S = setup_from(g)
+    rng = np.random.RandomState(3)
+    with make_ctx(S, max_stars=1) as ctx:
+        x = -rng.uniform(0, 250, 20000) ** rng.choice([1.0, 0.5, 2.0], 20000) % 650.0
+        x[:4] = [0.0, -1e-300, -700.0, -1e-9]
+        y = ctx.device_math(0, x)
+        assert np.max(np.abs(y - np.exp(x)) / np.exp(x)) < 5e-16
+        v = np.concatenate([rng.uniform(1e-3, 1e6, 20000), 10 ** rng.uniform(-300, 300, 2000), [1.0, 2.0, 0.5, 24.98]])
+        w = ctx.device_math(1, v)
+        assert np.max(np.abs(w - np.log(v)) / np.maximum(np.abs(np.log(v)), 1.0)) < 5e-16
+        r = ctx.device_math(2, v)
+        assert np.max(np.abs(r * v - 1.0)) < 5e-16
+
+
+def test_u32_image_path_is_lossless(monkeypatch):
+    """Integer-valued data takes the compact uint32 shared-memory layout; results are bit-identical to the
+    float64 layout, and non-integer data silently uses float64."""
+    g = golden("chain_one_star_m21")
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    outs = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("SRHMC_DISABLE_U32_IMAGES", off)
+        with make_ctx(S, max_stars=1) as ctx:
+            ctx.set_data(S.D)
+            r = ctx.run(q0[None], 20, 10, 0.2, normals=g["normals"][None, :21], lnu=g["lnu"][None, :21], g_ff2=S.g_ff2)
+            outs.append(r)
+    assert np.array_equal(outs[0].q_chain, outs[1].q_chain) and np.array_equal(outs[0].E_chain, outs[1].E_chain)
+    assert np.array_equal(outs[0].A_chain, outs[1].A_chain)
