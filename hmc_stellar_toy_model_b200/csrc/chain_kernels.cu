@@ -1,6 +1,7 @@
 // Warp-resident one-star chain kernel: instantiations, occupancy plan, launcher, and the device-math test hook.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "chain_kernel.cuh"
 #include "kernels_api.h"
@@ -10,7 +11,7 @@ namespace srhmc {
 namespace {
 
 constexpr int kLPC = 16;
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 1;
 
 size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     const size_t gpw = 32 / lpc;
@@ -37,14 +38,21 @@ int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm
 // Grid = (blocks per SM) x SMs with the per-SM count chosen so that every SM runs the same number of equally long
 // rounds (all chains of one launch run the same number of iterations).
 int balanced_grid(int max_blocks_per_sm, long long blocks_needed, int sms) {
+    if (const char* env = std::getenv("SRHMC_CHAIN_BLOCKS_PER_SM")) {  // tuning / experiments
+        const int k = std::atoi(env);
+        if (k >= 1) return (int)std::min<long long>(blocks_needed, (long long)std::min(k, max_blocks_per_sm) * sms);
+    }
     const long long cap = (long long)max_blocks_per_sm * sms;
     if (blocks_needed <= cap) return (int)std::max<long long>(1, blocks_needed);
+    // k resident warps per SM run ceil(needed / (k sms)) rounds; a round costs ~k (throughput-bound) but never less
+    // than ~kSat/2 (latency-bound), so prefer the largest k among near-ties.
+    const int k_lo = std::max(1, (3 * max_blocks_per_sm) / 4);
     int best_k = max_blocks_per_sm;
-    long long best_cost = -1;
-    for (int k = max_blocks_per_sm; k >= std::max(1, (max_blocks_per_sm + 1) / 2); --k) {
+    double best_cost = -1.0;
+    for (int k = max_blocks_per_sm; k >= k_lo; --k) {
         const long long rounds = (blocks_needed + (long long)k * sms - 1) / ((long long)k * sms);
-        const long long cost = rounds * k;
-        if (best_cost < 0 || cost < best_cost) {
+        const double cost = (double)rounds * k;
+        if (best_cost < 0 || cost < best_cost * 0.97) {
             best_cost = cost;
             best_k = k;
         }

@@ -28,7 +28,7 @@ int convert_image_launch(cudaStream_t stream, const double* src, float* dst, siz
 int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan);
 int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, cudaStream_t stream);
 
-void fill_log_table(double* host_table /* [256]: (rc_k, lc_k) pairs */);
+void fill_log_table(double* host_table /* (rc_k, lc_k) pairs, at most 128 of them */);
 int math_test_launch(cudaStream_t stream, int which, const double* x, double* y, int n, const double* log_table);
 int to_u32_launch(cudaStream_t stream, const double* src, unsigned int* dst, size_t n, int* not_exact_flag);
 

@@ -284,7 +284,7 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     c->stream = c->own_stream;
     c->timed = true;
     {
-        double tab[256];
+        double tab[256] = {0};
         fill_log_table(tab);
         int rc2 = c->logtab.ensure(sizeof(tab));
         if (rc2 == 0 && cudaMemcpy(c->logtab.ptr, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess)
