@@ -241,7 +241,7 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
 }
 
 template <int LPC, typename DT>
-__global__ void __launch_bounds__(32, 20) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
+__global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

@@ -19,16 +19,16 @@ size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-template <typename DT>
+template <int LPC, typename DT>
 int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
-    smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT));
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem = chain_smem_bytes(P, LPC, nw, sizeof(DT));
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<LPC, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(chain_kernel<LPC, DT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT>, 32 * nw, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<LPC, DT>, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
     blocks_per_sm = nb;
@@ -95,10 +95,18 @@ void fill_log_table(double* host_table /* [kLogTableSize*2] */) {
 
 int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
     plan.lpc = kLPC;
+    if (const char* env = std::getenv("SRHMC_CHAIN_LPC")) {  // experiments: 8 lanes per chain (4 chains per warp)
+        if (std::atoi(env) == 8) plan.lpc = 8;
+    }
     plan.nw = kWarpsPerBlock;
-    int rc = configure_one<double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
+    if (plan.lpc == 8) {
+        int rc = configure_one<8, double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
+        if (rc != 0) return rc;
+        return configure_one<8, unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
+    }
+    int rc = configure_one<16, double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
     if (rc != 0) return rc;
-    rc = configure_one<unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
+    rc = configure_one<16, unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
     return rc;
 }
 
@@ -107,10 +115,16 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLa
     const long long blocks = ((long long)A.n_fields + chains_per_block - 1) / chains_per_block;
     if (A.D_u32 != nullptr) {
         const int grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
-        chain_kernel<kLPC, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
+        if (plan.lpc == 8)
+            chain_kernel<8, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
+        else
+            chain_kernel<16, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
     } else {
         const int grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
-        chain_kernel<kLPC, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
+        if (plan.lpc == 8)
+            chain_kernel<8, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
+        else
+            chain_kernel<16, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
     }
     return (int)cudaGetLastError();
 }
