@@ -107,6 +107,17 @@ class RHMCContext:
                                    dptr(V), dptr(grad), dptr(H), dptr(Hg)))
         return V, grad, H, Hg
 
+    # ------------------------------------------------------------------ a5/a6: T, dtaudq, dtaudp
+    def kinetic(self, q, p, nstars=None, g_ff2=1.0):
+        q = as_f64(q, (self.F, self.S))
+        p = as_f64(p, (self.F, self.S))
+        ns = self._nstars(nstars)
+        T = np.empty(self.F)
+        dq = np.zeros((self.F, self.S))
+        dp = np.zeros((self.F, self.S))
+        check(self._lib.srhmc_kinetic(self._h, dptr(q), dptr(p), iptr(ns), float(g_ff2), dptr(T), dptr(dq), dptr(dp)))
+        return T, dq, dp
+
     # ------------------------------------------------------------------ a7: RHMC_single_step
     def step(self, q, p, nsteps, dt, delta=1e-6, counter_max=1000, g_ff2=1.0, beta=1.0, nstars=None,
              return_counts=False):

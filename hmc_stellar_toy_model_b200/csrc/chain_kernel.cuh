@@ -93,19 +93,35 @@ __device__ __forceinline__ double group_sum(double v) {
     return v;
 }
 
+// log1p(t) for |t| < 2^-7 by the alternating series through t^7 (truncation t^8/8 < 2^-59 absolute).
+__device__ __forceinline__ double log1p_small(double t) {
+    double p = kFM.log1p_c[7];
+#pragma unroll
+    for (int k = 6; k >= 1; --k) p = fma(p, t, kFM.log1p_c[k]);
+    return p * t;
+}
+
 // Pixel part of the gradient (and of V) for one chain; all lanes of the warp must call it together.
+//
+// V is evaluated in the separable form (Lambda_ij = B + a_i b_j with a_i = ex_i, b_j = f ey_j):
+//   sum(Lambda - D ln Lambda) = [R C B - ln B sum(D)] + (sum_i a_i)(sum_j b_j) - sum_ij D_ij log1p(a_i b_j / B)
+// so only the last sum needs per-pixel work, and log1p is tiered per image row by the largest |t| = |a_i b_j / B| any
+// lane of the warp sees in that row: table logarithm (|t| >= 2^-7), 7-term series (2^-18 <= |t| < 2^-7) or
+// t - t^2/2 (|t| < 2^-18; truncation < 2^-55).  `vconst` is the bracketed constant of this chain's image.
 template <int LPC, bool WANT_V, typename DT>
 __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
-                                           const double2* __restrict__ ltab, int sub, ChainState& s) {
+                                           const double2* __restrict__ ltab, int sub, double vconst, ChainState& s) {
     constexpr int CPL = 32 / LPC;
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
+    double sa = 0.0;
     for (int i = sub; i < R; i += LPC) {
         const double u = ((double)i + 0.5) - x;
         const double e = exp_neg(-(u * u) * P.inv2s2);
         rt[i] = make_double2(e, e * u);
+        if (WANT_V) sa += e;
     }
-    double ey[CPL], fey[CPL], eydy[CPL];
+    double ey[CPL], fey[CPL], eydy[CPL], tb[CPL], sb = 0.0, tbmax = 0.0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
         const int j = sub + LPC * c;
@@ -114,29 +130,72 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
         ey[c] = e;
         fey[c] = f * e;
         eydy[c] = e * v;
+        if (WANT_V) {
+            tb[c] = fey[c] * P.invB;
+            sb += fey[c];
+            tbmax = fmax(tbmax, fabs(tb[c]));
+        }
     }
     __syncwarp();
-    double c0[CPL], c1[CPL], vacc = 0.0;
+    double c0[CPL], c1[CPL], vlog = 0.0;
     int bad = 0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
+    if (!WANT_V) {
 #pragma unroll 4
-    for (int i = 0; i < R; ++i) {
-        const double2 re = rt[i];
+        for (int i = 0; i < R; ++i) {
+            const double2 re = rt[i];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const double lam = fma(re.x, fey[c], P.B);
-            const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
-            const double rho = fma(d, rcp_fast(lam), -1.0);
-            c0[c] = fma(rho, re.x, c0[c]);
-            c1[c] = fma(rho, re.y, c1[c]);
-            if (WANT_V) {
-                bad |= (__double2hiint(lam) < 0x00100000);  // Lambda <= 0 or subnormal: ln undefined -> NaN below
-                if (sub + LPC * c < C) vacc += fma(-d, log_pos(lam, ltab), lam);
+            for (int c = 0; c < CPL; ++c) {
+                const double lam = fma(re.x, fey[c], P.B);
+                const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
+                const double rho = fma(d, rcp_fast(lam), -1.0);
+                c0[c] = fma(rho, re.x, c0[c]);
+                c1[c] = fma(rho, re.y, c1[c]);
+            }
+        }
+    } else {
+        for (int i = 0; i < R; ++i) {
+            const double2 re = rt[i];
+            const double tmax = re.x * tbmax;
+            const bool big = __any_sync(0xffffffffu, tmax >= 0.0078125);
+            const bool mid = __any_sync(0xffffffffu, tmax >= 3.814697265625e-06);
+            if (big) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const double lam = fma(re.x, fey[c], P.B);
+                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
+                    const double rho = fma(d, rcp_fast(lam), -1.0);
+                    c0[c] = fma(rho, re.x, c0[c]);
+                    c1[c] = fma(rho, re.y, c1[c]);
+                    const double w = fma(re.x, tb[c], 1.0);
+                    bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN below
+                    vlog = fma(d, log_pos(w, ltab), vlog);
+                }
+            } else if (mid) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const double lam = fma(re.x, fey[c], P.B);
+                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
+                    const double rho = fma(d, rcp_fast(lam), -1.0);
+                    c0[c] = fma(rho, re.x, c0[c]);
+                    c1[c] = fma(rho, re.y, c1[c]);
+                    vlog = fma(d, log1p_small(re.x * tb[c]), vlog);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const double lam = fma(re.x, fey[c], P.B);
+                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
+                    const double rho = fma(d, rcp_fast(lam), -1.0);
+                    c0[c] = fma(rho, re.x, c0[c]);
+                    c1[c] = fma(rho, re.y, c1[c]);
+                    const double t = re.x * tb[c];
+                    vlog = fma(d, fma(-0.5 * t, t, t), vlog);
+                }
             }
         }
     }
-    if (WANT_V && bad) vacc = CUDART_NAN;
     __syncwarp();  // row table is rewritten by the next evaluation
     double sf = 0.0, sx = 0.0, sy = 0.0;
 #pragma unroll
@@ -151,7 +210,13 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     s.gf = -sf;
     s.gx = -sx * f * P.inv_s2;
     s.gy = -sy * f * P.inv_s2;
-    if (WANT_V) s.Vpix = group_sum<LPC>(vacc);
+    if (WANT_V) {
+        if (bad) vlog = CUDART_NAN;
+        sa = group_sum<LPC>(sa);
+        sb = group_sum<LPC>(sb);
+        vlog = group_sum<LPC>(vlog);
+        s.Vpix = fma(sa, sb, vconst) - vlog;
+    }
 }
 
 // V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential and metric
@@ -171,8 +236,8 @@ __device__ __forceinline__ void chain_energies(const FieldParams& P, const Chain
 // Requires s.g*, s.u, s.kap, s.ihxx, s.tphi valid at s.f on entry; leaves them valid on exit.
 template <int LPC, typename DT>
 __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const DT* sD, double2* rt,
-                                           const double2* ltab, int sub, ChainState& s, int counter_max, bool want_V,
-                                           int& cnt_p, int& cnt_q) {
+                                           const double2* ltab, int sub, double vconst, ChainState& s, int counter_max,
+                                           bool want_V, int& cnt_p, int& cnt_q) {
     const double h = K.h;
     // (1) p <- p - h dphi/dq(q)
     {
@@ -224,9 +289,9 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     s.pf = fma(-(K.hh * s.kap), s.pf * s.pf, s.pf);
     // (5) gradient at the new q and last half kick
     if (want_V)
-        chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
+        chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
     else
-        chain_eval<LPC, false>(P, sD, rt, ltab, sub, s);
+        chain_eval<LPC, false>(P, sD, rt, ltab, sub, vconst, s);
     {
         double gf = s.gf + s.tphi;
         if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
@@ -247,7 +312,8 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int grp = lane / LPC, sub = lane % LPC;
     const int R = P.R, C = P.C;
-    const size_t img_elems = (size_t)R * kChainCS;
+    // per-chain image stride padded by LPC elements: the GPW chains of a warp then sit on disjoint shared-memory banks
+    const size_t img_elems = (size_t)R * kChainCS + LPC;
     const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * sizeof(double2));
     double2* ltab = reinterpret_cast<double2*>(smem_raw);
     unsigned char* wbase = smem_raw + kLogTableSize * sizeof(double2) + (size_t)warp * warp_bytes;
@@ -264,8 +330,15 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
         constexpr int n = 1;  // the host routes only exactly-one-star batches to this kernel
         const DT* gD = reinterpret_cast<const DT*>(sizeof(DT) == 8 ? A.D : (const void*)A.D_u32) + (size_t)field * R * C;
         __syncwarp();
+        double sumD = 0.0;
         for (int i = 0; i < R; ++i)
-            for (int j = sub; j < kChainCS; j += LPC) sD[i * kChainCS + j] = (j < C) ? gD[i * C + j] : (DT)0;
+            for (int j = sub; j < kChainCS; j += LPC) {
+                const DT v = (j < C) ? gD[i * C + j] : (DT)0;
+                sD[i * kChainCS + j] = v;
+                sumD += (double)v;
+            }
+        sumD = group_sum<LPC>(sumD);
+        const double vconst = fma(-P.lnB, sumD, ((double)R * (double)C) * P.B);
         ChainState s;
         const double* q_in = A.q_in + (size_t)field * 3;
         s.f = n ? q_in[0] : 0.0;
@@ -284,7 +357,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
         int cp = 0, cq = 0;
 
         if (A.mode == MODE_EVAL) {
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V, T;
             chain_energies(P, K, s, A.f_pos, V, T);
@@ -301,9 +374,9 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
         } else if (A.mode == MODE_STEP) {
-            chain_eval<LPC, false>(P, sD, rt, ltab, sub, s);
+            chain_eval<LPC, false>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
-            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, false, cp, cq);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
@@ -312,7 +385,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
             }
         } else if (A.mode == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V0, T0;
             chain_energies(P, K, s, A.f_pos, V0, T0);
@@ -323,7 +396,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                 A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
             }
             for (int t = 1; t <= A.nsteps; ++t) {
-                chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, true, cp, cq);
+                chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
                 double V, T;
                 chain_energies(P, K, s, A.f_pos, V, T);
                 if (writer) {
@@ -339,7 +412,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
         } else {  // MODE_RUN
             const size_t rows = (size_t)A.n_rows;
             const int L = A.niter + 1;
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, s);
+            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             int n_acc = 0;
             for (int l = 0; l < L; ++l) {
                 if (A.gff2_sched && l < A.n_gff2) {
@@ -374,7 +447,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                     if (A.T_chain) A.T_chain[row] = T0;
                 }
                 for (int t = 0; t < A.nsteps; ++t)
-                    chain_step<LPC>(P, K, sD, rt, ltab, sub, s, A.counter_max, t == A.nsteps - 1, cp, cq);
+                    chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, V1, T1);
                 const double dE = (V1 + T1) - E0;

@@ -23,6 +23,7 @@ struct FieldParams {
     double norm;       // 1/(2 pi sigma^2)
     double c2;         // exp(-1/sigma^2): second-order ratio of the Gaussian recurrence
     double B, f_lim, f_low;
+    double lnB, invB;  // ln(B), 1/B (chain kernel's separable potential)
     double g0, g1, g2, g_xx, g_ff;
     double alpha, Vpc, vc_pow;
 };

@@ -19,6 +19,43 @@ __global__ void philox_dump_kernel(unsigned long long seed, int n_fields, int L,
     }
 }
 
+// Kinetic energy and the tau-part derivatives of one field per block (sampler_RHMC.py:353-363, 467-492):
+//   T = (sum p^2/H + sum ln|H|)/2,  dtau/dq_f = -p_f^2 H_ff'/H_ff^2 / 2 (flux slots only),  dtau/dp = p/H.
+__global__ void kinetic_kernel(const FieldParams P, int n_fields, const double* q, const double* p, const int* nstars,
+                               double g_ff2, double* T, double* dtaudq, double* dtaudp) {
+    __shared__ double red[2 * 32];
+    const int field = blockIdx.x;
+    if (field >= n_fields) return;
+    const int N = nstars ? nstars[field] : P.Nmax;
+    const size_t S = 3 * (size_t)P.Nmax;
+    double v[2] = {0.0, 0.0};
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const size_t o = (size_t)field * S + 3 * k;
+        const Metric m = metric_of(P, q[o], g_ff2);
+        const double pf = p[o], px = p[o + 1], py = p[o + 2];
+        v[0] += pf * pf / m.Hff + px * px / m.Hxx + py * py / m.Hxx;
+        v[1] += log(fabs(m.Hff)) + 2.0 * log(fabs(m.Hxx));
+        if (dtaudq) {
+            dtaudq[o] = -((pf * pf) * m.dHff / (m.Hff * m.Hff)) / 2.0;
+            dtaudq[o + 1] = 0.0;
+            dtaudq[o + 2] = 0.0;
+        }
+        if (dtaudp) {
+            dtaudp[o] = pf / m.Hff;
+            dtaudp[o + 1] = px / m.Hxx;
+            dtaudp[o + 2] = py / m.Hxx;
+        }
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0 && T) T[field] = (v[0] + v[1]) / 2.0;
+}
+
+int kinetic_launch(cudaStream_t stream, const FieldParams& P, int n_fields, const double* q, const double* p,
+                   const int* nstars, double g_ff2, double* T, double* dtaudq, double* dtaudp) {
+    kinetic_kernel<<<n_fields > 0 ? n_fields : 1, 128, 0, stream>>>(P, n_fields, q, p, nstars, g_ff2, T, dtaudq, dtaudp);
+    return (int)cudaGetLastError();
+}
+
 template <typename T>
 __global__ void convert_image_kernel(const double* src, T* dst, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -253,6 +253,8 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.norm = 1.0 / (M_PI * 2.0 * sigma * sigma);
     P.c2 = std::exp(-1.0 / (sigma * sigma));
     P.B = cfg->B_count;
+    P.lnB = std::log(cfg->B_count);
+    P.invB = 1.0 / cfg->B_count;
     P.f_lim = cfg->f_lim;
     P.f_low = cfg->f_low;
     P.g0 = cfg->g0; P.g1 = cfg->g1; P.g2 = cfg->g2;
@@ -420,6 +422,31 @@ int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_p
     if (grad && FS) if (int rc = download(c, grad, c->grad, FS)) return rc;
     if (H && FS) if (int rc = download(c, H, c->H, FS)) return rc;
     if (Hgrad && FS) if (int rc = download(c, Hgrad, c->Hg, FS)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_kinetic(srhmc_ctx* c, const double* q, const double* p, const int32_t* nstars, double g_ff2, double* T,
+                  double* dtaudq, double* dtaudp) {
+    if (!c || !q || !p) return fail(SRHMC_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = std::max<size_t>(F * S * 8, 8);
+    if (int rc = upload(c, c->q, q, FS)) return rc;
+    if (int rc = upload(c, c->p, p, FS)) return rc;
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    if (int rc = c->Vout.ensure(F * 8)) return rc;
+    if (int rc = c->grad.ensure(FS)) return rc;
+    if (int rc = c->H.ensure(FS)) return rc;
+    CU_TRY(cudaMemsetAsync(c->grad.ptr, 0, FS, c->stream));
+    CU_TRY(cudaMemsetAsync(c->H.ptr, 0, FS, c->stream));
+    const int e = kinetic_launch(c->stream, c->P, (int)F, c->q.as<double>(), c->p.as<double>(),
+                                 nstars ? c->nstars.as<int>() : nullptr, g_ff2, c->Vout.as<double>(),
+                                 c->grad.as<double>(), c->H.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "kinetic kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (T) if (int rc = download(c, T, c->Vout, F * 8)) return rc;
+    if (dtaudq && F * S) if (int rc = download(c, dtaudq, c->grad, F * S * 8)) return rc;
+    if (dtaudp && F * S) if (int rc = download(c, dtaudp, c->H, F * S * 8)) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
