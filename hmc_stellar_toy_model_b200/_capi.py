@@ -107,8 +107,10 @@ SIGNATURES = {
     "srhmc_set_data": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
     "srhmc_eval": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_double,
                              c_double_p, c_double_p, c_double_p, c_double_p]),
+    "srhmc_metric": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_double, c_double_p, c_double_p]),
     "srhmc_kinetic": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p, C.c_double,
                                 c_double_p, c_double_p, c_double_p]),
+    "srhmc_kinetic_diag": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "srhmc_step": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_double,
                              C.c_int32, C.c_double, C.c_double, c_int32_p]),
     "srhmc_run": (C.c_int, [C.c_void_p, C.POINTER(RunArgs)]),

@@ -107,6 +107,16 @@ class RHMCContext:
                                    dptr(V), dptr(grad), dptr(H), dptr(Hg)))
         return V, grad, H, Hg
 
+    # ------------------------------------------------------------------ a4: H alone
+    def metric(self, q, g_ff2=1.0):
+        """H and dH/df for a flat array of [f, x, y] triples of any length (no image involved)."""
+        q = as_f64(q).ravel()
+        n = q.size // 3
+        H = np.zeros(3 * n)
+        Hg = np.zeros(3 * n)
+        check(self._lib.srhmc_metric(self._h, dptr(q), n, float(g_ff2), dptr(H), dptr(Hg)))
+        return H, Hg
+
     # ------------------------------------------------------------------ a5/a6: T, dtaudq, dtaudp
     def kinetic(self, q, p, nstars=None, g_ff2=1.0):
         q = as_f64(q, (self.F, self.S))
@@ -117,6 +127,15 @@ class RHMCContext:
         dp = np.zeros((self.F, self.S))
         check(self._lib.srhmc_kinetic(self._h, dptr(q), dptr(p), iptr(ns), float(g_ff2), dptr(T), dptr(dq), dptr(dp)))
         return T, dq, dp
+
+    def kinetic_diag(self, p, H_diag):
+        """T(p, H_diag) for an explicit diagonal (any length)."""
+        p = as_f64(p).ravel()
+        H = as_f64(H_diag).ravel()
+        assert p.size == H.size
+        T = np.empty(1)
+        check(self._lib.srhmc_kinetic_diag(self._h, dptr(p), dptr(H), p.size, dptr(T)))
+        return float(T[0])
 
     # ------------------------------------------------------------------ a7: RHMC_single_step
     def step(self, q, p, nsteps, dt, delta=1e-6, counter_max=1000, g_ff2=1.0, beta=1.0, nstars=None,

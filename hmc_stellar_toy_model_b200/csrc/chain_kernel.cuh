@@ -101,40 +101,132 @@ __device__ __forceinline__ double log1p_small(double t) {
     return p * t;
 }
 
+// One column slot (the lane's column sub + LPC*c) over image rows [r0, r1): gradient column sums and, per TIER, the
+// D * log1p(t) part of the potential.  TIER 0: table logarithm; 1: 7-term series (|t| < 2^-7); 2: t - t^2/2
+// (|t| < 2^-18, truncation < 2^-55); 3: gradient only.
+template <int TIER, typename DT>
+__device__ __forceinline__ void slot_rows(int r0, int r1, const DT* __restrict__ sDc, const double2* __restrict__ rt,
+                                          const double2* __restrict__ ltab, double B, double feyc, double tbc,
+                                          double& c0, double& c1, double& vlog, int& bad) {
+#pragma unroll 4
+    for (int i = r0; i < r1; ++i) {
+        const double2 re = rt[i];
+        const double lam = fma(re.x, feyc, B);
+        const double d = ld_pix(sDc + i * kChainCS);
+        const double rho = fma(d, rcp_fast(lam), -1.0);
+        c0 = fma(rho, re.x, c0);
+        c1 = fma(rho, re.y, c1);
+        if (TIER == 0) {
+            const double w = fma(re.x, tbc, 1.0);
+            bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN
+            vlog = fma(d, log_pos(w, ltab), vlog);
+        } else if (TIER == 1) {
+            vlog = fma(d, log1p_small(re.x * tbc), vlog);
+        } else if (TIER == 2) {
+            const double t = re.x * tbc;
+            vlog = fma(d, fma(-0.5 * t, t, t), vlog);
+        }
+    }
+}
+
+// Rows i whose Gaussian weight exp(-(i+.5-x)^2/2s^2) can reach `thresh / peak` (peak >= 0): the conservative integer
+// window [lo, hi) in float arithmetic, empty (lo = R, hi = 0) when peak < thresh.  NaN-safe.
+__device__ __forceinline__ void row_window(float xc, float peak, float thresh, float two_s2, int R, int& lo, int& hi) {
+    lo = R;
+    hi = 0;
+    if (peak >= thresh) {
+        const float w = sqrtf(__logf(peak / thresh) * two_s2) + 0.51f;
+        lo = (int)fminf(fmaxf(floorf(xc - w), 0.0f), (float)R);
+        hi = (int)fminf(fmaxf(ceilf(xc + w) + 1.0f, 0.0f), (float)R);
+    }
+}
+
 // Pixel part of the gradient (and of V) for one chain; all lanes of the warp must call it together.
+//
+// Tables: lane `sub` owns rows sub + LPC k and columns sub + LPC c.  Along that stride the Gaussian obeys
+//   e(u + L) = e(u) r(u),  r(u + L) = r(u) exp(-L^2/s^2),  r(u) = exp(-(2 L u + L^2)/2s^2)
+// so each lane evaluates two exponentials per axis and multiplies its way along (error a few ulp per step).
+//
+// Rows farther than P.wcut pixels from the star have ex_i < 2^-50: their pixels change neither the gradient sums nor
+// V beyond 1e-13 relative, and are skipped (the window is the union over the chains of the warp).
 //
 // V is evaluated in the separable form (Lambda_ij = B + a_i b_j with a_i = ex_i, b_j = f ey_j):
 //   sum(Lambda - D ln Lambda) = [R C B - ln B sum(D)] + (sum_i a_i)(sum_j b_j) - sum_ij D_ij log1p(a_i b_j / B)
-// so only the last sum needs per-pixel work, and log1p is tiered per image row by the largest |t| = |a_i b_j / B| any
-// lane of the warp sees in that row: table logarithm (|t| >= 2^-7), 7-term series (2^-18 <= |t| < 2^-7) or
-// t - t^2/2 (|t| < 2^-18; truncation < 2^-55).  `vconst` is the bracketed constant of this chain's image.
+// so only the last sum needs per-pixel work; log1p is tiered per (column slot, row range) by the largest
+// |t| = |a_i b_j / B| the warp sees there (see slot_rows).  `vconst` is the bracketed constant of this chain's image.
 template <int LPC, bool WANT_V, typename DT>
 __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
                                            const double2* __restrict__ ltab, int sub, double vconst, ChainState& s) {
     constexpr int CPL = 32 / LPC;
+    constexpr unsigned FULL = 0xffffffffu;
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
+    const double cL = (LPC == 8) ? P.cL8 : P.cL16;  // exp(-LPC^2/s^2)
     double sa = 0.0;
-    for (int i = sub; i < R; i += LPC) {
-        const double u = ((double)i + 0.5) - x;
-        const double e = exp_neg(-(u * u) * P.inv2s2);
-        rt[i] = make_double2(e, e * u);
-        if (WANT_V) sa += e;
-    }
-    double ey[CPL], fey[CPL], eydy[CPL], tb[CPL], sb = 0.0, tbmax = 0.0;
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-        const int j = sub + LPC * c;
-        const double v = ((double)j + 0.5) - y;
-        const double e = (j < C) ? exp_neg(-(v * v) * P.inv2s2) * P.norm : 0.0;
-        ey[c] = e;
-        fey[c] = f * e;
-        eydy[c] = e * v;
-        if (WANT_V) {
-            tb[c] = fey[c] * P.invB;
-            sb += fey[c];
-            tbmax = fmax(tbmax, fabs(tb[c]));
+    {
+        // rows: anchor at the lane's row nearest the star and recur outwards in both directions, so the anchor never
+        // underflows while the star is within ~55 px of the image (beyond that every weight is 0 in double anyway)
+        const int K = (R - sub + LPC - 1) / LPC;
+        if (K > 0) {
+            const double kf = fmin(fmax(rint((x - 0.5 - (double)sub) * (1.0 / LPC)), 0.0), (double)(K - 1));
+            const int ks = (int)kf;
+            const double us = ((double)(sub + LPC * ks) + 0.5) - x;
+            const double arg = (us * us) * P.inv2s2;
+            const bool ok = arg < 690.0;
+            const double es = ok ? exp_neg(-arg) : 0.0;
+            const double r_up = ok ? exp_neg(-fma(2.0 * LPC, us, (double)(LPC * LPC)) * P.inv2s2) : 0.0;
+            const double r_dn = ok ? exp_neg(fma(2.0 * LPC, us, -(double)(LPC * LPC)) * P.inv2s2) : 0.0;
+            double e = es, r = r_up, u = us;
+            for (int k = ks; k < K; ++k) {
+                rt[sub + LPC * k] = make_double2(e, e * u);
+                if (WANT_V) sa += e;
+                e *= r;
+                r *= cL;
+                u += (double)LPC;
+            }
+            e = es * r_dn;
+            r = r_dn * cL;
+            u = us - (double)LPC;
+            for (int k = ks - 1; k >= 0; --k) {
+                rt[sub + LPC * k] = make_double2(e, e * u);
+                if (WANT_V) sa += e;
+                e *= r;
+                r *= cL;
+                u -= (double)LPC;
+            }
         }
+    }
+    double ey[CPL], fey[CPL], eydy[CPL], tb[CPL], sb = 0.0;
+    {
+        // columns: at most 32 of them, so the first column's weight cannot underflow for a star near the image
+        double v = ((double)sub + 0.5) - y;
+        const double arg = (v * v) * P.inv2s2;
+        const bool ok = arg < 690.0;
+        double e = ok ? exp_neg(-arg) * P.norm : 0.0;
+        double r = ok ? exp_neg(-fma(2.0 * LPC, v, (double)(LPC * LPC)) * P.inv2s2) : 0.0;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const bool in = sub + LPC * c < C;
+            ey[c] = in ? e : 0.0;
+            fey[c] = f * ey[c];
+            eydy[c] = ey[c] * v;
+            if (WANT_V) {
+                tb[c] = fey[c] * P.invB;
+                sb += fey[c];
+            }
+            e *= r;
+            r *= cL;
+            v += (double)LPC;
+        }
+    }
+    // row window of the warp
+    int i_lo, i_hi;
+    {
+        const double xc = x - 0.5;
+        const int lo = (int)fmin(fmax(ceil(xc - P.wcut), 0.0), (double)R);
+        const int hi = (int)fmin(fmax(floor(xc + P.wcut) + 1.0, 0.0), (double)R);
+        i_lo = __reduce_min_sync(FULL, lo);
+        i_hi = __reduce_max_sync(FULL, hi);
     }
     __syncwarp();
     double c0[CPL], c1[CPL], vlog = 0.0;
@@ -143,7 +235,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
     if (!WANT_V) {
 #pragma unroll 4
-        for (int i = 0; i < R; ++i) {
+        for (int i = i_lo; i < i_hi; ++i) {
             const double2 re = rt[i];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
@@ -155,45 +247,27 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             }
         }
     } else {
-        for (int i = 0; i < R; ++i) {
-            const double2 re = rt[i];
-            const double tmax = re.x * tbmax;
-            const bool big = __any_sync(0xffffffffu, tmax >= 0.0078125);
-            const bool mid = __any_sync(0xffffffffu, tmax >= 3.814697265625e-06);
-            if (big) {
+        const float xc = (float)(x - 0.5), two_s2 = (float)(1.0 / P.inv2s2);
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const double lam = fma(re.x, fey[c], P.B);
-                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
-                    const double rho = fma(d, rcp_fast(lam), -1.0);
-                    c0[c] = fma(rho, re.x, c0[c]);
-                    c1[c] = fma(rho, re.y, c1[c]);
-                    const double w = fma(re.x, tb[c], 1.0);
-                    bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN below
-                    vlog = fma(d, log_pos(w, ltab), vlog);
-                }
-            } else if (mid) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const double lam = fma(re.x, fey[c], P.B);
-                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
-                    const double rho = fma(d, rcp_fast(lam), -1.0);
-                    c0[c] = fma(rho, re.x, c0[c]);
-                    c1[c] = fma(rho, re.y, c1[c]);
-                    vlog = fma(d, log1p_small(re.x * tb[c]), vlog);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const double lam = fma(re.x, fey[c], P.B);
-                    const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
-                    const double rho = fma(d, rcp_fast(lam), -1.0);
-                    c0[c] = fma(rho, re.x, c0[c]);
-                    c1[c] = fma(rho, re.y, c1[c]);
-                    const double t = re.x * tb[c];
-                    vlog = fma(d, fma(-0.5 * t, t, t), vlog);
-                }
-            }
+        for (int c = 0; c < CPL; ++c) {
+            const float peak = fabsf((float)tb[c]) * 1.0001f;
+            int n0, n1, m0, m1;
+            row_window(xc, peak, 0.0078125f, two_s2, R, n0, n1);          // |t| >= 2^-7
+            row_window(xc, peak, 3.814697265625e-06f, two_s2, R, m0, m1);  // |t| >= 2^-18
+            n0 = __reduce_min_sync(FULL, n0);
+            n1 = __reduce_max_sync(FULL, n1);
+            m0 = __reduce_min_sync(FULL, m0);
+            m1 = __reduce_max_sync(FULL, m1);
+            m0 = min(max(m0, i_lo), i_hi);
+            m1 = min(max(m1, m0), i_hi);
+            n0 = min(max(n0, m0), m1);
+            n1 = min(max(n1, n0), m1);
+            const DT* sDc = sD + sub + LPC * c;
+            slot_rows<2>(i_lo, m0, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
+            slot_rows<1>(m0, n0, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
+            slot_rows<0>(n0, n1, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
+            slot_rows<1>(n1, m1, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
+            slot_rows<2>(m1, i_hi, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
         }
     }
     __syncwarp();  // row table is rewritten by the next evaluation

@@ -22,6 +22,9 @@ int field_kernel_launch(int precision, int mr, int mc, int grid, int threads, si
                         const FieldParams& P, const LaunchArgs& A, double* scratch, int d_in_smem);
 int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, double* normals,
                        double* lnu);
+int metric_launch(cudaStream_t stream, const FieldParams& P, size_t n_stars, const double* q, double g_ff2, double* H,
+                  double* Hgrad);
+int kinetic_diag_launch(cudaStream_t stream, size_t n, const double* p, const double* H, double* T);
 int kinetic_launch(cudaStream_t stream, const FieldParams& P, int n_fields, const double* q, const double* p,
                    const int* nstars, double g_ff2, double* T, double* dtaudq, double* dtaudp);
 int convert_image_launch(cudaStream_t stream, const double* src, float* dst, size_t n);

@@ -50,6 +50,39 @@ __global__ void kinetic_kernel(const FieldParams P, int n_fields, const double* 
     if (threadIdx.x == 0 && T) T[field] = (v[0] + v[1]) / 2.0;
 }
 
+// Diagonal metric and its flux derivative for n flat [f, x, y] triples (sampler_RHMC.py:229-292).
+__global__ void metric_kernel(const FieldParams P, size_t n_stars, const double* q, double g_ff2, double* H, double* Hgrad) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n_stars; k += (size_t)gridDim.x * blockDim.x) {
+        const Metric m = metric_of(P, q[3 * k], g_ff2);
+        if (H) { H[3 * k] = m.Hff; H[3 * k + 1] = m.Hxx; H[3 * k + 2] = m.Hxx; }
+        if (Hgrad) { Hgrad[3 * k] = m.dHff; Hgrad[3 * k + 1] = m.dHxx; Hgrad[3 * k + 2] = m.dHxx; }
+    }
+}
+
+int metric_launch(cudaStream_t stream, const FieldParams& P, size_t n_stars, const double* q, double g_ff2, double* H,
+                  double* Hgrad) {
+    const int blocks = (int)((n_stars + 127) / 128 < 4096 ? (n_stars + 127) / 128 : 4096);
+    metric_kernel<<<blocks > 0 ? blocks : 1, 128, 0, stream>>>(P, n_stars, q, g_ff2, H, Hgrad);
+    return (int)cudaGetLastError();
+}
+
+// T(p, H_diag) = (sum p^2/H + sum ln|H|)/2 for an explicit diagonal (sampler_RHMC.py:353-363); one block.
+__global__ void kinetic_diag_kernel(size_t n, const double* p, const double* H, double* T) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0.0, 0.0};
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        v[0] += p[i] * p[i] / H[i];
+        v[1] += log(fabs(H[i]));
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) T[0] = (v[0] + v[1]) / 2.0;
+}
+
+int kinetic_diag_launch(cudaStream_t stream, size_t n, const double* p, const double* H, double* T) {
+    kinetic_diag_kernel<<<1, 256, 0, stream>>>(n, p, H, T);
+    return (int)cudaGetLastError();
+}
+
 int kinetic_launch(cudaStream_t stream, const FieldParams& P, int n_fields, const double* q, const double* p,
                    const int* nstars, double g_ff2, double* T, double* dtaudq, double* dtaudp) {
     kinetic_kernel<<<n_fields > 0 ? n_fields : 1, 128, 0, stream>>>(P, n_fields, q, p, nstars, g_ff2, T, dtaudq, dtaudp);

@@ -255,6 +255,9 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.B = cfg->B_count;
     P.lnB = std::log(cfg->B_count);
     P.invB = 1.0 / cfg->B_count;
+    P.cL8 = std::exp(-64.0 / (sigma * sigma));
+    P.cL16 = std::exp(-256.0 / (sigma * sigma));
+    P.wcut = std::sqrt(50.0 * M_LN2 * 2.0 * sigma * sigma);
     P.f_lim = cfg->f_lim;
     P.f_low = cfg->f_low;
     P.g0 = cfg->g0; P.g1 = cfg->g1; P.g2 = cfg->g2;
@@ -426,6 +429,22 @@ int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_p
     return 0;
 }
 
+int srhmc_metric(srhmc_ctx* c, const double* q, int64_t n_stars, double g_ff2, double* H, double* Hgrad) {
+    if (!c || !q || n_stars < 0) return fail(SRHMC_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t bytes = std::max<size_t>((size_t)n_stars * 24, 8);
+    if (int rc = upload(c, c->q, q, bytes)) return rc;
+    if (int rc = c->H.ensure(bytes)) return rc;
+    if (int rc = c->Hg.ensure(bytes)) return rc;
+    const int e = metric_launch(c->stream, c->P, (size_t)n_stars, c->q.as<double>(), g_ff2, c->H.as<double>(), c->Hg.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "metric kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (H && n_stars) if (int rc = download(c, H, c->H, (size_t)n_stars * 24)) return rc;
+    if (Hgrad && n_stars) if (int rc = download(c, Hgrad, c->Hg, (size_t)n_stars * 24)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int srhmc_kinetic(srhmc_ctx* c, const double* q, const double* p, const int32_t* nstars, double g_ff2, double* T,
                   double* dtaudq, double* dtaudp) {
     if (!c || !q || !p) return fail(SRHMC_ERR_INVALID, "null argument");
@@ -447,6 +466,21 @@ int srhmc_kinetic(srhmc_ctx* c, const double* q, const double* p, const int32_t*
     if (T) if (int rc = download(c, T, c->Vout, F * 8)) return rc;
     if (dtaudq && F * S) if (int rc = download(c, dtaudq, c->grad, F * S * 8)) return rc;
     if (dtaudp && F * S) if (int rc = download(c, dtaudp, c->H, F * S * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_kinetic_diag(srhmc_ctx* c, const double* p, const double* H_diag, int64_t n, double* T) {
+    if (!c || !p || !H_diag || !T || n < 0) return fail(SRHMC_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t bytes = std::max<size_t>((size_t)n * 8, 8);
+    if (int rc = upload(c, c->p, p, bytes)) return rc;
+    if (int rc = upload(c, c->H, H_diag, bytes)) return rc;
+    if (int rc = c->Vout.ensure(8)) return rc;
+    const int e = kinetic_diag_launch(c->stream, (size_t)n, c->p.as<double>(), c->H.as<double>(), c->Vout.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "kinetic kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (int rc = download(c, T, c->Vout, 8)) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -136,10 +136,18 @@ int srhmc_set_data(srhmc_ctx* ctx, const double* D, int64_t n_images);
 int srhmc_eval(srhmc_ctx* ctx, const double* q, const int32_t* nstars, int32_t f_pos, double g_ff2, double beta,
                double* V, double* grad, double* H, double* Hgrad);
 
+/* Diagonal metric alone (no image needed).  Replaces base_class.H / H_xx / H_ff (sampler_RHMC.py:229-292).
+ * q [n_stars*3] flat [f,x,y] triples (any count, independent of the context's field shape);
+ * H, Hgrad [n_stars*3] = [H_ff,H_xx,H_xx] and their d/df (either may be NULL). */
+int srhmc_metric(srhmc_ctx* ctx, const double* q, int64_t n_stars, double g_ff2, double* H, double* Hgrad);
+
 /* Kinetic part per field.  Replaces base_class.T (sampler_RHMC.py:353-363), dtaudq (:467-483), dtaudp (:485-492).
  * q, p [F,S]; outputs (any may be NULL): T [F] = (sum p^2/H + sum ln|H|)/2 with H = H(q), dtaudq [F,S], dtaudp [F,S]. */
 int srhmc_kinetic(srhmc_ctx* ctx, const double* q, const double* p, const int32_t* nstars, double g_ff2,
                   double* T, double* dtaudq, double* dtaudp);
+
+/* T for an explicit diagonal H_diag, as base_class.T(p, H_diag) takes it (sampler_RHMC.py:353-363): p, H_diag [n]. */
+int srhmc_kinetic_diag(srhmc_ctx* ctx, const double* p, const double* H_diag, int64_t n, double* T);
 
 /* nsteps generalised-leapfrog steps in place.  Replaces base_class.RHMC_single_step (sampler_RHMC.py:522-566).
  * fp_counts, if not NULL, receives [F,2]: the two fixed-point iteration counts of the LAST step. */
