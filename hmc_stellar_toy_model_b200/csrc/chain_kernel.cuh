@@ -101,30 +101,34 @@ __device__ __forceinline__ double log1p_small(double t) {
     return p * t;
 }
 
-// One column slot (the lane's column sub + LPC*c) over image rows [r0, r1): gradient column sums and, per TIER, the
+// Image rows [r0, r1), all column slots of the lane (columns sub + LPC c): gradient column sums and, per TIER, the
 // D * log1p(t) part of the potential.  TIER 0: table logarithm; 1: 7-term series (|t| < 2^-7); 2: t - t^2/2
-// (|t| < 2^-18, truncation < 2^-55); 3: gradient only.
-template <int TIER, typename DT>
-__device__ __forceinline__ void slot_rows(int r0, int r1, const DT* __restrict__ sDc, const double2* __restrict__ rt,
-                                          const double2* __restrict__ ltab, double B, double feyc, double tbc,
-                                          double& c0, double& c1, double& vlog, int& bad) {
-#pragma unroll 4
+// (|t| < 2^-18, truncation < 2^-55).
+template <int TIER, int LPC, typename DT>
+__device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restrict__ sDl, const double2* __restrict__ rt,
+                                               const double2* __restrict__ ltab, double B, const double (&fey)[32 / LPC],
+                                               const double (&tb)[32 / LPC], double (&c0)[32 / LPC],
+                                               double (&c1)[32 / LPC], double& vlog, int& bad) {
+    constexpr int CPL = 32 / LPC;
     for (int i = r0; i < r1; ++i) {
         const double2 re = rt[i];
-        const double lam = fma(re.x, feyc, B);
-        const double d = ld_pix(sDc + i * kChainCS);
-        const double rho = fma(d, rcp_fast(lam), -1.0);
-        c0 = fma(rho, re.x, c0);
-        c1 = fma(rho, re.y, c1);
-        if (TIER == 0) {
-            const double w = fma(re.x, tbc, 1.0);
-            bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN
-            vlog = fma(d, log_pos(w, ltab), vlog);
-        } else if (TIER == 1) {
-            vlog = fma(d, log1p_small(re.x * tbc), vlog);
-        } else if (TIER == 2) {
-            const double t = re.x * tbc;
-            vlog = fma(d, fma(-0.5 * t, t, t), vlog);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const double lam = fma(re.x, fey[c], B);
+            const double d = ld_pix(sDl + i * kChainCS + LPC * c);
+            const double rho = fma(d, rcp_fast(lam), -1.0);
+            c0[c] = fma(rho, re.x, c0[c]);
+            c1[c] = fma(rho, re.y, c1[c]);
+            if (TIER == 0) {
+                const double w = fma(re.x, tb[c], 1.0);
+                bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN
+                vlog = fma(d, log_pos(w, ltab), vlog);
+            } else if (TIER == 1) {
+                vlog = fma(d, log1p_small(re.x * tb[c]), vlog);
+            } else {
+                const double t = re.x * tb[c];
+                vlog = fma(d, fma(-0.5 * t, t, t), vlog);
+            }
         }
     }
 }
@@ -152,8 +156,10 @@ __device__ __forceinline__ void row_window(float xc, float peak, float thresh, f
 //
 // V is evaluated in the separable form (Lambda_ij = B + a_i b_j with a_i = ex_i, b_j = f ey_j):
 //   sum(Lambda - D ln Lambda) = [R C B - ln B sum(D)] + (sum_i a_i)(sum_j b_j) - sum_ij D_ij log1p(a_i b_j / B)
-// so only the last sum needs per-pixel work; log1p is tiered per (column slot, row range) by the largest
-// |t| = |a_i b_j / B| the warp sees there (see slot_rows).  `vconst` is the bracketed constant of this chain's image.
+// so only the last sum needs per-pixel work; log1p is tiered per row range by the largest |t| = |a_i b_j / B| the
+// warp sees there (see rows_all_slots).  Code size matters here: a build that unrolled per-slot tier loops grew the
+// kernel to 30k instructions and spent 31% of its issue slots waiting for instruction fetch, so the kernel is
+// specialised per mode (template MODE) and the tier loops are kept compact.  `vconst` is the bracketed constant of this chain's image.
 template <int LPC, bool WANT_V, typename DT>
 __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
                                            const double2* __restrict__ ltab, int sub, double vconst, ChainState& s) {
@@ -162,48 +168,52 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
     const double cL = (LPC == 8) ? P.cL8 : P.cL16;  // exp(-LPC^2/s^2)
+    // All exponentials of this evaluation up front in one straight-line block (four independent Horner chains).
+    // rows: anchor at the lane's row nearest the star and recur outwards in both directions, so the anchor never
+    // underflows while the star is within ~55 px of the image (beyond that every weight is 0 in double anyway);
+    // columns: at most 32 of them, so the first column's weight cannot underflow for a star near the image.
+    const int K = (R - sub + LPC - 1) / LPC;  // rows of this lane
+    const double kf = fmin(fmax(rint((x - 0.5 - (double)sub) * (1.0 / LPC)), 0.0), (double)(K > 0 ? K - 1 : 0));
+    const int ks = (int)kf;
+    const double us = ((double)(sub + LPC * ks) + 0.5) - x;
+    const double v0 = ((double)sub + 0.5) - y;
+    const double arg_r = (us * us) * P.inv2s2, arg_c = (v0 * v0) * P.inv2s2;
+    const bool ok_r = arg_r < 690.0, ok_c = arg_c < 690.0;
+    const double LL = (double)(LPC * LPC);
+    const double e_r = exp_neg(-arg_r);
+    const double w_r = exp_neg(-(2.0 * LPC * P.inv2s2) * us);   // r_up = w cLh, r_dn = cLh / w, cLh = exp(-L^2/2s^2)
+    const double e_c = exp_neg(-arg_c);
+    const double r_c = exp_neg(-fma(2.0 * LPC, v0, LL) * P.inv2s2);
+    const double cLh = (LPC == 8) ? P.cLh8 : P.cLh16;
     double sa = 0.0;
-    {
-        // rows: anchor at the lane's row nearest the star and recur outwards in both directions, so the anchor never
-        // underflows while the star is within ~55 px of the image (beyond that every weight is 0 in double anyway)
-        const int K = (R - sub + LPC - 1) / LPC;
-        if (K > 0) {
-            const double kf = fmin(fmax(rint((x - 0.5 - (double)sub) * (1.0 / LPC)), 0.0), (double)(K - 1));
-            const int ks = (int)kf;
-            const double us = ((double)(sub + LPC * ks) + 0.5) - x;
-            const double arg = (us * us) * P.inv2s2;
-            const bool ok = arg < 690.0;
-            const double es = ok ? exp_neg(-arg) : 0.0;
-            const double r_up = ok ? exp_neg(-fma(2.0 * LPC, us, (double)(LPC * LPC)) * P.inv2s2) : 0.0;
-            const double r_dn = ok ? exp_neg(fma(2.0 * LPC, us, -(double)(LPC * LPC)) * P.inv2s2) : 0.0;
-            double e = es, r = r_up, u = us;
-            for (int k = ks; k < K; ++k) {
-                rt[sub + LPC * k] = make_double2(e, e * u);
-                if (WANT_V) sa += e;
-                e *= r;
-                r *= cL;
-                u += (double)LPC;
-            }
-            e = es * r_dn;
-            r = r_dn * cL;
-            u = us - (double)LPC;
-            for (int k = ks - 1; k >= 0; --k) {
-                rt[sub + LPC * k] = make_double2(e, e * u);
-                if (WANT_V) sa += e;
-                e *= r;
-                r *= cL;
-                u -= (double)LPC;
-            }
+    if (K > 0) {
+        const double es = ok_r ? e_r : 0.0;
+        const double r_up = ok_r ? w_r * cLh : 0.0;
+        const double r_dn = ok_r ? rcp_fast(w_r) * cLh : 0.0;
+        double e = es, r = r_up, u = us;
+        for (int k = ks; k < K; ++k) {
+            rt[sub + LPC * k] = make_double2(e, e * u);
+            if (WANT_V) sa += e;
+            e *= r;
+            r *= cL;
+            u += (double)LPC;
+        }
+        e = es * r_dn;
+        r = r_dn * cL;
+        u = us - (double)LPC;
+        for (int k = ks - 1; k >= 0; --k) {
+            rt[sub + LPC * k] = make_double2(e, e * u);
+            if (WANT_V) sa += e;
+            e *= r;
+            r *= cL;
+            u -= (double)LPC;
         }
     }
     double ey[CPL], fey[CPL], eydy[CPL], tb[CPL], sb = 0.0;
     {
-        // columns: at most 32 of them, so the first column's weight cannot underflow for a star near the image
-        double v = ((double)sub + 0.5) - y;
-        const double arg = (v * v) * P.inv2s2;
-        const bool ok = arg < 690.0;
-        double e = ok ? exp_neg(-arg) * P.norm : 0.0;
-        double r = ok ? exp_neg(-fma(2.0 * LPC, v, (double)(LPC * LPC)) * P.inv2s2) : 0.0;
+        double v = v0;
+        double e = ok_c ? e_c * P.norm : 0.0;
+        double r = ok_c ? r_c : 0.0;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const bool in = sub + LPC * c < C;
@@ -247,28 +257,28 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             }
         }
     } else {
-        const float xc = (float)(x - 0.5), two_s2 = (float)(1.0 / P.inv2s2);
+        // row tiers from the largest |t| any lane of the warp can see in a row: [n0, n1) table log, [m0, m1) series
+        float peak = 0.0f;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const float peak = fabsf((float)tb[c]) * 1.0001f;
-            int n0, n1, m0, m1;
-            row_window(xc, peak, 0.0078125f, two_s2, R, n0, n1);          // |t| >= 2^-7
-            row_window(xc, peak, 3.814697265625e-06f, two_s2, R, m0, m1);  // |t| >= 2^-18
-            n0 = __reduce_min_sync(FULL, n0);
-            n1 = __reduce_max_sync(FULL, n1);
-            m0 = __reduce_min_sync(FULL, m0);
-            m1 = __reduce_max_sync(FULL, m1);
-            m0 = min(max(m0, i_lo), i_hi);
-            m1 = min(max(m1, m0), i_hi);
-            n0 = min(max(n0, m0), m1);
-            n1 = min(max(n1, n0), m1);
-            const DT* sDc = sD + sub + LPC * c;
-            slot_rows<2>(i_lo, m0, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
-            slot_rows<1>(m0, n0, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
-            slot_rows<0>(n0, n1, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
-            slot_rows<1>(n1, m1, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
-            slot_rows<2>(m1, i_hi, sDc, rt, ltab, P.B, fey[c], tb[c], c0[c], c1[c], vlog, bad);
-        }
+        for (int c = 0; c < CPL; ++c) peak = fmaxf(peak, fabsf((float)tb[c]));
+        peak *= 1.0001f;
+        const float xc = (float)(x - 0.5), two_s2 = (float)(1.0 / P.inv2s2);
+        int n0, n1, m0, m1;
+        row_window(xc, peak, 0.0078125f, two_s2, R, n0, n1);          // |t| >= 2^-7
+        row_window(xc, peak, 3.814697265625e-06f, two_s2, R, m0, m1);  // |t| >= 2^-18
+        n0 = __reduce_min_sync(FULL, n0);
+        n1 = __reduce_max_sync(FULL, n1);
+        m0 = __reduce_min_sync(FULL, m0);
+        m1 = __reduce_max_sync(FULL, m1);
+        m0 = min(max(m0, i_lo), i_hi);
+        m1 = min(max(m1, m0), i_hi);
+        n0 = min(max(n0, m0), m1);
+        n1 = min(max(n1, n0), m1);
+        rows_all_slots<2, LPC>(i_lo, m0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<1, LPC>(m0, n0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<0, LPC>(n0, n1, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<1, LPC>(n1, m1, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<2, LPC>(m1, i_hi, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
     }
     __syncwarp();  // row table is rewritten by the next evaluation
     double sf = 0.0, sx = 0.0, sy = 0.0;
@@ -379,7 +389,7 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py = -s.py;
 }
 
-template <int LPC, typename DT>
+template <int LPC, typename DT, int MODE>
 __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
         ChainConst K = make_chain_const(P, g_ff2, h, A.delta);
         int cp = 0, cq = 0;
 
-        if (A.mode == MODE_EVAL) {
+        if (MODE == MODE_EVAL) {
             chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V, T;
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                 if (A.H_out) { A.H_out[o] = m.Hff; A.H_out[o + 1] = m.Hxx; A.H_out[o + 2] = m.Hxx; }
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
-        } else if (A.mode == MODE_STEP) {
+        } else if (MODE == MODE_STEP) {
             chain_eval<LPC, false>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                 A.p_out[o] = s.pf; A.p_out[o + 1] = s.px; A.p_out[o + 2] = s.py;
                 if (A.fp_counts) { A.fp_counts[2 * field] = cp; A.fp_counts[2 * field + 1] = cq; }
             }
-        } else if (A.mode == MODE_SINGLE) {
+        } else if (MODE == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
             chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);

@@ -19,20 +19,39 @@ size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-template <int LPC, typename DT>
-int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
-    smem = chain_smem_bytes(P, LPC, nw, sizeof(DT));
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<LPC, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int LPC, typename DT, int MODE>
+int configure_mode(size_t smem, int nw, int& blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<LPC, DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<LPC, DT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(chain_kernel<LPC, DT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<LPC, DT>, 32 * nw, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<LPC, DT, MODE>, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
-    blocks_per_sm = nb;
+    blocks_per_sm = blocks_per_sm == 0 ? nb : std::min(blocks_per_sm, nb);
     return 0;
+}
+
+template <int LPC, typename DT>
+int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
+    smem = chain_smem_bytes(P, LPC, nw, sizeof(DT));
+    blocks_per_sm = 0;
+    if (int rc = configure_mode<LPC, DT, MODE_EVAL>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<LPC, DT, MODE_STEP>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<LPC, DT, MODE_RUN>(smem, nw, blocks_per_sm)) return rc;
+    return configure_mode<LPC, DT, MODE_SINGLE>(smem, nw, blocks_per_sm);
+}
+
+template <int LPC, typename DT>
+void launch_mode(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
+    switch (A.mode) {
+        case MODE_EVAL: chain_kernel<LPC, DT, MODE_EVAL><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_STEP: chain_kernel<LPC, DT, MODE_STEP><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_SINGLE: chain_kernel<LPC, DT, MODE_SINGLE><<<grid, threads, smem, stream>>>(P, A); break;
+        default: chain_kernel<LPC, DT, MODE_RUN><<<grid, threads, smem, stream>>>(P, A); break;
+    }
 }
 
 // Grid = (blocks per SM) x SMs with the per-SM count chosen so that every SM runs the same number of equally long
@@ -116,15 +135,15 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLa
     if (A.D_u32 != nullptr) {
         const int grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
         if (plan.lpc == 8)
-            chain_kernel<8, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
+            launch_mode<8, unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);
         else
-            chain_kernel<16, unsigned int><<<grid, 32 * plan.nw, plan.smem_u32, stream>>>(P, A);
+            launch_mode<16, unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);
     } else {
         const int grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
         if (plan.lpc == 8)
-            chain_kernel<8, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
+            launch_mode<8, double>(grid, 32 * plan.nw, plan.smem_f64, stream, P, A);
         else
-            chain_kernel<16, double><<<grid, 32 * plan.nw, plan.smem_f64, stream>>>(P, A);
+            launch_mode<16, double>(grid, 32 * plan.nw, plan.smem_f64, stream, P, A);
     }
     return (int)cudaGetLastError();
 }

@@ -25,6 +25,7 @@ struct FieldParams {
     double B, f_lim, f_low;
     double lnB, invB;  // ln(B), 1/B (chain kernel's separable potential)
     double cL8, cL16;  // exp(-64/sigma^2), exp(-256/sigma^2): stride-8 / stride-16 Gaussian recurrences
+    double cLh8, cLh16;  // their square roots exp(-L^2/2 sigma^2)
     double wcut;       // |i + .5 - x| beyond which exp(-(..)^2/2 sigma^2) < 2^-50
     double g0, g1, g2, g_xx, g_ff;
     double alpha, Vpc, vc_pow;

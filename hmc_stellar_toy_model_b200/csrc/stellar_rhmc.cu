@@ -257,6 +257,8 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.invB = 1.0 / cfg->B_count;
     P.cL8 = std::exp(-64.0 / (sigma * sigma));
     P.cL16 = std::exp(-256.0 / (sigma * sigma));
+    P.cLh8 = std::exp(-32.0 / (sigma * sigma));
+    P.cLh16 = std::exp(-128.0 / (sigma * sigma));
     P.wcut = std::sqrt(50.0 * M_LN2 * 2.0 * sigma * sigma);
     P.f_lim = cfg->f_lim;
     P.f_low = cfg->f_low;
