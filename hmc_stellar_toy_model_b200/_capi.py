@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstellar_rhmc.so")
+LIB_PATH = os.environ.get("SRHMC_LIB") or os.path.join(_HERE, "libstellar_rhmc.so")  # SRHMC_LIB: experimental builds
 ABI_VERSION = 1
 
 c_double_p = C.POINTER(C.c_double)

@@ -80,11 +80,28 @@ __device__ __forceinline__ void refresh_metric(const ChainConst& K, ChainState& 
     s.tphi = fma(-0.5 * uw, w, dxx);
 }
 
-// data pixel as double: plain load, or exact uint32 count through the 2^52 trick (one DADD, no conversion unit)
+// data pixel as double: plain load, or exact unsigned count
 __device__ __forceinline__ double ld_pix(const double* p) { return *p; }
-__device__ __forceinline__ double ld_pix(const unsigned int* p) {
-    return __hiloint2double(0x43300000, (int)*p) - 4503599627370496.0;
+// integer count -> double: one I2F on the (otherwise idle) conversion unit; measured 9% faster than the 2^52 bias trick
+// (a MOV plus a DADD on the FP64 pipe)
+__device__ __forceinline__ double ld_pix(const unsigned int* p) { return (double)*p; }
+__device__ __forceinline__ double ld_pix(const unsigned short* p) { return (double)(unsigned int)*p; }
+#ifdef SRHMC_EXP_NEWTON2
+// EXPERIMENT (not adopted): one quadratic Newton step is 8% faster but its 2^-40 error grows to 1e-8 in q over 30
+// Metropolis iterations, beyond the 1e-9 trajectory tolerance of the parity tests
+__device__ __forceinline__ double rcp_pix(double a) {
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
+    return fma(x0, fma(-a, x0, 1.0), x0);
 }
+#else
+__device__ __forceinline__ double rcp_pix(double a) { return rcp_fast(a); }
+#endif
+
+// Elements of padding after each chain image so that the chains of one warp sit on disjoint shared-memory banks:
+// the LPC lanes of a chain read LPC consecutive pixels, so shifting chain g by g*LPC pixels tiles the banks.
+template <typename DT>
+__host__ __device__ constexpr int chain_pad(int lpc) { return lpc; }
 
 template <int LPC>
 __device__ __forceinline__ double group_sum(double v) {
@@ -116,7 +133,7 @@ __device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restr
         for (int c = 0; c < CPL; ++c) {
             const double lam = fma(re.x, fey[c], B);
             const double d = ld_pix(sDl + i * kChainCS + LPC * c);
-            const double rho = fma(d, rcp_fast(lam), -1.0);
+            const double rho = fma(d, rcp_pix(lam), -1.0);
             c0[c] = fma(rho, re.x, c0[c]);
             c1[c] = fma(rho, re.y, c1[c]);
             if (TIER == 0) {
@@ -251,7 +268,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             for (int c = 0; c < CPL; ++c) {
                 const double lam = fma(re.x, fey[c], P.B);
                 const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
-                const double rho = fma(d, rcp_fast(lam), -1.0);
+                const double rho = fma(d, rcp_pix(lam), -1.0);
                 c0[c] = fma(rho, re.x, c0[c]);
                 c1[c] = fma(rho, re.y, c1[c]);
             }
@@ -389,15 +406,15 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py = -s.py;
 }
 
-template <int LPC, typename DT, int MODE>
-__global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
+template <int LPC, typename DT, int MODE, int MAXREG = 168>
+__global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int grp = lane / LPC, sub = lane % LPC;
     const int R = P.R, C = P.C;
     // per-chain image stride padded by LPC elements: the GPW chains of a warp then sit on disjoint shared-memory banks
-    const size_t img_elems = (size_t)R * kChainCS + LPC;
+    const size_t img_elems = (size_t)R * kChainCS + chain_pad<DT>(LPC);
     const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * sizeof(double2));
     double2* ltab = reinterpret_cast<double2*>(smem_raw);
     unsigned char* wbase = smem_raw + kLogTableSize * sizeof(double2) + (size_t)warp * warp_bytes;
@@ -407,12 +424,20 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
     for (int i = threadIdx.x; i < kLogTableSize; i += blockDim.x) ltab[i] = A.log_table[i];
     __syncthreads();
 
-    const int chains_per_block = nw * GPW;
-    for (int base = blockIdx.x * chains_per_block + warp * GPW; base < A.n_fields; base += gridDim.x * chains_per_block) {
+    // Work items are (group of GPW chains, chunk of Metropolis iterations); chunk c of a group may run on a different
+    // warp than chunk c-1 (the chain state travels through global memory, ordered by a per-group counter), which
+    // lets a batch that is not a multiple of the resident warp count finish without a long under-filled tail.
+    const int G = (A.n_fields + GPW - 1) / GPW;
+    const int n_chunks = (MODE == MODE_RUN && A.n_chunks > 1) ? A.n_chunks : 1;
+    const long long n_tasks = (long long)G * n_chunks;
+    const long long gw = (long long)blockIdx.x * nw + warp, W = (long long)gridDim.x * nw;
+    for (long long task = gw; task < n_tasks; task += W) {
+        const int chunk = (int)(task / G);
+        const int base = (int)(task % G) * GPW;
         const bool live = base + grp < A.n_fields;
         const int field = live ? base + grp : A.n_fields - 1;  // idle group shadows a valid chain, writes nothing
         constexpr int n = 1;  // the host routes only exactly-one-star batches to this kernel
-        const DT* gD = reinterpret_cast<const DT*>(sizeof(DT) == 8 ? A.D : (const void*)A.D_u32) + (size_t)field * R * C;
+        const DT* gD = reinterpret_cast<const DT*>(sizeof(DT) == 8 ? A.D : A.D_int) + (size_t)field * R * C;
         __syncwarp();
         double sumD = 0.0;
         for (int i = 0; i < R; ++i)
@@ -496,11 +521,36 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
         } else {  // MODE_RUN
             const size_t rows = (size_t)A.n_rows;
             const int L = A.niter + 1;
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+            const int Lc = (L + n_chunks - 1) / n_chunks;
+            const int l0 = chunk * Lc, l1 = min(L, l0 + Lc);
+            const int grp_id = base / GPW;
             int n_acc = 0;
-            for (int l = 0; l < L; ++l) {
-                if (A.gff2_sched && l < A.n_gff2) {
-                    g_ff2 = A.gff2_sched[l];
+            if (chunk == 0) {
+                chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+            } else {
+                // wait until the previous chunk of this group has published its state (bounded spin: a scheduler
+                // fault must not hang the device)
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    while (*((volatile int*)A.sched_done + grp_id) < chunk) {
+                        if (clock64() - t0 > 120000000000LL) {  // ~60 s
+                            atomicExch(A.sched_err, 1);
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
+                }
+                __syncwarp();
+                __threadfence();
+                const double* st = A.sched_state + (size_t)field * 8;
+                s.f = __ldcg(st); s.x = __ldcg(st + 1); s.y = __ldcg(st + 2);
+                s.gf = __ldcg(st + 3); s.gx = __ldcg(st + 4); s.gy = __ldcg(st + 5);
+                s.Vpix = __ldcg(st + 6);
+                n_acc = (int)__ldcg(st + 7);
+            }
+            for (int l = l0; l < l1; ++l) {
+                if (A.gff2_sched && A.n_gff2 > 0) {
+                    g_ff2 = A.gff2_sched[min(l, A.n_gff2 - 1)];  // stays at the last entry once the schedule ends
                     K = make_chain_const(P, g_ff2, h, A.delta);
                 }
                 refresh_metric(K, s);
@@ -546,9 +596,22 @@ __global__ void __launch_bounds__(32, (LPC >= 16 ? 20 : 10)) chain_kernel(const 
                     s.Vpix = s0.Vpix;
                 }
             }
-            if (writer) {
-                if (A.q_out) { A.q_out[(size_t)field * 3] = s.f; A.q_out[(size_t)field * 3 + 1] = s.x; A.q_out[(size_t)field * 3 + 2] = s.y; }
-                if (A.accept_rate) A.accept_rate[field] = (double)n_acc / (double)L;
+            if (l1 >= L) {
+                if (writer) {
+                    if (A.q_out) { A.q_out[(size_t)field * 3] = s.f; A.q_out[(size_t)field * 3 + 1] = s.x; A.q_out[(size_t)field * 3 + 2] = s.y; }
+                    if (A.accept_rate) A.accept_rate[field] = (double)n_acc / (double)L;
+                }
+            } else {
+                if (writer) {
+                    double* st = A.sched_state + (size_t)field * 8;
+                    __stcg(st, s.f); __stcg(st + 1, s.x); __stcg(st + 2, s.y);
+                    __stcg(st + 3, s.gf); __stcg(st + 4, s.gx); __stcg(st + 5, s.gy);
+                    __stcg(st + 6, s.Vpix);
+                    __stcg(st + 7, (double)n_acc);
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicExch(A.sched_done + grp_id, chunk + 1);
             }
         }
     }

@@ -19,38 +19,51 @@ size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-template <int LPC, typename DT, int MODE>
+template <typename DT, int MODE>
 int configure_mode(size_t smem, int nw, int& blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<LPC, DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<LPC, DT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<LPC, DT, MODE>, 32 * nw, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT, MODE>, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
     blocks_per_sm = blocks_per_sm == 0 ? nb : std::min(blocks_per_sm, nb);
     return 0;
 }
 
-template <int LPC, typename DT>
+template <typename DT>
 int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
-    smem = chain_smem_bytes(P, LPC, nw, sizeof(DT));
+    smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT));
     blocks_per_sm = 0;
-    if (int rc = configure_mode<LPC, DT, MODE_EVAL>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<LPC, DT, MODE_STEP>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<LPC, DT, MODE_RUN>(smem, nw, blocks_per_sm)) return rc;
-    return configure_mode<LPC, DT, MODE_SINGLE>(smem, nw, blocks_per_sm);
+    if (int rc = configure_mode<DT, MODE_EVAL>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_STEP>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_RUN>(smem, nw, blocks_per_sm)) return rc;
+    return configure_mode<DT, MODE_SINGLE>(smem, nw, blocks_per_sm);
 }
 
-template <int LPC, typename DT>
+// EXPERIMENT: register-capped variants of the uint16 run kernel (SRHMC_CHAIN_MINB = 128 | 112 | 104 registers)
+template <int MINB>
+int configure_minb(size_t smem, int& nb) {
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, 32, smem);
+    return (int)e;
+}
+int g_minb = 0, g_minb_blocks = 0;
+
+template <typename DT>
 void launch_mode(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
     switch (A.mode) {
-        case MODE_EVAL: chain_kernel<LPC, DT, MODE_EVAL><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_STEP: chain_kernel<LPC, DT, MODE_STEP><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_SINGLE: chain_kernel<LPC, DT, MODE_SINGLE><<<grid, threads, smem, stream>>>(P, A); break;
-        default: chain_kernel<LPC, DT, MODE_RUN><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_EVAL: chain_kernel<kLPC, DT, MODE_EVAL><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_STEP: chain_kernel<kLPC, DT, MODE_STEP><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_SINGLE: chain_kernel<kLPC, DT, MODE_SINGLE><<<grid, threads, smem, stream>>>(P, A); break;
+        default: chain_kernel<kLPC, DT, MODE_RUN><<<grid, threads, smem, stream>>>(P, A); break;
     }
 }
 
@@ -89,16 +102,19 @@ __global__ void math_test_kernel(int which, const double* x, double* y, int n, c
     }
 }
 
-// exact-count image check + conversion (1 flag word: set when a pixel is not a uint32-representable integer)
-__global__ void to_u32_kernel(const double* src, unsigned int* dst, size_t n, int* not_exact) {
+// exact-count image check + conversion.  flags bit 0: a pixel is not a uint32-representable integer; bit 1: a pixel
+// exceeds 65535 (the uint16 copy is then unusable).
+__global__ void to_counts_kernel(const double* src, unsigned int* dst32, unsigned short* dst16, size_t n, int* flags) {
     int bad = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const double v = src[i];
         const bool ok = (v >= 0.0) && (v <= 4294967295.0) && (v == floor(v));
-        bad |= !ok;
-        dst[i] = ok ? (unsigned int)v : 0u;
+        bad |= ok ? 0 : 1;
+        bad |= (ok && v <= 65535.0) ? 0 : 2;
+        dst32[i] = ok ? (unsigned int)v : 0u;
+        dst16[i] = (ok && v <= 65535.0) ? (unsigned short)v : (unsigned short)0;
     }
-    if (bad) atomicOr(not_exact, 1);
+    if (bad) atomicOr(flags, bad);
 }
 
 }  // namespace
@@ -114,36 +130,59 @@ void fill_log_table(double* host_table /* [kLogTableSize*2] */) {
 
 int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
     plan.lpc = kLPC;
-    if (const char* env = std::getenv("SRHMC_CHAIN_LPC")) {  // experiments: 16 lanes per chain (2 chains per warp)
-        if (std::atoi(env) == 16) plan.lpc = 16;
-    }
     plan.nw = kWarpsPerBlock;
-    if (plan.lpc == 8) {
-        int rc = configure_one<8, double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
-        if (rc != 0) return rc;
-        return configure_one<8, unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
+    if (int rc = configure_one<double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64)) return rc;
+    if (int rc = configure_one<unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32)) return rc;
+    if (int rc = configure_one<unsigned short>(P, plan.nw, plan.smem_u16, plan.blocks_per_sm_u16)) return rc;
+    g_minb = 0;
+    if (const char* env = std::getenv("SRHMC_CHAIN_MINB")) {
+        g_minb = std::atoi(env);
+        int rc = 0;
+        if (g_minb == 128) rc = configure_minb<128>(plan.smem_u16, g_minb_blocks);
+        else if (g_minb == 112) rc = configure_minb<112>(plan.smem_u16, g_minb_blocks);
+        else if (g_minb == 104) rc = configure_minb<104>(plan.smem_u16, g_minb_blocks);
+        else g_minb = 0;
+        if (rc) return rc;
     }
-    int rc = configure_one<16, double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64);
-    if (rc != 0) return rc;
-    rc = configure_one<16, unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32);
-    return rc;
+    return 0;
 }
 
-int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, cudaStream_t stream) {
+// Iteration chunks per chain for a MODE_RUN launch of `groups` warp-sized work items on `warps` resident warps.
+// One chunk when everything is resident at once (or the chains are short); otherwise enough chunks that the
+// under-filled last round costs a few percent instead of up to half the launch.
+int pick_chunks(long long groups, long long warps, int L) {
+    if (const char* env = std::getenv("SRHMC_CHAIN_CHUNKS")) {
+        const int c = std::atoi(env);
+        if (c >= 1) return std::max(1, std::min(c, L));
+    }
+    if (groups <= warps || L < 64) return 1;
+    return std::max(1, std::min(16, L / 32));
+}
+
+int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const ChainLaunchPlan& plan, int sms, cudaStream_t stream) {
+    LaunchArgs A = A_in;
     const int chains_per_block = plan.nw * (32 / plan.lpc);
     const long long blocks = ((long long)A.n_fields + chains_per_block - 1) / chains_per_block;
-    if (A.D_u32 != nullptr) {
-        const int grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
-        if (plan.lpc == 8)
-            launch_mode<8, unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);
-        else
-            launch_mode<16, unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);
+    int grid;
+    const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
+    const bool minb = u16 && A.mode == MODE_RUN && g_minb > 0;
+    if (minb) grid = balanced_grid(g_minb_blocks, blocks, sms);
+    else if (u16) grid = balanced_grid(plan.blocks_per_sm_u16, blocks, sms);
+    else if (A.D_int != nullptr) grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
+    else grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
+    A.n_chunks = 1;
+    if (A.mode == MODE_RUN && A.sched_done != nullptr)
+        A.n_chunks = pick_chunks(blocks, (long long)grid * plan.nw, A.niter + 1);
+    if (minb) {
+        if (g_minb == 128) chain_kernel<kLPC, unsigned short, MODE_RUN, 128><<<grid, 32, plan.smem_u16, stream>>>(P, A);
+        else if (g_minb == 112) chain_kernel<kLPC, unsigned short, MODE_RUN, 112><<<grid, 32, plan.smem_u16, stream>>>(P, A);
+        else chain_kernel<kLPC, unsigned short, MODE_RUN, 104><<<grid, 32, plan.smem_u16, stream>>>(P, A);
+    } else if (u16) {
+        launch_mode<unsigned short>(grid, 32 * plan.nw, plan.smem_u16, stream, P, A);
+    } else if (A.D_int != nullptr) {
+        launch_mode<unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);
     } else {
-        const int grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
-        if (plan.lpc == 8)
-            launch_mode<8, double>(grid, 32 * plan.nw, plan.smem_f64, stream, P, A);
-        else
-            launch_mode<16, double>(grid, 32 * plan.nw, plan.smem_f64, stream, P, A);
+        launch_mode<double>(grid, 32 * plan.nw, plan.smem_f64, stream, P, A);
     }
     return (int)cudaGetLastError();
 }
@@ -154,9 +193,10 @@ int math_test_launch(cudaStream_t stream, int which, const double* x, double* y,
     return (int)cudaGetLastError();
 }
 
-int to_u32_launch(cudaStream_t stream, const double* src, unsigned int* dst, size_t n, int* not_exact_flag) {
+int to_counts_launch(cudaStream_t stream, const double* src, unsigned int* dst32, unsigned short* dst16, size_t n,
+                     int* flags) {
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 4096));
-    to_u32_kernel<<<blocks, 256, 0, stream>>>(src, dst, n, not_exact_flag);
+    to_counts_kernel<<<blocks, 256, 0, stream>>>(src, dst32, dst16, n, flags);
     return (int)cudaGetLastError();
 }
 

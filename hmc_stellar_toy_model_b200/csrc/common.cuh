@@ -38,7 +38,8 @@ struct LaunchArgs {
     int mode;
     int n_fields;
     const void* D;          // [n_images, R*C] in the pixel type
-    const unsigned int* D_u32;  // same images as exact uint32 counts, or nullptr (chain kernel, lossless)
+    const void* D_int;      // same images as exact unsigned integer counts, or nullptr (chain kernel, lossless)
+    int D_int_bytes;        // 4: uint32, 2: uint16 (every count < 65536)
     const double2* log_table;   // fastmath.cuh reciprocal/log table [128]
     const int* nstars;      // [F] or nullptr
     // state in / out
@@ -64,6 +65,12 @@ struct LaunchArgs {
     // EVAL outputs
     double* V_out; double* grad_out; double* H_out; double* Hgrad_out;
     int* fp_counts;         // [F,2]
+    // chain-kernel work scheduler (MODE_RUN): iteration chunks per chain, per-group completion counters [ceil(F/4)],
+    // travelling chain state [F,8], error word
+    int n_chunks;
+    int* sched_done;
+    double* sched_state;
+    int* sched_err;
     double* draws_normals;  // philox dump
     double* draws_lnu;
 };

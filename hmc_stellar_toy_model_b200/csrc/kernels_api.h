@@ -11,8 +11,8 @@ namespace srhmc {
 struct ChainLaunchPlan {
     int lpc = 16;   // lanes per chain
     int nw = 4;     // warps per block
-    size_t smem_f64 = 0, smem_u32 = 0;
-    int blocks_per_sm_f64 = 0, blocks_per_sm_u32 = 0;
+    size_t smem_f64 = 0, smem_u32 = 0, smem_u16 = 0;
+    int blocks_per_sm_f64 = 0, blocks_per_sm_u32 = 0, blocks_per_sm_u16 = 0;
 };
 
 // CTA-per-field kernel (field_kernel.cuh); precision 64|32, (mr, mc) in {(2,4), (2,2), (1,2)}
@@ -35,7 +35,8 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLa
 
 void fill_log_table(double* host_table /* (rc_k, lc_k) pairs, at most 128 of them */);
 int math_test_launch(cudaStream_t stream, int which, const double* x, double* y, int n, const double* log_table);
-int to_u32_launch(cudaStream_t stream, const double* src, unsigned int* dst, size_t n, int* not_exact_flag);
+int to_counts_launch(cudaStream_t stream, const double* src, unsigned int* dst32, unsigned short* dst16, size_t n,
+                     int* flags);
 
 // FMA-chain roofline microbenchmark
 int fma_peak_run(int precision, int sms, double* tflops, float* ms);

@@ -81,8 +81,10 @@ struct srhmc_ctx {
     ChainLaunchPlan chain_plan;
     size_t pix_bytes = 8;
     // device buffers
-    DevBuf D32, logtab, flag;       // exact uint32 copy of the images, fastmath log table, scratch flag
-    bool d_u32_ok = false;
+    DevBuf sched_done, sched_state, sched_err;  // chain-kernel work scheduler (see chain_kernel.cuh)
+    bool sched_used = false;
+    DevBuf D32, D16, logtab, flag;  // exact uint32 / uint16 copies of the images, fastmath log table, scratch flag
+    int d_int_bytes = 0;            // 0: float64 images only; 4 / 2: the integer copy the chain kernel should read
     DevBuf D, Dstage, q, p, nstars, normals, lnu, sg, sb, qchain, pchain, E, V, T, A, acc, scratch, qout, pout, Vout,
         grad, H, Hg, counts;
     // sizes of the last uploaded run
@@ -144,9 +146,24 @@ int configure(srhmc_ctx* c) {
     return 0;
 }
 
-int launch_field(srhmc_ctx* c, const LaunchArgs& A, bool one_star_everywhere) {
+int launch_field(srhmc_ctx* c, const LaunchArgs& A_in, bool one_star_everywhere) {
+    LaunchArgs A = A_in;
+    const bool chain = c->chain_ok && one_star_everywhere;
+    if (chain && A.mode == MODE_RUN) {
+        // scheduler state of the chunked chain kernel: completion counters start at 0 for every launch
+        const size_t groups = ((size_t)A.n_fields + 3) / 4;
+        if (int rc = c->sched_done.ensure(groups * sizeof(int))) return rc;
+        if (int rc = c->sched_state.ensure((size_t)A.n_fields * 8 * sizeof(double))) return rc;
+        if (int rc = c->sched_err.ensure(sizeof(int))) return rc;
+        CU_TRY(cudaMemsetAsync(c->sched_done.ptr, 0, groups * sizeof(int), c->stream));
+        CU_TRY(cudaMemsetAsync(c->sched_err.ptr, 0, sizeof(int), c->stream));
+        A.sched_done = c->sched_done.as<int>();
+        A.sched_state = c->sched_state.as<double>();
+        A.sched_err = c->sched_err.as<int>();
+        c->sched_used = true;
+    }
     if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
-    if (c->chain_ok && one_star_everywhere) {
+    if (chain) {
         int rc = chain_kernel_launch(c->P, A, c->chain_plan, c->sm_count, c->stream);
         if (rc != 0) return fail(SRHMC_ERR_CUDA, "chain kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     } else {
@@ -310,7 +327,7 @@ int srhmc_destroy(srhmc_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->D32, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
+    DevBuf* all[] = {&c->sched_done, &c->sched_state, &c->sched_err, &c->D32, &c->D16, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
                      &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout,
                      &c->grad, &c->H, &c->Hg, &c->counts};
     for (DevBuf* b : all) b->release();
@@ -362,19 +379,23 @@ int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
         if (e != 0) return fail(SRHMC_ERR_CUDA, "image conversion failed: %s", cudaGetErrorString((cudaError_t)e));
         c->launches += 1;
     }
-    c->d_u32_ok = false;
+    c->d_int_bytes = 0;
     if (c->chain_ok && c->cfg.precision == 64) {
-        // lossless compact copy for the warp-resident kernel when every pixel is an integer count (Poisson data)
+        // lossless compact copies for the warp-resident kernel when every pixel is an integer count (Poisson data)
         if (int rc = c->D32.ensure(n * 4)) return rc;
+        if (int rc = c->D16.ensure(n * 2)) return rc;
         CU_TRY(cudaMemsetAsync(c->flag.ptr, 0, 4, c->stream));
-        const int e = to_u32_launch(c->stream, c->D.as<double>(), c->D32.as<unsigned int>(), n, c->flag.as<int>());
+        const int e = to_counts_launch(c->stream, c->D.as<double>(), c->D32.as<unsigned int>(), c->D16.as<unsigned short>(), n,
+                                       c->flag.as<int>());
         if (e != 0) return fail(SRHMC_ERR_CUDA, "count conversion failed: %s", cudaGetErrorString((cudaError_t)e));
         c->launches += 1;
-        int not_exact = 1;
-        CU_TRY(cudaMemcpyAsync(&not_exact, c->flag.ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+        int flags = 3;
+        CU_TRY(cudaMemcpyAsync(&flags, c->flag.ptr, 4, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        const char* off = std::getenv("SRHMC_DISABLE_U32_IMAGES");
-        c->d_u32_ok = (not_exact == 0) && !(off && off[0] == '1');
+        const char* off = std::getenv("SRHMC_DISABLE_U32_IMAGES");   // both integer layouts off
+        const char* off16 = std::getenv("SRHMC_DISABLE_U16_IMAGES");
+        if (!(off && off[0] == '1') && (flags & 1) == 0)
+            c->d_int_bytes = ((flags & 2) == 0 && !(off16 && off16[0] == '1')) ? 2 : 4;
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
     c->have_data = true;
@@ -407,7 +428,8 @@ int srhmc_eval(srhmc_ctx* c, const double* q, const int32_t* nstars, int32_t f_p
     A.mode = MODE_EVAL;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
-    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.D_int = c->d_int_bytes == 2 ? c->D16.ptr : (c->d_int_bytes == 4 ? c->D32.ptr : nullptr);
+    A.D_int_bytes = c->d_int_bytes;
     A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
@@ -508,7 +530,8 @@ int srhmc_step(srhmc_ctx* c, double* q, double* p, const int32_t* nstars, int32_
     A.mode = MODE_STEP;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
-    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.D_int = c->d_int_bytes == 2 ? c->D16.ptr : (c->d_int_bytes == 4 ? c->D32.ptr : nullptr);
+    A.D_int_bytes = c->d_int_bytes;
     A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
@@ -588,7 +611,8 @@ int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
     A.mode = MODE_RUN;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
-    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.D_int = c->d_int_bytes == 2 ? c->D16.ptr : (c->d_int_bytes == 4 ? c->D32.ptr : nullptr);
+    A.D_int_bytes = c->d_int_bytes;
     A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = c->run_has_nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
@@ -633,7 +657,10 @@ int srhmc_run_download(srhmc_ctx* c, const srhmc_run_args* a) {
     if (a->A_chain) if (int rc = download(c, a->A_chain, c->A, F * rows)) return rc;
     if (a->q_final && S) if (int rc = download(c, a->q_final, c->qout, F * S * 8)) return rc;
     if (a->accept_rate) if (int rc = download(c, a->accept_rate, c->acc, F * 8)) return rc;
+    int sched_err = 0;
+    if (c->sched_used) CU_TRY(cudaMemcpyAsync(&sched_err, c->sched_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    if (sched_err) return fail(SRHMC_ERR_CUDA, "chain kernel scheduler timed out waiting for a predecessor chunk");
     return 0;
 }
 
@@ -670,7 +697,8 @@ int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int
     A.mode = MODE_SINGLE;
     A.n_fields = (int)F;
     A.D = c->D.ptr;
-    A.D_u32 = c->d_u32_ok ? c->D32.as<unsigned int>() : nullptr;
+    A.D_int = c->d_int_bytes == 2 ? c->D16.ptr : (c->d_int_bytes == 4 ? c->D32.ptr : nullptr);
+    A.D_int_bytes = c->d_int_bytes;
     A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();

@@ -312,3 +312,25 @@ def test_u32_image_path_is_lossless(monkeypatch):
             outs.append(r)
     assert np.array_equal(outs[0].q_chain, outs[1].q_chain) and np.array_equal(outs[0].E_chain, outs[1].E_chain)
     assert np.array_equal(outs[0].A_chain, outs[1].A_chain)
+
+
+def test_chunked_scheduler_is_bit_identical(monkeypatch):
+    """The chain kernel may split a chain's iterations into chunks that migrate between warps (work scheduler for
+    batches that do not fill the resident warps evenly).  Chunking must not change a single bit of any output."""
+    g = golden("chain_one_star_m19")
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    F, niter = 37, 45
+    rng = np.random.RandomState(5)
+    D = rng.poisson(np.repeat(so.model_image(S, q0)[None], F, axis=0)).astype(float)
+    q = np.repeat(q0[None], F, axis=0)
+    outs = []
+    for chunks in ("1", "7", "46"):
+        monkeypatch.setenv("SRHMC_CHAIN_CHUNKS", chunks)
+        with make_ctx(S, n_fields=F, max_stars=1) as ctx:
+            ctx.set_data(D)
+            outs.append(ctx.run(q, niter, 10, 0.2, seed=99, g_ff2=S.g_ff2, f_pos=True))
+    for o in outs[1:]:
+        for name in ("q_chain", "p_chain", "E_chain", "V_chain", "T_chain", "A_chain", "q_final", "accept_rate"):
+            assert np.array_equal(getattr(outs[0], name), getattr(o, name)), name
+    assert 0.3 < outs[0].accept_rate.mean() <= 1.0
