@@ -163,16 +163,19 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     LaunchArgs A = A_in;
     const int chains_per_block = plan.nw * (32 / plan.lpc);
     const long long blocks = ((long long)A.n_fields + chains_per_block - 1) / chains_per_block;
-    int grid;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
     const bool minb = u16 && A.mode == MODE_RUN && g_minb > 0;
-    if (minb) grid = balanced_grid(g_minb_blocks, blocks, sms);
-    else if (u16) grid = balanced_grid(plan.blocks_per_sm_u16, blocks, sms);
-    else if (A.D_int != nullptr) grid = balanced_grid(plan.blocks_per_sm_u32, blocks, sms);
-    else grid = balanced_grid(plan.blocks_per_sm_f64, blocks, sms);
+    const int max_k = minb ? g_minb_blocks
+                           : (u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64));
+    int grid = balanced_grid(max_k, blocks, sms);
     A.n_chunks = 1;
-    if (A.mode == MODE_RUN && A.sched_done != nullptr)
+    if (A.mode == MODE_RUN && A.sched_done != nullptr) {
+        // with the chunked scheduler a partly filled last round costs little, so run at full residency
+        const int full = (int)std::min<long long>(blocks, (long long)max_k * sms);
+        const int chunks = pick_chunks(blocks, (long long)full * plan.nw, A.niter + 1);
+        if (chunks > 1 && !std::getenv("SRHMC_CHAIN_BLOCKS_PER_SM")) grid = full;
         A.n_chunks = pick_chunks(blocks, (long long)grid * plan.nw, A.niter + 1);
+    }
     if (minb) {
         if (g_minb == 128) chain_kernel<kLPC, unsigned short, MODE_RUN, 128><<<grid, 32, plan.smem_u16, stream>>>(P, A);
         else if (g_minb == 112) chain_kernel<kLPC, unsigned short, MODE_RUN, 112><<<grid, 32, plan.smem_u16, stream>>>(P, A);
