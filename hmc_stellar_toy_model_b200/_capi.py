@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRHMC_LIB") or os.path.join(_HERE, "libstellar_rhmc.so")  # SRHMC_LIB: experimental builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -88,6 +88,8 @@ class RunArgs(C.Structure):
         ("A_chain", c_uint8_p),
         ("q_final", c_double_p),
         ("accept_rate", c_double_p),
+        ("field_id_base", C.c_int32),
+        ("field_id_stride", C.c_int32),
     ]
 
 
@@ -121,6 +123,8 @@ SIGNATURES = {
                                    C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_philox_draws": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, c_double_p, c_double_p]),
+    "srhmc_philox_draws_ids": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, c_double_p,
+                                         c_double_p]),
     "srhmc_test_device_math": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32]),
     "srhmc_measure_fma_peak": (C.c_int, [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_float)]),
 }

@@ -151,7 +151,8 @@ class RHMCContext:
     # ------------------------------------------------------------------ a8: run_RHMC move-0 leg
     def make_run_args(self, q0, niter, nsteps, dt, *, nstars=None, delta=1e-6, counter_max=1000, f_pos=True,
                       g_ff2=1.0, beta=1.0, schedule_g_ff2=None, schedule_beta=None, normals=None, lnu=None, seed=0,
-                      chain_stride=1, want=("q", "p", "E", "V", "T", "A"), out=None):
+                      chain_stride=1, want=("q", "p", "E", "V", "T", "A"), out=None, field_id_base=0,
+                      field_id_stride=1):
         """Build the argument block (and the host arrays it points at).  `out` may supply preallocated
         (e.g. pinned) output arrays keyed like RunResult fields."""
         F, S, L = self.F, self.S, int(niter) + 1
@@ -188,7 +189,8 @@ class RHMCContext:
             normals=dptr(keep["normals"]), lnu=dptr(keep["lnu"]), seed=int(seed), chain_stride=int(chain_stride),
             reserved=0, q_chain=dptr(keep["q_chain"]), p_chain=dptr(keep["p_chain"]), E_chain=dptr(keep["E_chain"]),
             V_chain=dptr(keep["V_chain"]), T_chain=dptr(keep["T_chain"]), A_chain=bptr(keep["A_chain"]),
-            q_final=dptr(keep["q_final"]), accept_rate=dptr(keep["accept_rate"]))
+            q_final=dptr(keep["q_final"]), accept_rate=dptr(keep["accept_rate"]),
+            field_id_base=int(field_id_base), field_id_stride=int(field_id_stride))
         return a, keep
 
     def _result(self, keep):
@@ -240,9 +242,10 @@ class RHMCContext:
         return y
 
     # ------------------------------------------------------------------ device RNG replay
-    def philox_draws(self, seed, niter):
+    def philox_draws(self, seed, niter, field_id_base=0, field_id_stride=1):
         L = int(niter) + 1
         normals = np.zeros((self.F, L, self.S))
         lnu = np.zeros((self.F, L))
-        check(self._lib.srhmc_philox_draws(self._h, int(seed), int(niter), dptr(normals), dptr(lnu)))
+        check(self._lib.srhmc_philox_draws_ids(self._h, int(seed), int(niter), int(field_id_base),
+                                               int(field_id_stride), dptr(normals), dptr(lnu)))
         return normals, lnu

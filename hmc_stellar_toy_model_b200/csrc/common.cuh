@@ -56,6 +56,7 @@ struct LaunchArgs {
     const double* normals;  // [F,L,S] or nullptr -> Philox
     const double* lnu;      // [F,L] or nullptr -> Philox
     unsigned long long seed;
+    int fid_base, fid_stride;  // Philox field id of local field i = fid_base + i * fid_stride
     // outputs
     int chain_stride;
     int n_rows;             // chain rows kept per field

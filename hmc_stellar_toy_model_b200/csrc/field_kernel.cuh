@@ -611,7 +611,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                         const double* zp = A.normals + ((size_t)field * L + l) * S + 3 * k;
                         z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
                     } else {
-                        philox_normals3(A.seed, (uint32_t)field, (uint32_t)l, (uint32_t)k, z);
+                        philox_normals3(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l, (uint32_t)k, z);
                     }
                     c.p[3 * k] = z[0] * sqrt(m.Hff);
                     c.p[3 * k + 1] = z[1] * sqrt(m.Hxx);
@@ -640,7 +640,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                     rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, s == A.nsteps - 1, Vpix, nullptr);
                 const Energies e1 = energies(c, Vpix, A.f_pos, true);
                 const double dE = (e1.V + e1.T) - E0;
-                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)field, (uint32_t)l);
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l);
                 const bool accept = (dE < 0.0) || (lnu < -dE);
                 if (keep && tid == 0 && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
                 if (accept) {

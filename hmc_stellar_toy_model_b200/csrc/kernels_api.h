@@ -20,8 +20,8 @@ size_t field_layout_total(int precision, const FieldParams& P, bool d_in_smem);
 int field_kernel_configure(int precision, int mr, int mc, size_t smem);
 int field_kernel_launch(int precision, int mr, int mc, int grid, int threads, size_t smem, cudaStream_t stream,
                         const FieldParams& P, const LaunchArgs& A, double* scratch, int d_in_smem);
-int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, double* normals,
-                       double* lnu);
+int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, int fid_base,
+                       int fid_stride, double* normals, double* lnu);
 int metric_launch(cudaStream_t stream, const FieldParams& P, size_t n_stars, const double* q, double g_ff2, double* H,
                   double* Hgrad);
 int kinetic_diag_launch(cudaStream_t stream, size_t n, const double* p, const double* H, double* T);

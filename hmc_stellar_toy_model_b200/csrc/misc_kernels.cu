@@ -5,17 +5,19 @@
 namespace srhmc {
 
 // Device normals / log-uniforms exactly as MODE_RUN consumes them (for replay through another implementation).
-__global__ void philox_dump_kernel(unsigned long long seed, int n_fields, int L, int Nmax, double* normals, double* lnu) {
+__global__ void philox_dump_kernel(unsigned long long seed, int n_fields, int L, int Nmax, int fid_base, int fid_stride,
+                                   double* normals, double* lnu) {
     const size_t total = (size_t)n_fields * L * Nmax;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(t % Nmax);
         const int l = (int)((t / Nmax) % L);
         const int f = (int)(t / ((size_t)Nmax * L));
         double z[3];
-        philox_normals3(seed, (uint32_t)f, (uint32_t)l, (uint32_t)k, z);
+        const uint32_t fid = (uint32_t)(fid_base + f * fid_stride);
+        philox_normals3(seed, fid, (uint32_t)l, (uint32_t)k, z);
         double* o = normals + (((size_t)f * L + l) * Nmax + k) * 3;
         o[0] = z[0]; o[1] = z[1]; o[2] = z[2];
-        if (k == 0) lnu[(size_t)f * L + l] = philox_lnu(seed, (uint32_t)f, (uint32_t)l);
+        if (k == 0) lnu[(size_t)f * L + l] = philox_lnu(seed, fid, (uint32_t)l);
     }
 }
 
@@ -115,11 +117,11 @@ int field_kernel_launch(int precision, int mr, int mc, int grid, int threads, si
                            : field_kernel_launch_f32(mr, mc, grid, threads, smem, stream, P, A, scratch, dsm);
 }
 
-int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, double* normals,
-                       double* lnu) {
+int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, int fid_base,
+                       int fid_stride, double* normals, double* lnu) {
     const size_t total = (size_t)n_fields * L * Nmax;
     const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-    philox_dump_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(seed, n_fields, L, Nmax, normals, lnu);
+    philox_dump_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(seed, n_fields, L, Nmax, fid_base, fid_stride, normals, lnu);
     return (int)cudaGetLastError();
 }
 

@@ -632,6 +632,8 @@ int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
     A.normals = c->run_has_normals ? c->normals.as<double>() : nullptr;
     A.lnu = c->run_has_lnu ? c->lnu.as<double>() : nullptr;
     A.seed = a->seed;
+    A.fid_base = a->field_id_base;
+    A.fid_stride = a->field_id_stride == 0 ? 1 : a->field_id_stride;
     A.chain_stride = a->chain_stride;
     A.n_rows = (int)rows;
     A.q_chain = a->q_chain ? c->qchain.as<double>() : nullptr;
@@ -728,13 +730,20 @@ int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int
 }
 
 int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* normals, double* lnu) {
+    return srhmc_philox_draws_ids(c, seed, niter, 0, 1, normals, lnu);
+}
+
+int srhmc_philox_draws_ids(srhmc_ctx* c, uint64_t seed, int32_t niter, int32_t fid_base, int32_t fid_stride, double* normals,
+                           double* lnu) {
     if (!c || !normals || !lnu || niter < 0) return fail(SRHMC_ERR_INVALID, "bad argument");
+    if (fid_stride == 0) fid_stride = 1;
     CU_TRY(cudaSetDevice(c->cfg.device));
     const size_t F = c->cfg.n_fields, N = (size_t)c->cfg.max_stars, L = (size_t)niter + 1;
     if (N == 0) return fail(SRHMC_ERR_INVALID, "max_stars is 0");
     if (int rc = c->normals.ensure(F * L * N * 3 * 8)) return rc;
     if (int rc = c->lnu.ensure(F * L * 8)) return rc;
-    const int e = philox_dump_launch(c->stream, seed, (int)F, (int)L, (int)N, c->normals.as<double>(), c->lnu.as<double>());
+    const int e = philox_dump_launch(c->stream, seed, (int)F, (int)L, (int)N, fid_base, fid_stride, c->normals.as<double>(),
+                                     c->lnu.as<double>());
     if (e != 0) return fail(SRHMC_ERR_CUDA, "philox dump failed: %s", cudaGetErrorString((cudaError_t)e));
     c->launches += 1;
     if (int rc = download(c, normals, c->normals, F * L * N * 3 * 8)) return rc;

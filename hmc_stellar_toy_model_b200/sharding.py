@@ -1,0 +1,99 @@
+"""Sharding of independent chains / fields over the GPUs of one node (BASELINE configs[1] and [3]).
+
+Independent chains need no data-path collective: rank r owns the global chain ids r, r+W, r+2W, ...
+(`ids[r::W]`), runs them in ONE resident launch on its own GPU, and the device RNG is keyed by the *global* chain id
+(`field_id_base = r`, `field_id_stride = W`), so the sharded run is bit-identical to the same batch on one GPU.
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used only to gather the per-rank chain arrays; the
+compute is handed in as a callable so the host logic can be exercised without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import numpy as np
+
+
+def shard_ids(n_items: int, rank: int, world: int) -> np.ndarray:
+    """Global ids owned by `rank`: ids[rank::world]."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    return np.arange(rank, n_items, world, dtype=np.int64)
+
+
+def shard_counts(n_items: int, world: int) -> np.ndarray:
+    """Items per rank under ids[rank::world]."""
+    base, extra = divmod(n_items, world)
+    return np.array([base + (1 if r < extra else 0) for r in range(world)], dtype=np.int64)
+
+
+def scatter_back(parts, n_items: int, world: int) -> np.ndarray:
+    """Inverse of the strided sharding: parts[r] holds the rows of ids[r::world], in order."""
+    first = next(p for p in parts if p is not None and len(p))
+    out = np.empty((n_items,) + tuple(first.shape[1:]), dtype=first.dtype)
+    for r, p in enumerate(parts):
+        ids = shard_ids(n_items, r, world)
+        if len(ids):
+            out[ids] = p
+    return out
+
+
+def run_sharded(run_local: Callable[[np.ndarray, int, int], Dict[str, np.ndarray]], n_items: int, rank: int,
+                world: int, gather: bool = True, dist=None) -> Dict[str, np.ndarray] | None:
+    """Run `run_local(ids, field_id_base, field_id_stride)` on this rank's shard and gather the named result arrays
+    (leading axis = local chain) onto rank 0 in global-id order.  Returns the gathered dict on rank 0 (and the local
+    one when `gather` is False), None on the other ranks."""
+    ids = shard_ids(n_items, rank, world)
+    local = run_local(ids, rank, world)
+    if not gather or world == 1:
+        return local if (world == 1 or not gather) else None
+    if dist is None:
+        import torch.distributed as dist  # noqa: PLC0415
+    import torch  # noqa: PLC0415
+
+    counts = shard_counts(n_items, world)
+    result = {} if rank == 0 else None
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    for name in sorted(local):
+        arr = np.ascontiguousarray(local[name])
+        tail = tuple(arr.shape[1:])
+        # pad every shard to the largest so all_gather sees equal shapes
+        width = int(counts.max())
+        buf = np.zeros((width,) + tail, dtype=arr.dtype)
+        buf[: arr.shape[0]] = arr
+        view = buf.view(np.uint8) if buf.dtype == np.bool_ else buf
+        t = torch.from_numpy(view).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        if rank == 0:
+            parts = []
+            for r in range(world):
+                a = outs[r].cpu().numpy()
+                if arr.dtype == np.bool_:
+                    a = a.view(np.bool_)
+                parts.append(a[: counts[r]])
+            result[name] = scatter_back(parts, n_items, world)
+    return result
+
+
+def run_chains_sharded(make_context, D, q0, niter, nsteps, dt, rank, world, seed=0, gather=True, dist=None,
+                       want=("q", "E", "A"), **run_kw):
+    """Convenience wrapper for BASELINE configs[1]/[3]: `make_context(n_local)` builds an RHMCContext for this rank's
+    GPU; `D` [F,R,C] and `q0` [F,S] are the full batch (every rank slices its own shard)."""
+    D = np.asarray(D)
+    q0 = np.asarray(q0)
+    n_items = q0.shape[0]
+
+    def run_local(ids, base, stride):
+        with make_context(len(ids)) as ctx:
+            ctx.set_data(D[ids])
+            r = ctx.run(q0[ids], niter, nsteps, dt, seed=seed, want=want, field_id_base=base, field_id_stride=stride,
+                        **run_kw)
+            out = {"q_final": r.q_final, "accept_rate": r.accept_rate}
+            for key, name in (("q", "q_chain"), ("p", "p_chain"), ("E", "E_chain"), ("V", "V_chain"),
+                              ("T", "T_chain"), ("A", "A_chain")):
+                if key in want:
+                    out[name] = getattr(r, name)
+            return out
+
+    return run_sharded(run_local, n_items, rank, world, gather=gather, dist=dist)

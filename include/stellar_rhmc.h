@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SRHMC_ABI_VERSION 1
+#define SRHMC_ABI_VERSION 2
 
 typedef enum srhmc_status {
     SRHMC_OK = 0,
@@ -104,6 +104,11 @@ typedef struct srhmc_run_args {
     uint8_t* A_chain;
     double* q_final;       /* [F,S] state after the last iteration (accepted or restored), may be NULL */
     double* accept_rate;   /* [F] fraction of accepted iterations, may be NULL */
+    /* Global identity of the context's fields for the device RNG: field i draws the Philox stream of chain
+     * field_id_base + i * field_id_stride (0 / 0 means base 0, stride 1).  A batch sharded over GPUs as
+     * ids[rank::world] passes base = rank, stride = world and reproduces the single-GPU run bit for bit. */
+    int32_t field_id_base;
+    int32_t field_id_stride;
 } srhmc_run_args;
 
 int srhmc_abi_version(void);
@@ -171,6 +176,9 @@ int srhmc_run_single(srhmc_ctx* ctx, const double* q0, const double* p0, const i
 /* Draws of the device generator, for replaying a Philox run through another implementation:
  * normals [F,L,S], lnu [F,L] exactly as srhmc_run would consume them for `seed`. */
 int srhmc_philox_draws(srhmc_ctx* ctx, uint64_t seed, int32_t niter, double* normals, double* lnu);
+/* Same with the global field identity of srhmc_run_args. */
+int srhmc_philox_draws_ids(srhmc_ctx* ctx, uint64_t seed, int32_t niter, int32_t field_id_base, int32_t field_id_stride,
+                           double* normals, double* lnu);
 
 /* Diagnostic: evaluate the kernels' own device math on n values (which = 0: exp_neg(x), x <= 0; 1: log_pos(x), x > 0;
  * 2: rcp_fast(x)) so the test-suite can bound its error against libm. */

@@ -1,0 +1,107 @@
+"""Host-side multi-GPU logic on CPU: the strided sharding of independent chains, exercised with two gloo ranks, and
+(on a GPU box) the bit-identity of a sharded run with the single-context run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from hmc_stellar_toy_model_b200 import sharding
+
+
+def test_shard_ids_partition_every_batch():
+    for n in (0, 1, 5, 8, 11000, 8192):
+        for world in (1, 2, 3, 4, 8):
+            parts = [sharding.shard_ids(n, r, world) for r in range(world)]
+            assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
+            assert [len(p) for p in parts] == list(sharding.shard_counts(n, world))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_ids(4, 2, 2)
+
+
+def test_scatter_back_inverts_the_sharding():
+    full = np.arange(7 * 3, dtype=float).reshape(7, 3)
+    parts = [full[sharding.shard_ids(7, r, 3)] for r in range(3)]
+    assert np.array_equal(sharding.scatter_back(parts, 7, 3), full)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_items, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def run_local(ids, base, stride):
+            # a stand-in for the resident launch: results are pure functions of the GLOBAL chain id, which is what
+            # the device RNG keying (field_id_base + i * field_id_stride) guarantees on the GPU
+            assert base == rank and stride == world
+            gid = base + stride * np.arange(len(ids))
+            assert np.array_equal(gid, ids)
+            return {"q_final": np.stack([gid * 1.5, gid + 0.25, -gid], axis=1).astype(float),
+                    "accept_rate": (gid % 7) / 7.0,
+                    "A_chain": (gid[:, None] + np.arange(4)[None, :]) % 2 == 0}
+
+        out = sharding.run_sharded(run_local, n_items, rank, world, dist=dist)
+        if rank == 0:
+            q.put({k: v for k, v in out.items()})
+        else:
+            assert out is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [9, 16])
+def test_two_rank_gloo_gather_restores_global_order(n_items):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gid = np.arange(n_items)
+    assert np.array_equal(out["q_final"], np.stack([gid * 1.5, gid + 0.25, -gid], axis=1))
+    assert np.array_equal(out["accept_rate"], (gid % 7) / 7.0)
+    assert out["A_chain"].dtype == np.bool_
+    assert np.array_equal(out["A_chain"], (gid[:, None] + np.arange(4)[None, :]) % 2 == 0)
+
+
+@pytest.mark.gpu
+def test_sharded_run_is_bit_identical_to_single_context():
+    """Two shards run one after the other on cuda:0 with (base, stride) = (r, 2) reproduce the unsharded batch."""
+    import stellar_oracle as so
+    from helpers import golden, setup_from
+    from test_gpu_parity import make_ctx
+
+    g = golden("chain_one_star_m19")
+    S = setup_from(g)
+    q0 = so.format_q(S, g["q_model"])
+    F, niter = 10, 25
+    rng = np.random.RandomState(8)
+    D = rng.poisson(np.repeat(so.model_image(S, q0)[None], F, axis=0)).astype(float)
+    q = np.repeat(q0[None], F, axis=0)
+    with make_ctx(S, n_fields=F, max_stars=1) as ctx:
+        ctx.set_data(D)
+        full = ctx.run(q, niter, 10, 0.2, seed=5, g_ff2=S.g_ff2)
+    parts_q, parts_A = [], []
+    for r in range(2):
+        out = sharding.run_chains_sharded(lambda n: make_ctx(S, n_fields=n, max_stars=1), D, q, niter, 10, 0.2, r, 2,
+                                          seed=5, gather=False, g_ff2=S.g_ff2)
+        parts_q.append(out["q_chain"])
+        parts_A.append(out["A_chain"])
+    assert np.array_equal(sharding.scatter_back(parts_q, F, 2), full.q_chain)
+    assert np.array_equal(sharding.scatter_back(parts_A, F, 2), full.A_chain)
