@@ -54,6 +54,34 @@ class Config(C.Structure):
         ("alpha", C.c_double),
         ("V_prior_const", C.c_double),
         ("Vc_r_pow", C.c_double),
+        ("enable_hessian", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+class LsArgs(C.Structure):
+    """struct srhmc_ls_args"""
+
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("niter", C.c_int32),
+        ("q0", c_double_p),
+        ("nstars", c_int32_p),
+        ("dt", c_double_p),
+        ("n_dt", C.c_int32),
+        ("zero_xy_momentum", C.c_int32),
+        ("f_lim", C.c_double),
+        ("factor1", C.c_double),
+        ("normals", c_double_p),
+        ("steps", c_int32_p),
+        ("lnu", c_double_p),
+        ("background", c_double_p),
+        ("q_chain", c_double_p),
+        ("E_chain", c_double_p),
+        ("dE_chain", c_double_p),
+        ("A_chain", c_uint8_p),
+        ("q_final", c_double_p),
+        ("accept_count", c_double_p),
     ]
 
 
@@ -90,6 +118,7 @@ class RunArgs(C.Structure):
         ("accept_rate", c_double_p),
         ("field_id_base", C.c_int32),
         ("field_id_stride", C.c_int32),
+        ("field_ids", c_int32_p),
     ]
 
 
@@ -122,6 +151,10 @@ SIGNATURES = {
     "srhmc_run_single": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_double,
                                    C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "srhmc_ls_run": (C.c_int, [C.c_void_p, C.POINTER(LsArgs)]),
+    "srhmc_eval_background": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, c_double_p, c_double_p, c_double_p]),
+    "srhmc_hessian": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p, C.c_double, C.c_int32,
+                                c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_philox_draws": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, c_double_p, c_double_p]),
     "srhmc_philox_draws_ids": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, c_double_p,
                                          c_double_p]),

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import Config, RunArgs, as_f64, bptr, check, dptr, iptr
+from ._capi import Config, LsArgs, RunArgs, as_f64, bptr, check, dptr, iptr
 
 
 @dataclass
@@ -32,14 +32,16 @@ class RHMCContext:
 
     def __init__(self, *, n_fields, num_rows, num_cols, max_stars, psf_fwhm_pix, B_count, f_lim, f_low, g0, g1, g2,
                  g_xx, g_ff, use_prior=False, alpha=2.0, V_prior_const=0.0, use_Vc=False, Vc_r_pow=1.0,
-                 precision=64, patch_radius=0, shared_data=False, fixed_point_mode=0, device=0):
+                 precision=64, patch_radius=0, shared_data=False, fixed_point_mode=0, device=0,
+                 enable_hessian=False):
         self._lib = _capi.load_library()
         cfg = Config(
             abi_version=_capi.ABI_VERSION, device=device, precision=precision, n_fields=n_fields, num_rows=num_rows,
             num_cols=num_cols, max_stars=max_stars, patch_radius=patch_radius, shared_data=int(bool(shared_data)),
             fixed_point_mode=fixed_point_mode, use_prior=int(bool(use_prior)), use_Vc=int(bool(use_Vc)),
             psf_fwhm_pix=psf_fwhm_pix, B_count=B_count, f_lim=f_lim, f_low=f_low, g0=g0, g1=g1, g2=g2, g_xx=g_xx,
-            g_ff=g_ff, alpha=alpha, V_prior_const=V_prior_const, Vc_r_pow=Vc_r_pow)
+            g_ff=g_ff, alpha=alpha, V_prior_const=V_prior_const, Vc_r_pow=Vc_r_pow,
+            enable_hessian=int(bool(enable_hessian)), reserved0=0)
         self.cfg = cfg
         self._h = C.c_void_p()
         check(self._lib.srhmc_create(C.byref(cfg), C.byref(self._h)))
@@ -152,7 +154,7 @@ class RHMCContext:
     def make_run_args(self, q0, niter, nsteps, dt, *, nstars=None, delta=1e-6, counter_max=1000, f_pos=True,
                       g_ff2=1.0, beta=1.0, schedule_g_ff2=None, schedule_beta=None, normals=None, lnu=None, seed=0,
                       chain_stride=1, want=("q", "p", "E", "V", "T", "A"), out=None, field_id_base=0,
-                      field_id_stride=1):
+                      field_id_stride=1, field_ids=None):
         """Build the argument block (and the host arrays it points at).  `out` may supply preallocated
         (e.g. pinned) output arrays keyed like RunResult fields."""
         F, S, L = self.F, self.S, int(niter) + 1
@@ -164,6 +166,7 @@ class RHMCContext:
         keep["sb"] = None if schedule_beta is None else as_f64(schedule_beta).ravel()
         keep["normals"] = None if normals is None else as_f64(normals, (F, L, S))
         keep["lnu"] = None if lnu is None else as_f64(lnu, (F, L))
+        keep["field_ids"] = None if field_ids is None else np.ascontiguousarray(field_ids, dtype=np.int32).reshape(F)
         out = dict(out or {})
 
         def buf(key, shape, dtype=np.float64):
@@ -190,7 +193,7 @@ class RHMCContext:
             reserved=0, q_chain=dptr(keep["q_chain"]), p_chain=dptr(keep["p_chain"]), E_chain=dptr(keep["E_chain"]),
             V_chain=dptr(keep["V_chain"]), T_chain=dptr(keep["T_chain"]), A_chain=bptr(keep["A_chain"]),
             q_final=dptr(keep["q_final"]), accept_rate=dptr(keep["accept_rate"]),
-            field_id_base=int(field_id_base), field_id_stride=int(field_id_stride))
+            field_id_base=int(field_id_base), field_id_stride=int(field_id_stride), field_ids=iptr(keep["field_ids"]))
         return a, keep
 
     def _result(self, keep):
@@ -233,6 +236,60 @@ class RHMCContext:
                                          int(counter_max), int(bool(f_pos)), float(g_ff2), float(beta), dptr(qc),
                                          dptr(pc), dptr(E), dptr(V), dptr(T)))
         return qc, pc, E, V, T
+
+    # ------------------------------------------------------------------ a10/a11: lightsource_gym family
+    LS_HMC, LS_DIAG, LS_HESS, LS_TRIAL = 0, 1, 2, 3
+
+    def hessian(self, q, p=None, f_lim=0.0, d2_only=False, nstars=None):
+        """RHMC_efficient_computation: (d1, d2, d3, dqdt, dpdt, E), or d2 alone when d2_only."""
+        F, S = self.F, self.S
+        q = as_f64(q, (F, S))
+        ns = self._nstars(nstars)
+        d2 = np.zeros((F, S))
+        if d2_only:
+            check(self._lib.srhmc_hessian(self._h, dptr(q), None, iptr(ns), float(f_lim), 1, None, dptr(d2), None, None,
+                                          None, None))
+            return d2
+        p = as_f64(p, (F, S))
+        d1, d3, dq, dp = (np.zeros((F, S)) for _ in range(4))
+        E = np.zeros(F)
+        check(self._lib.srhmc_hessian(self._h, dptr(q), dptr(p), iptr(ns), float(f_lim), 0, dptr(d1), dptr(d2), dptr(d3),
+                                      dptr(dq), dptr(dp), dptr(E)))
+        return d1, d2, d3, dq, dp, E
+
+    def eval_background(self, q, background, nstars=None):
+        """V and dV/dq on a per-pixel background image (lightsource_gym.V_single / dVdq_single)."""
+        q = as_f64(q, (self.F, self.S))
+        bg = as_f64(background, (self.F, self.cfg.num_rows, self.cfg.num_cols))
+        ns = self._nstars(nstars)
+        V = np.zeros(self.F)
+        grad = np.zeros((self.F, self.S))
+        check(self._lib.srhmc_eval_background(self._h, dptr(q), iptr(ns), dptr(bg), dptr(V), dptr(grad)))
+        return V, grad
+
+    def ls_run(self, variant, q0, dt, normals, steps, lnu, f_lim=0.0, factor1=0.0, background=None, zero_xy=False,
+               nstars=None):
+        """One lightsource_gym chain per field with injected draws -> dict(q_chain, E_chain, dE_chain, A_chain,
+        q_final, accept_count)."""
+        F, S = self.F, self.S
+        steps = np.ascontiguousarray(steps, dtype=np.int32).reshape(F, -1)
+        niter = steps.shape[1]
+        L = niter + 1
+        q0 = as_f64(q0, (F, S))
+        dt = as_f64(dt).ravel()
+        normals = as_f64(normals, (F, L, S))
+        lnu = as_f64(lnu, (F, niter))
+        ns = self._nstars(nstars)
+        bg = None if background is None else as_f64(background, (F, self.cfg.num_rows, self.cfg.num_cols))
+        out = dict(q_chain=np.zeros((F, L, S)), E_chain=np.zeros((F, L)), dE_chain=np.zeros((F, L)),
+                   A_chain=np.zeros((F, niter), dtype=np.uint8), q_final=np.zeros((F, S)), accept_count=np.zeros(F))
+        a = LsArgs(variant=int(variant), niter=niter, q0=dptr(q0), nstars=iptr(ns), dt=dptr(dt), n_dt=dt.size,
+                   zero_xy_momentum=int(bool(zero_xy)), f_lim=float(f_lim), factor1=float(factor1),
+                   normals=dptr(normals), steps=iptr(steps), lnu=dptr(lnu), background=dptr(bg),
+                   q_chain=dptr(out["q_chain"]), E_chain=dptr(out["E_chain"]), dE_chain=dptr(out["dE_chain"]),
+                   A_chain=bptr(out["A_chain"]), q_final=dptr(out["q_final"]), accept_count=dptr(out["accept_count"]))
+        check(self._lib.srhmc_ls_run(self._h, C.byref(a)))
+        return out
 
     def device_math(self, which, x):
         """Diagnostic: the kernels' exp_neg (0), log_pos (1) or rcp_fast (2) evaluated on the device."""

@@ -559,7 +559,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                     const double* zp = A.normals + ((size_t)field * L + l) * 3;
                     z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
                 } else {
-                    philox_normals3(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l, 0u, z);
+                    philox_normals3(A.seed, A.philox_field(field), (uint32_t)l, 0u, z);
                 }
                 {
                     const double sxx = sqrt(rcp_fast(s.ihxx));
@@ -585,7 +585,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, V1, T1);
                 const double dE = (V1 + T1) - E0;
-                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l);
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, A.philox_field(field), (uint32_t)l);
                 const bool accept = (dE < 0.0) || (lnu < -dE);
                 if (keep && writer && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
                 if (accept) {

@@ -18,6 +18,7 @@ struct FieldParams {
     int fp_mode;       // 0 parity (field-wide stop rule), 1 per-star
     int D_shared;      // all fields read image 0
     int use_prior, use_Vc, vc_int;  // vc_int: Vc_r_pow as small non-negative integer, or -1
+    int hess;          // shared memory holds a second image for the Hessian path
     double inv2s2;     // 1/(2 sigma^2)
     double inv_s2;     // 1/sigma^2
     double norm;       // 1/(2 pi sigma^2)
@@ -32,6 +33,34 @@ struct FieldParams {
 };
 
 enum Mode : int { MODE_EVAL = 0, MODE_STEP = 1, MODE_RUN = 2, MODE_SINGLE = 3 };
+// samplers.lightsource_gym family (ls_kernel.cuh)
+enum LsVariant : int { LS_HMC = 0, LS_DIAG = 1, LS_HESS = 2, LS_TRIAL = 3, LS_EVAL_HESS = 4, LS_EVAL_BG = 5 };
+
+struct LsArgs {
+    int variant, n_fields, niter;
+    const void* D;
+    const int* nstars;
+    const double* q0;        // [F,S]
+    const double* p0;        // [F,S] (LS_EVAL_HESS) or nullptr
+    const double* dt;        // [S] per-coordinate steps (LS_HMC, LS_HESS, LS_TRIAL: [3]); LS_DIAG: dt[0] = dt_global
+    double f_lim, factor1;
+    const double* normals;   // [F, niter+1, S]
+    const int* steps;        // [F, niter]
+    const double* lnu;       // [F, niter]
+    const double* background;  // [F,R,C] (LS_TRIAL) or nullptr
+    int zero_xy;             // LS_TRIAL: zero the position momenta (flux-only tuning pass)
+    double* q_chain;         // [F, niter+1, S]
+    double* E_chain;         // [F, niter+1]
+    double* dE_chain;        // [F, niter+1]
+    unsigned char* A_chain;  // [F, niter]
+    double* q_final;         // [F,S]
+    double* accept_count;    // [F]
+    // LS_EVAL_HESS outputs
+    double* d1; double* d2; double* d3;   // [F,S] dV/dq, d2V/dq2, d3V/dq3 (diagonal)
+    double* dqdt; double* dpdt;           // [F,S]
+    double* E_out;                        // [F]
+    int d2_only;
+};
 
 // Per-launch arguments (device pointers).
 struct LaunchArgs {
@@ -56,7 +85,11 @@ struct LaunchArgs {
     const double* normals;  // [F,L,S] or nullptr -> Philox
     const double* lnu;      // [F,L] or nullptr -> Philox
     unsigned long long seed;
-    int fid_base, fid_stride;  // Philox field id of local field i = fid_base + i * fid_stride
+    int fid_base, fid_stride;  // Philox field id of local field i = fid_base + i * fid_stride ...
+    const int* field_ids;      // ... unless an explicit id array [F] is given
+    __device__ __forceinline__ unsigned int philox_field(int field) const {
+        return (unsigned int)(field_ids ? field_ids[field] : fid_base + field * fid_stride);
+    }
     // outputs
     int chain_stride;
     int n_rows;             // chain rows kept per field

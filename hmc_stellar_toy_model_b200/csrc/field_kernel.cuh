@@ -22,7 +22,7 @@
 namespace srhmc {
 
 struct SmemLayout {
-    size_t q, p, g, a1, a2, red, D, L, tabx, taby, span, total;
+    size_t q, p, g, a1, a2, red, D, L, L2, tabx, taby, span, total;
 };
 
 template <typename T>
@@ -43,6 +43,7 @@ __host__ __device__ inline SmemLayout make_layout(const FieldParams& P, bool d_i
     s.red = take(8 * 32 * sizeof(double));
     s.D = take(d_in_smem ? (size_t)P.R * P.C * sizeof(T) : 0);
     s.L = take((size_t)P.R * P.C * sizeof(T));
+    s.L2 = take(P.hess ? (size_t)P.R * P.C * sizeof(T) : 0);  // 1/Lambda image of the Hessian path (samplers.py:828-927)
     s.tabx = take((size_t)P.Kc * P.sx * sizeof(T));
     s.taby = take((size_t)P.Kc * P.sy * sizeof(T));
     s.span = take((size_t)P.Kc * 4 * sizeof(short));
@@ -58,6 +59,9 @@ struct Ctx {
     T* tabx;
     T* taby;
     const T* gD;   // this field's image in global memory
+    T* sL2;        // 1/Lambda image (Hessian path), nullptr otherwise
+    const double* bg;  // optional per-pixel background replacing the constant B (HMC_find_best_dt's model_data)
+    bool hess_out; // render writes rho0 = D/Lambda to sL and 1/Lambda to sL2 instead of rho = D/Lambda - 1
     double *q, *p, *g, *a1, *a2, *red;
     short* span;
     int N;
@@ -137,7 +141,8 @@ __device__ void render_chunk(const Ctx<T>& c, int nk, bool first, bool last, boo
 #pragma unroll
             for (int cc = 0; cc < MC; ++cc) {
                 const bool ok = (ib + r < P.R) && (jb + cc < P.C);
-                acc[r][cc] = first ? (T)P.B : (ok ? c.sL[(ib + r) * P.C + jb + cc] : (T)0);
+                acc[r][cc] = first ? ((c.bg && ok) ? (T)c.bg[(ib + r) * P.C + jb + cc] : (T)P.B)
+                                   : (ok ? c.sL[(ib + r) * P.C + jb + cc] : (T)0);
             }
         auto accumulate = [&](int kk) {
             T fx[MR], fy[MC];
@@ -179,7 +184,13 @@ __device__ void render_chunk(const Ctx<T>& c, int nk, bool first, bool last, boo
                     } else {
                         const T lam = acc[r][cc];
                         const T d = c.sD ? c.sD[pix] : c.gD[pix];
-                        c.sL[pix] = fma(d, rcp_fast(lam), (T)-1);  // rho = D/Lambda - 1
+                        const T il = rcp_fast(lam);
+                        if (c.hess_out) {
+                            c.sL[pix] = d * il;  // rho0 = D/Lambda
+                            c.sL2[pix] = il;
+                        } else {
+                            c.sL[pix] = fma(d, il, (T)-1);  // rho = D/Lambda - 1
+                        }
                         if (want_V) {
                             const double ld = (double)lam;
                             vacc += ld - (double)d * log(ld);
@@ -504,6 +515,9 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
         c.taby = reinterpret_cast<T*>(smem_raw + lay.taby);
         c.span = reinterpret_cast<short*>(smem_raw + lay.span);
         c.gD = reinterpret_cast<const T*>(A.D) + (P.D_shared ? 0 : (size_t)field * P.R * P.C);
+        c.sL2 = nullptr;
+        c.bg = nullptr;
+        c.hess_out = false;
         c.N = A.nstars ? A.nstars[field] : P.Nmax;
         c.g_ff2 = A.g_ff2;
         c.beta = A.beta;
@@ -611,7 +625,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                         const double* zp = A.normals + ((size_t)field * L + l) * S + 3 * k;
                         z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
                     } else {
-                        philox_normals3(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l, (uint32_t)k, z);
+                        philox_normals3(A.seed, A.philox_field(field), (uint32_t)l, (uint32_t)k, z);
                     }
                     c.p[3 * k] = z[0] * sqrt(m.Hff);
                     c.p[3 * k + 1] = z[1] * sqrt(m.Hxx);
@@ -640,7 +654,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                     rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, s == A.nsteps - 1, Vpix, nullptr);
                 const Energies e1 = energies(c, Vpix, A.f_pos, true);
                 const double dE = (e1.V + e1.T) - E0;
-                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, (uint32_t)(A.fid_base + field * A.fid_stride), (uint32_t)l);
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, A.philox_field(field), (uint32_t)l);
                 const bool accept = (dE < 0.0) || (lnu < -dE);
                 if (keep && tid == 0 && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
                 if (accept) {

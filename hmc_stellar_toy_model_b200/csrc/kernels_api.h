@@ -20,6 +20,10 @@ size_t field_layout_total(int precision, const FieldParams& P, bool d_in_smem);
 int field_kernel_configure(int precision, int mr, int mc, size_t smem);
 int field_kernel_launch(int precision, int mr, int mc, int grid, int threads, size_t smem, cudaStream_t stream,
                         const FieldParams& P, const LaunchArgs& A, double* scratch, int d_in_smem);
+// lightsource_gym family (ls_kernel.cuh), FP64
+int ls_kernel_configure(int mr, int mc, size_t smem);
+int ls_kernel_launch(int mr, int mc, int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P,
+                     const LsArgs& A, double* scratch, int dsm);
 int philox_dump_launch(cudaStream_t stream, unsigned long long seed, int n_fields, int L, int Nmax, int fid_base,
                        int fid_stride, double* normals, double* lnu);
 int metric_launch(cudaStream_t stream, const FieldParams& P, size_t n_stars, const double* q, double g_ff2, double* H,

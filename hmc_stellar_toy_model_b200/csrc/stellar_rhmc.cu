@@ -81,6 +81,9 @@ struct srhmc_ctx {
     ChainLaunchPlan chain_plan;
     size_t pix_bytes = 8;
     // device buffers
+    DevBuf ls_dt, ls_steps, ls_bg, ls_scratch, ls_d1, ls_d2, ls_d3;
+    DevBuf field_ids;
+    bool run_has_field_ids = false;
     DevBuf sched_done, sched_state, sched_err;  // chain-kernel work scheduler (see chain_kernel.cuh)
     bool sched_used = false;
     DevBuf D32, D16, logtab, flag;  // exact uint32 / uint16 copies of the images, fastmath log table, scratch flag
@@ -143,6 +146,10 @@ int configure(srhmc_ctx* c) {
     c->smem = field_layout_total(prec, P, dsm);
     const int e = field_kernel_configure(prec, c->kc.mr, c->kc.mc, c->smem);
     if (e != 0) return fail(SRHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B shared) failed: %s", c->smem, cudaGetErrorString((cudaError_t)e));
+    if (prec == 64) {
+        const int e2 = ls_kernel_configure(c->kc.mr, c->kc.mc, c->smem);
+        if (e2 != 0) return fail(SRHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B shared) failed: %s", c->smem, cudaGetErrorString((cudaError_t)e2));
+    }
     return 0;
 }
 
@@ -264,6 +271,7 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.D_shared = cfg->shared_data ? 1 : 0;
     P.use_prior = cfg->use_prior ? 1 : 0;
     P.use_Vc = cfg->use_Vc ? 1 : 0;
+    P.hess = (cfg->enable_hessian && cfg->precision == 64) ? 1 : 0;
     const double sigma = cfg->psf_fwhm_pix / 2.354;  // utils.py:480
     P.inv2s2 = 1.0 / (2.0 * sigma * sigma);
     P.inv_s2 = 1.0 / (sigma * sigma);
@@ -327,7 +335,7 @@ int srhmc_destroy(srhmc_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->sched_done, &c->sched_state, &c->sched_err, &c->D32, &c->D16, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
+    DevBuf* all[] = {&c->ls_dt, &c->ls_steps, &c->ls_bg, &c->ls_scratch, &c->ls_d1, &c->ls_d2, &c->ls_d3, &c->field_ids, &c->sched_done, &c->sched_state, &c->sched_err, &c->D32, &c->D16, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
                      &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout,
                      &c->grad, &c->H, &c->Hg, &c->counts};
     for (DevBuf* b : all) b->release();
@@ -577,6 +585,8 @@ int srhmc_run_upload(srhmc_ctx* c, const srhmc_run_args* a) {
     c->run_one_star = all_one_star(c, a->nstars);
     c->run_has_normals = a->normals != nullptr;
     c->run_has_lnu = a->lnu != nullptr;
+    c->run_has_field_ids = a->field_ids != nullptr;
+    if (a->field_ids) if (int rc = upload(c, c->field_ids, a->field_ids, F * sizeof(int32_t))) return rc;
     if (a->normals) if (int rc = upload(c, c->normals, a->normals, std::max<size_t>(F * L * S * 8, 8))) return rc;
     if (a->lnu) if (int rc = upload(c, c->lnu, a->lnu, F * L * 8)) return rc;
     if (a->g_ff2_schedule && a->n_g_ff2 > 0) if (int rc = upload(c, c->sg, a->g_ff2_schedule, (size_t)a->n_g_ff2 * 8)) return rc;
@@ -634,6 +644,7 @@ int srhmc_run_launch(srhmc_ctx* c, const srhmc_run_args* a) {
     A.seed = a->seed;
     A.fid_base = a->field_id_base;
     A.fid_stride = a->field_id_stride == 0 ? 1 : a->field_id_stride;
+    A.field_ids = c->run_has_field_ids ? c->field_ids.as<int>() : nullptr;
     A.chain_stride = a->chain_stride;
     A.n_rows = (int)rows;
     A.q_chain = a->q_chain ? c->qchain.as<double>() : nullptr;
@@ -725,6 +736,152 @@ int srhmc_run_single(srhmc_ctx* c, const double* q0, const double* p0, const int
     if (E_chain) if (int rc = download(c, E_chain, c->E, F * rows * 8)) return rc;
     if (V_chain) if (int rc = download(c, V_chain, c->V, F * rows * 8)) return rc;
     if (T_chain) if (int rc = download(c, T_chain, c->T, F * rows * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int ls_common(srhmc_ctx* c, LsArgs& A, const double* q0, const double* p0, const int32_t* nstars) {
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    if (c->cfg.precision != 64) return fail(SRHMC_ERR_INVALID, "the lightsource_gym entry points need a precision=64 context");
+    if (c->cfg.use_prior || c->cfg.use_Vc) return fail(SRHMC_ERR_INVALID, "lightsource_gym has no prior / repulsion: create the context with use_prior = use_Vc = 0");
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = std::max<size_t>(F * S * 8, 8);
+    if (int rc = upload(c, c->q, q0, FS)) return rc;
+    if (p0) if (int rc = upload(c, c->p, p0, FS)) return rc;
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    if (int rc = c->ls_scratch.ensure(5 * FS)) return rc;
+    std::memset(&A, 0, sizeof(A));
+    A.n_fields = (int)F;
+    A.D = c->D.ptr;
+    A.nstars = nstars ? c->nstars.as<int>() : nullptr;
+    A.q0 = c->q.as<double>();
+    A.p0 = p0 ? c->p.as<double>() : nullptr;
+    return 0;
+}
+
+static int ls_launch(srhmc_ctx* c, const LsArgs& A) {
+    if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    const int rc = ls_kernel_launch(c->kc.mr, c->kc.mc, std::max(1, A.n_fields), c->threads, c->smem, c->stream, c->P, A,
+                                    c->ls_scratch.as<double>(), c->d_in_smem);
+    if (rc != 0) return fail(SRHMC_ERR_CUDA, "lightsource kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c->timed) CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    return 0;
+}
+
+int srhmc_ls_run(srhmc_ctx* c, const srhmc_ls_args* a) {
+    if (!c || !a || !a->q0 || !a->dt || !a->normals || !a->lnu || !a->steps) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (a->variant < SRHMC_LS_HMC || a->variant > SRHMC_LS_TRIAL) return fail(SRHMC_ERR_INVALID, "unknown variant %d", a->variant);
+    if (a->niter < 0) return fail(SRHMC_ERR_INVALID, "niter must be >= 0");
+    if (a->variant == SRHMC_LS_HESS && !c->P.hess) return fail(SRHMC_ERR_STATE, "context was created without enable_hessian");
+    if (a->variant == SRHMC_LS_TRIAL && c->cfg.max_stars != 1) return fail(SRHMC_ERR_INVALID, "the step-size trial is a one-star problem");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, L = (size_t)a->niter + 1, n = (size_t)a->niter;
+    const size_t need_dt = a->variant == SRHMC_LS_DIAG ? 1 : S;
+    if ((size_t)a->n_dt < need_dt) return fail(SRHMC_ERR_INVALID, "dt has %d entries, %zu needed", a->n_dt, need_dt);
+    for (size_t i = 0; i < F * n; ++i)
+        if (a->steps[i] < 0) return fail(SRHMC_ERR_INVALID, "negative trajectory length");
+    LsArgs A;
+    if (int rc = ls_common(c, A, a->q0, nullptr, a->nstars)) return rc;
+    if (int rc = upload(c, c->ls_dt, a->dt, std::max<size_t>(need_dt * 8, 8))) return rc;
+    if (int rc = upload(c, c->normals, a->normals, std::max<size_t>(F * L * S * 8, 8))) return rc;
+    if (int rc = upload(c, c->lnu, a->lnu, std::max<size_t>(F * n * 8, 8))) return rc;
+    if (int rc = upload(c, c->ls_steps, a->steps, std::max<size_t>(F * n * 4, 8))) return rc;
+    c->run_has_normals = c->run_has_lnu = false;  // staging buffers of srhmc_run were overwritten
+    if (a->background) if (int rc = upload(c, c->ls_bg, a->background, F * (size_t)c->P.R * c->P.C * 8)) return rc;
+    if (int rc = c->qchain.ensure(std::max<size_t>(F * L * S * 8, 8))) return rc;
+    if (int rc = c->E.ensure(F * L * 8)) return rc;
+    if (int rc = c->V.ensure(F * L * 8)) return rc;
+    if (int rc = c->A.ensure(std::max<size_t>(F * n, 8))) return rc;
+    if (int rc = c->qout.ensure(std::max<size_t>(F * S * 8, 8))) return rc;
+    if (int rc = c->acc.ensure(F * 8)) return rc;
+    CU_TRY(cudaMemsetAsync(c->qchain.ptr, 0, std::max<size_t>(F * L * S * 8, 8), c->stream));
+    CU_TRY(cudaMemsetAsync(c->E.ptr, 0, F * L * 8, c->stream));
+    CU_TRY(cudaMemsetAsync(c->V.ptr, 0, F * L * 8, c->stream));
+    CU_TRY(cudaMemsetAsync(c->A.ptr, 0, std::max<size_t>(F * n, 8), c->stream));
+    A.variant = a->variant;
+    A.niter = a->niter;
+    A.dt = c->ls_dt.as<double>();
+    A.f_lim = a->f_lim;
+    A.factor1 = a->factor1;
+    A.normals = c->normals.as<double>();
+    A.steps = c->ls_steps.as<int>();
+    A.lnu = c->lnu.as<double>();
+    A.background = a->background ? c->ls_bg.as<double>() : nullptr;
+    A.zero_xy = a->zero_xy_momentum;
+    A.q_chain = c->qchain.as<double>();
+    A.E_chain = c->E.as<double>();
+    A.dE_chain = c->V.as<double>();
+    A.A_chain = c->A.as<unsigned char>();
+    A.q_final = c->qout.as<double>();
+    A.accept_count = c->acc.as<double>();
+    if (int rc = ls_launch(c, A)) return rc;
+    if (a->q_chain && S) if (int rc = download(c, a->q_chain, c->qchain, F * L * S * 8)) return rc;
+    if (a->E_chain) if (int rc = download(c, a->E_chain, c->E, F * L * 8)) return rc;
+    if (a->dE_chain) if (int rc = download(c, a->dE_chain, c->V, F * L * 8)) return rc;
+    if (a->A_chain && n) if (int rc = download(c, a->A_chain, c->A, F * n)) return rc;
+    if (a->q_final && S) if (int rc = download(c, a->q_final, c->qout, F * S * 8)) return rc;
+    if (a->accept_count) if (int rc = download(c, a->accept_count, c->acc, F * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_eval_background(srhmc_ctx* c, const double* q, const int32_t* nstars, const double* background, double* V,
+                          double* grad) {
+    if (!c || !q || !background) return fail(SRHMC_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = std::max<size_t>(F * S * 8, 8);
+    LsArgs A;
+    if (int rc = ls_common(c, A, q, nullptr, nstars)) return rc;
+    if (int rc = upload(c, c->ls_bg, background, F * (size_t)c->P.R * c->P.C * 8)) return rc;
+    if (int rc = c->ls_d1.ensure(FS)) return rc;
+    if (int rc = c->Vout.ensure(F * 8)) return rc;
+    CU_TRY(cudaMemsetAsync(c->ls_d1.ptr, 0, FS, c->stream));
+    A.variant = LS_EVAL_BG;
+    A.background = c->ls_bg.as<double>();
+    A.d1 = c->ls_d1.as<double>();
+    A.E_out = c->Vout.as<double>();
+    if (int rc = ls_launch(c, A)) return rc;
+    if (V) if (int rc = download(c, V, c->Vout, F * 8)) return rc;
+    if (grad && F * S) if (int rc = download(c, grad, c->ls_d1, F * S * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_hessian(srhmc_ctx* c, const double* q, const double* p, const int32_t* nstars, double f_lim, int32_t d2_only,
+                  double* d1, double* d2, double* d3, double* dqdt, double* dpdt, double* E) {
+    if (!c || !q) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!d2_only && !p) return fail(SRHMC_ERR_INVALID, "p is required unless d2_only");
+    if (!c->P.hess) return fail(SRHMC_ERR_STATE, "context was created without enable_hessian");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, FS = std::max<size_t>(F * S * 8, 8);
+    LsArgs A;
+    if (int rc = ls_common(c, A, q, p, nstars)) return rc;
+    DevBuf* outs[] = {&c->ls_d1, &c->ls_d2, &c->ls_d3, &c->grad, &c->H};
+    for (DevBuf* b : outs) {
+        if (int rc = b->ensure(FS)) return rc;
+        CU_TRY(cudaMemsetAsync(b->ptr, 0, FS, c->stream));
+    }
+    if (int rc = c->Vout.ensure(F * 8)) return rc;
+    A.variant = LS_EVAL_HESS;
+    A.f_lim = f_lim;
+    A.d2_only = d2_only ? 1 : 0;
+    A.d1 = c->ls_d1.as<double>();
+    A.d2 = c->ls_d2.as<double>();
+    A.d3 = c->ls_d3.as<double>();
+    A.dqdt = c->grad.as<double>();
+    A.dpdt = c->H.as<double>();
+    A.E_out = c->Vout.as<double>();
+    if (int rc = ls_launch(c, A)) return rc;
+    if (F * S) {
+        if (d2) if (int rc = download(c, d2, c->ls_d2, F * S * 8)) return rc;
+        if (!d2_only) {
+            if (d1) if (int rc = download(c, d1, c->ls_d1, F * S * 8)) return rc;
+            if (d3) if (int rc = download(c, d3, c->ls_d3, F * S * 8)) return rc;
+            if (dqdt) if (int rc = download(c, dqdt, c->grad, F * S * 8)) return rc;
+            if (dpdt) if (int rc = download(c, dpdt, c->H, F * S * 8)) return rc;
+        }
+    }
+    if (E && !d2_only) if (int rc = download(c, E, c->Vout, F * 8)) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

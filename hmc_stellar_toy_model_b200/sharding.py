@@ -1,8 +1,9 @@
 """Sharding of independent chains / fields over the GPUs of one node (BASELINE configs[1] and [3]).
 
-Independent chains need no data-path collective: rank r owns the global chain ids r, r+W, r+2W, ...
-(`ids[r::W]`), runs them in ONE resident launch on its own GPU, and the device RNG is keyed by the *global* chain id
-(`field_id_base = r`, `field_id_stride = W`), so the sharded run is bit-identical to the same batch on one GPU.
+Independent chains need no data-path collective: the batch is cut into blocks of `BLOCK` = 4 consecutive chains (the
+one-star kernel's warp group) and rank r owns blocks r, r+W, r+2W, ... (`blocks[r::W]`), runs them in ONE resident
+launch on its own GPU, and the device RNG is keyed by the *global* chain id (`field_ids`), so the sharded run is
+bit-identical to the same batch on one GPU.
 `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used only to gather the per-rank chain arrays; the
 compute is handed in as a callable so the host logic can be exercised without a GPU.
 """
@@ -13,17 +14,20 @@ from typing import Callable, Dict
 import numpy as np
 
 
-def shard_ids(n_items: int, rank: int, world: int) -> np.ndarray:
-    """Global ids owned by `rank`: ids[rank::world]."""
+BLOCK = 4  # chains per warp group of the one-star kernel: shards keep these groups intact
+
+
+def shard_ids(n_items: int, rank: int, world: int, block: int = BLOCK) -> np.ndarray:
+    """Global ids owned by `rank`: the chains of blocks[rank::world], blocks of `block` consecutive ids."""
     if not (0 <= rank < world):
         raise ValueError("rank %d outside world of %d" % (rank, world))
-    return np.arange(rank, n_items, world, dtype=np.int64)
+    ids = np.arange(n_items, dtype=np.int64)
+    return ids[(ids // block) % world == rank]
 
 
-def shard_counts(n_items: int, world: int) -> np.ndarray:
-    """Items per rank under ids[rank::world]."""
-    base, extra = divmod(n_items, world)
-    return np.array([base + (1 if r < extra else 0) for r in range(world)], dtype=np.int64)
+def shard_counts(n_items: int, world: int, block: int = BLOCK) -> np.ndarray:
+    """Items per rank under shard_ids."""
+    return np.array([len(shard_ids(n_items, r, world, block)) for r in range(world)], dtype=np.int64)
 
 
 def scatter_back(parts, n_items: int, world: int) -> np.ndarray:
@@ -37,13 +41,13 @@ def scatter_back(parts, n_items: int, world: int) -> np.ndarray:
     return out
 
 
-def run_sharded(run_local: Callable[[np.ndarray, int, int], Dict[str, np.ndarray]], n_items: int, rank: int,
+def run_sharded(run_local: Callable[[np.ndarray], Dict[str, np.ndarray]], n_items: int, rank: int,
                 world: int, gather: bool = True, dist=None) -> Dict[str, np.ndarray] | None:
-    """Run `run_local(ids, field_id_base, field_id_stride)` on this rank's shard and gather the named result arrays
+    """Run `run_local(global_ids)` on this rank's shard and gather the named result arrays
     (leading axis = local chain) onto rank 0 in global-id order.  Returns the gathered dict on rank 0 (and the local
     one when `gather` is False), None on the other ranks."""
     ids = shard_ids(n_items, rank, world)
-    local = run_local(ids, rank, world)
+    local = run_local(ids)
     if not gather or world == 1:
         return local if (world == 1 or not gather) else None
     if dist is None:
@@ -84,11 +88,10 @@ def run_chains_sharded(make_context, D, q0, niter, nsteps, dt, rank, world, seed
     q0 = np.asarray(q0)
     n_items = q0.shape[0]
 
-    def run_local(ids, base, stride):
+    def run_local(ids):
         with make_context(len(ids)) as ctx:
             ctx.set_data(D[ids])
-            r = ctx.run(q0[ids], niter, nsteps, dt, seed=seed, want=want, field_id_base=base, field_id_stride=stride,
-                        **run_kw)
+            r = ctx.run(q0[ids], niter, nsteps, dt, seed=seed, want=want, field_ids=ids, **run_kw)
             out = {"q_final": r.q_final, "accept_rate": r.accept_rate}
             for key, name in (("q", "q_chain"), ("p", "p_chain"), ("E", "E_chain"), ("V", "V_chain"),
                               ("T", "T_chain"), ("A", "A_chain")):

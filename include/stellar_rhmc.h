@@ -64,7 +64,46 @@ typedef struct srhmc_config {
     double alpha;            /* prior exponent (sampler_RHMC.py:326,409) */
     double V_prior_const;    /* gym.V_prior_const (sampler_RHMC.py:320-321) */
     double Vc_r_pow;         /* repulsion exponent (sampler_RHMC.py:349,417) */
+    int32_t enable_hessian;  /* 1: reserve the second shared-memory image the Hessian path needs (srhmc_hessian,
+                                SRHMC_LS_HESS); FP64 contexts only */
+    int32_t reserved0;
 } srhmc_config;
+
+/* samplers.lightsource_gym family: one chain per field with injected draws (the reference's np.random order is
+ * p_sample() once, then per iteration p_sample(), randint(steps_min, steps_max), random(); samplers.py:507,520,529,562).
+ * Shapes (F fields, S = 3*max_stars, L = niter+1): q0 [F,S]; dt [S] per-coordinate (HMC, HESS, TRIAL) or [1] global
+ * (DIAG); normals [F,L,S] (row 0 = the initial p_sample; TRIAL ignores row 0); steps [F,niter]; lnu [F,niter];
+ * background [F,R,C] (TRIAL: HMC_find_best_dt's model_data, replaces the constant B) or NULL;
+ * outputs (any may be NULL): q_chain [F,L,S], E_chain, dE_chain [F,L], A_chain [F,niter], q_final [F,S],
+ * accept_count [F]. */
+typedef enum srhmc_ls_variant {
+    SRHMC_LS_HMC = 0,   /* lightsource_gym.HMC_random        samplers.py:460-572 */
+    SRHMC_LS_DIAG = 1,  /* lightsource_gym.RHMC_random_diag  samplers.py:668-825 */
+    SRHMC_LS_HESS = 2,  /* lightsource_gym.RHMC_random       samplers.py:930-1105 */
+    SRHMC_LS_TRIAL = 3  /* one acceptance-rate trial of HMC_find_best_dt  samplers.py:327-370, 395-432 */
+} srhmc_ls_variant;
+
+typedef struct srhmc_ls_args {
+    int32_t variant;
+    int32_t niter;
+    const double* q0;
+    const int32_t* nstars;
+    const double* dt;
+    int32_t n_dt;
+    int32_t zero_xy_momentum;  /* TRIAL: the flux-only tuning pass zeroes p_x, p_y (samplers.py:343-344) */
+    double f_lim;              /* gym.f_lim of the run (samplers.py:482-485) */
+    double factor1;            /* gym.factor1 (DIAG mass matrix, samplers.py:592-600) */
+    const double* normals;
+    const int32_t* steps;
+    const double* lnu;
+    const double* background;
+    double* q_chain;
+    double* E_chain;
+    double* dE_chain;
+    uint8_t* A_chain;
+    double* q_final;
+    double* accept_count;
+} srhmc_ls_args;
 
 /* Arguments of one resident chain run.  Replaces the move-0 leg of multi_gym.run_RHMC
  * (sampler_RHMC.py:1009-1083): all (niter+1) x nsteps leapfrog steps, the momentum refresh, the energies and the
@@ -109,6 +148,11 @@ typedef struct srhmc_run_args {
      * ids[rank::world] passes base = rank, stride = world and reproduces the single-GPU run bit for bit. */
     int32_t field_id_base;
     int32_t field_id_stride;
+    /* Optional explicit ids [F] overriding base/stride (any shard map).  Note: the one-star kernel packs 4 consecutive
+     * fields into a warp and its row windows / log tiers are the union over the warp, so bit-identity with an
+     * unsharded run additionally needs shards made of whole groups of 4 consecutive chains (sharding.py does that);
+     * otherwise results agree to ~1e-15 relative. */
+    const int32_t* field_ids;
 } srhmc_run_args;
 
 int srhmc_abi_version(void);
@@ -172,6 +216,22 @@ int srhmc_run_download(srhmc_ctx* ctx, const srhmc_run_args* args);
 int srhmc_run_single(srhmc_ctx* ctx, const double* q0, const double* p0, const int32_t* nstars, int32_t nsteps,
                      double dt, double delta, int32_t counter_max, int32_t f_pos, double g_ff2, double beta,
                      double* q_chain, double* p_chain, double* E_chain, double* V_chain, double* T_chain);
+
+/* lightsource_gym chains (see srhmc_ls_args).  Contexts for these calls are created with use_prior = use_Vc = 0. */
+int srhmc_ls_run(srhmc_ctx* ctx, const srhmc_ls_args* args);
+
+/* Replaces lightsource_gym.RHMC_efficient_computation (samplers.py:828-927).  q, p [F,S]; f_lim as gym.f_lim;
+ * d2_only != 0: only d2 = dVdqq is produced and the flux floor is not checked (the reference's dVdqq_only=True);
+ * otherwise d1 = dVdq, d2, d3 = dVdqqq, dqdt, dpdt [F,S] and E [F] (all +inf when a flux is below f_lim).
+ * Needs enable_hessian = 1 at context creation. */
+int srhmc_hessian(srhmc_ctx* ctx, const double* q, const double* p, const int32_t* nstars, double f_lim, int32_t d2_only,
+                  double* d1, double* d2, double* d3, double* dqdt, double* dpdt, double* E);
+
+/* Potential and gradient of the fields' stars on a per-pixel background image replacing the constant B.  Replaces
+ * lightsource_gym.V_single / dVdq_single (samplers.py:77-127) with max_stars = 1 (background = model_data).
+ * q [F,S]; background [F,R,C]; V [F] = -sum(D ln Lambda - Lambda); grad [F,S]. */
+int srhmc_eval_background(srhmc_ctx* ctx, const double* q, const int32_t* nstars, const double* background, double* V,
+                          double* grad);
 
 /* Draws of the device generator, for replaying a Philox run through another implementation:
  * normals [F,L,S], lnu [F,L] exactly as srhmc_run would consume them for `seed`. */

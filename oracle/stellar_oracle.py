@@ -696,6 +696,103 @@ def ls_rhmc_random_diag(L: LightSetup, q0, dt_global, normals, steps, lnu, niter
     return out
 
 
+def ls_rhmc_random(L: LightSetup, q0, dt, normals, steps, lnu, niter, f_lim=0.0):
+    """Hessian-metric RHMC (lightsource_gym.RHMC_random, samplers.py:930-1105) with injected draws: normals[i] is the
+    p_sample of iteration i (0..niter); steps[i-1], lnu[i-1] belong to iteration i >= 1.  Quirks kept: the position
+    test `(x < 0) or (x < num_rows)` (:1038-1043) flags every in-image star, the flags are never cleared inside an
+    iteration, flagged momenta are sign-flipped instead of kicked, the state advances in place so a rejection does
+    not restore it (:1031), and a chain below 50% acceptance at a multiple of 100 iterations is abandoned."""
+    L = L.clone(f_lim=f_lim)
+    d = q0.size
+    n = d // 3
+    out = LsChains(q=np.zeros((niter + 1, d)), E=np.zeros(niter + 1), dE=np.zeros(niter + 1), A=np.zeros(niter))
+    q = np.array(q0, dtype=float)
+    p = np.zeros(d)
+    e_prev = 0.0
+    for i in range(niter + 1):
+        d2 = ls_efficient(L, q, p, dVdqq_only=True)
+        p = normals[i] * np.sqrt(d2)
+        dqdt, dpdt, E = ls_efficient(L, q, p)
+        if i == 0:
+            out.q[0] = q
+            out.E[0] = E
+            e_prev = E
+            continue
+        e0 = E
+        out.E[i] = e0
+        out.dE[i] = e0 - e_prev
+        nst = int(steps[i - 1])
+        p_half = p + dt * dpdt / 2.0
+        flag = np.zeros(d, dtype=bool)
+        for z in range(nst):
+            dqdt, dpdt, E = ls_efficient(L, q, p_half)
+            if E == np.inf:
+                break
+            q += dt * dqdt
+            for k in range(n):
+                if q[3 * k] < L.f_lim:
+                    flag[3 * k] = True
+                if (q[3 * k + 1] < 0) or (q[3 * k + 1] < L.num_rows):
+                    flag[3 * k + 1] = True
+                if (q[3 * k + 2] < 0) or (q[3 * k + 2] < L.num_rows):
+                    flag[3 * k + 2] = True
+            dt_tmp = dt / 2.0 if z == nst - 1 else dt
+            dqdt, dpdt, E = ls_efficient(L, q, p_half)
+            neg = -p_half
+            p_half = p_half + dt_tmp * dpdt
+            p_half[flag] = neg[flag]
+        _, _, e1 = ls_efficient(L, q, p_half)
+        dE = e1 - e0
+        e_prev = e0
+        if (dE < 0) or (lnu[i - 1] < -dE):
+            out.A[i - 1] = 1
+        out.q[i] = q
+        if (i % 100) == 0 and np.sum(out.A[:i]) * 100 / float(i) < 50:
+            break
+    return out
+
+
+def ls_single(L: LightSetup, q_single, model_data):
+    """V_single and the full dVdq_single on a model_data background (samplers.py:77-127)."""
+    f, x, y = q_single
+    psf = gauss_psf(L.num_rows, L.num_cols, x, y, L.PSF_FWHM_pix)
+    lam = model_data + f * psf
+    rho = (L.D / lam) - 1.0
+    li = np.arange(0, L.num_rows)[:, None] * np.ones((1, L.num_cols), dtype=int)
+    mj = np.arange(0, L.num_cols)[None, :] * np.ones((L.num_rows, 1), dtype=int)
+    var = (L.PSF_FWHM_pix / FWHM_TO_SIGMA) ** 2
+    g = np.array([-np.sum(rho * psf), -np.sum(rho * (li - x + 0.5) * psf) * f / var,
+                  -np.sum(rho * (mj - y + 0.5) * psf) * f / var])
+    return -np.sum(L.D * np.log(lam) - lam), g
+
+
+def ls_trial(L: LightSetup, q_start, model_data, dt, normals, steps, lnu, zero_xy):
+    """One acceptance-rate trial of HMC_find_best_dt (samplers.py:327-370): single-star HMC on model_data whose
+    leapfrog kicks all three momenta with the scalar FLUX gradient (dVdq_single's default f_only=True).
+    normals[i], steps[i-1], lnu[i-1] belong to iteration i = 1..n.  Returns the number of accepted proposals."""
+    q = np.array(q_start, dtype=float)
+    acc = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(1, len(steps) + 1):
+            q_init = q
+            p = np.array(normals[i], dtype=float)
+            if zero_xy:
+                p[1:] = 0
+            e0 = ls_single(L, q, model_data)[0] + np.dot(p, p) / 2.0
+            p_half = p - dt * ls_single(L, q, model_data)[1][0] / 2.0
+            for _ in range(int(steps[i - 1])):
+                q = q + dt * p_half
+                p_half = p_half - dt * ls_single(L, q, model_data)[1][0]
+            p = p_half + dt * ls_single(L, q, model_data)[1][0] / 2.0
+            e1 = ls_single(L, q, model_data)[0] + np.dot(p, p) / 2.0
+            dE = e1 - e0
+            if (dE < 0) or (lnu[i - 1] < -dE):
+                acc += 1
+            else:
+                q = q_init
+    return acc
+
+
 def star_steps(niter_plus_one: int, nsteps: int, nstars: int) -> int:
     """Units of BASELINE.json's metric produced by one run_rhmc call."""
     return niter_plus_one * nsteps * nstars

@@ -276,7 +276,65 @@ def light_chains(seed=11, niter=40, mT=19.0):
                 B_count=np.float64(gym.B_count), PSF_FWHM_pix=np.float64(gym.PSF_FWHM_pix))
 
 
+def light_hess(seed=21, niter=40, mT=19.0):
+    """lightsource_gym.RHMC_random (Hessian metric) and RHMC_efficient_computation on Poisson data."""
+    np.random.seed(seed)
+    gym = smp.lightsource_gym()
+    gym.num_rows = gym.num_cols = 32
+    q0 = np.array([[utils.mag2flux(mT) * gym.flux_to_count, 16.0 + 0.3 * np.random.randn(), 16.0 + 0.3 * np.random.randn()]])
+    gym.gen_mock_data(q_true=q0)
+    f_lim = utils.mag2flux(22.0) * gym.flux_to_count
+    gym.f_lim = f_lim
+    gym.Nobjs, gym.d = 1, 3
+    qe = q0.reshape(-1) * np.array([1.02, 1.0, 1.0]) + np.array([0.0, 0.21, -0.13])
+    pe = np.array([0.01, -0.4, 0.3])
+    dqdt, dpdt, E = gym.RHMC_efficient_computation(qe, pe, debug=False)
+    d2 = gym.RHMC_efficient_computation(qe, pe, debug=False, dVdqq_only=True)
+    q_start = np.copy(q0)
+    with ref_shim.quiet():
+        gym.RHMC_random(q_start, Nchain=1, Niter=niter, steps_max=12, steps_min=4, f_lim=f_lim, dt_RHMC_xy=0.3,
+                        dt_RHMC_f=0.3, debug=False)
+    return dict(D=gym.D, q0=q0.reshape(-1), f_lim=f_lim, niter=niter, seed=seed, qe=qe, pe=pe, dqdt=dqdt, dpdt=dpdt,
+                E_eff=E, dVdqq=d2, q_chain=gym.q_chain[0].copy(), E_chain=gym.E_chain[0, :, 0].copy(),
+                dE_chain=gym.dE_chain[0, :, 0].copy(), A_chain=gym.A_chain[0, :, 0].copy(),
+                q_after=q_start.reshape(-1).copy(), next_uniform=np.random.random(1),
+                B_count=np.float64(gym.B_count), PSF_FWHM_pix=np.float64(gym.PSF_FWHM_pix))
+
+
+def best_dt(seed=31, mT=19.0):
+    """lightsource_gym.HMC_find_best_dt followed by a short HMC_random (one-star-inference-single.py:21-71)."""
+    np.random.seed(seed)
+    gym = smp.lightsource_gym()
+    gym.num_rows = gym.num_cols = 32
+    q0 = np.array([[utils.mag2flux(mT) * gym.flux_to_count, 16.0 + np.random.randn(), 16.0 + np.random.randn()]])
+    gym.gen_mock_data(q_true=q0)
+    model_data = np.ones((32, 32)) * gym.B_count * 1.1
+    qs = q0.reshape(-1)
+    Vs = gym.V_single(qs, model_data)
+    gs = np.array(gym.dVdq_single(qs, model_data, return_all=True))
+    with ref_shim.quiet():
+        gym.HMC_find_best_dt(q0, default=False, dt_f_coeff=1, dt_xy_coeff=10, Niter_per_trial=20, Ntrial=6,
+                             steps_min=5, steps_max=12, A_target_f=0.99, A_target_xy=0.5)
+    dt_vec = np.copy(gym.dt)
+    f_lim = utils.mag2flux(22.0) * gym.flux_to_count
+    with ref_shim.quiet():
+        gym.HMC_random(np.copy(q0), Nchain=1, Niter=25, steps_max=20, steps_min=5, f_lim=f_lim)
+    return dict(D=gym.D, q0=qs, seed=seed, dt_vec=dt_vec, f_lim=f_lim, model_data=model_data, V_single=Vs,
+                dVdq_single=gs, q_chain=gym.q_chain[0].copy(), E_chain=gym.E_chain[0, :, 0].copy(),
+                A_chain=gym.A_chain[0, :, 0].copy(), next_uniform=np.random.random(1),
+                B_count=np.float64(gym.B_count), PSF_FWHM_pix=np.float64(gym.PSF_FWHM_pix))
+
+
 def main():
+    only = sys.argv[1:]
+    if only:
+        makers = {"light_hess": light_hess, "best_dt": best_dt}
+        for name in only:
+            arrays = makers[name]()
+            path = os.path.join(HERE, name + ".npz")
+            np.savez_compressed(path, **arrays)
+            print("%-24s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
+        return
     cases = {
         "kat1": kat1(),
         "kat2": kat2(),
@@ -290,6 +348,8 @@ def main():
         "single_traj": single_traj(),
         "field_eval_204": field_eval(),
         "light_chains": light_chains(),
+        "light_hess": light_hess(),
+        "best_dt": best_dt(),
     }
     for name, arrays in cases.items():
         path = os.path.join(HERE, name + ".npz")

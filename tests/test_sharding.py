@@ -15,7 +15,10 @@ def test_shard_ids_partition_every_batch():
             parts = [sharding.shard_ids(n, r, world) for r in range(world)]
             assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
             assert [len(p) for p in parts] == list(sharding.shard_counts(n, world))
-            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= sharding.BLOCK
+            for p in parts:  # whole warp groups stay together
+                assert all(len(set(p[p // sharding.BLOCK == b])) in (0, min(sharding.BLOCK, n - b * sharding.BLOCK))
+                           for b in np.unique(p // sharding.BLOCK))
     with pytest.raises(ValueError):
         sharding.shard_ids(4, 2, 2)
 
@@ -39,12 +42,11 @@ def _worker(rank, world, port, n_items, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        def run_local(ids, base, stride):
+        def run_local(ids):
             # a stand-in for the resident launch: results are pure functions of the GLOBAL chain id, which is what
-            # the device RNG keying (field_id_base + i * field_id_stride) guarantees on the GPU
-            assert base == rank and stride == world
-            gid = base + stride * np.arange(len(ids))
-            assert np.array_equal(gid, ids)
+            # the device RNG keying (field_ids) guarantees on the GPU
+            assert np.array_equal(ids, sharding.shard_ids(n_items, rank, world))
+            gid = ids
             return {"q_final": np.stack([gid * 1.5, gid + 0.25, -gid], axis=1).astype(float),
                     "accept_rate": (gid % 7) / 7.0,
                     "A_chain": (gid[:, None] + np.arange(4)[None, :]) % 2 == 0}
@@ -82,7 +84,7 @@ def test_two_rank_gloo_gather_restores_global_order(n_items):
 
 @pytest.mark.gpu
 def test_sharded_run_is_bit_identical_to_single_context():
-    """Two shards run one after the other on cuda:0 with (base, stride) = (r, 2) reproduce the unsharded batch."""
+    """Two shards run one after the other on cuda:0 with their global chain ids reproduce the unsharded batch."""
     import stellar_oracle as so
     from helpers import golden, setup_from
     from test_gpu_parity import make_ctx
