@@ -122,6 +122,31 @@ class RunArgs(C.Structure):
     ]
 
 
+class BigConfig(C.Structure):
+    """struct srhmc_big_config"""
+
+    _fields_ = [(n, C.c_int32) for n in ("abi_version", "device", "rows_global", "cols", "own_lo", "own_hi", "row0",
+                                         "nrows", "nrows_halo", "max_stars", "max_ghosts", "patch_radius", "use_prior",
+                                         "world_size", "rank")] + \
+               [(n, C.c_double) for n in ("psf_fwhm_pix", "B_count", "f_lim", "f_low", "g0", "g1", "g2", "g_xx", "g_ff",
+                                          "alpha", "V_prior_const")]
+
+
+class BigStep(C.Structure):
+    """struct srhmc_big_step"""
+
+    _fields_ = [("dt", C.c_double), ("delta", C.c_double), ("g_ff2", C.c_double), ("counter_max", C.c_int32),
+                ("f_pos", C.c_int32), ("iteration", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
+
+
+class BigBuffers(C.Structure):
+    """struct srhmc_big_buffers_t"""
+
+    _fields_ = [("ghost_send", C.c_void_p), ("ghost_send_doubles", C.c_int64), ("ghost_recv", C.c_void_p),
+                ("ghost_recv_doubles", C.c_int64), ("scalars", C.c_void_p), ("global_scalars", C.c_void_p),
+                ("n_scalars", C.c_int64), ("counters", C.c_void_p), ("n_counters", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/stellar_rhmc.h
 SIGNATURES = {
     "srhmc_abi_version": (C.c_int, []),
@@ -160,6 +185,23 @@ SIGNATURES = {
                                          c_double_p]),
     "srhmc_test_device_math": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32]),
     "srhmc_measure_fma_peak": (C.c_int, [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_float)]),
+    "srhmc_big_last_error": (C.c_char_p, []),
+    "srhmc_big_create": (C.c_int, [C.POINTER(BigConfig), C.POINTER(C.c_void_p)]),
+    "srhmc_big_destroy": (C.c_int, [C.c_void_p]),
+    "srhmc_big_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srhmc_big_synchronize": (C.c_int, [C.c_void_p]),
+    "srhmc_big_launch_count": (C.c_int64, [C.c_void_p]),
+    "srhmc_big_set_data": (C.c_int, [C.c_void_p, c_double_p]),
+    "srhmc_big_set_stars": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int32]),
+    "srhmc_big_get_stars": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "srhmc_big_set_momenta": (C.c_int, [C.c_void_p, c_double_p]),
+    "srhmc_big_buffers": (C.c_int, [C.c_void_p, C.POINTER(BigBuffers)]),
+    "srhmc_big_set_draws": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32]),
+    "srhmc_big_alloc_chains": (C.c_int, [C.c_void_p, C.c_int32]),
+    "srhmc_big_read_chains": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_uint8_p,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "srhmc_big_read_scalars": (C.c_int, [C.c_void_p, c_double_p]),
+    "srhmc_big_phase": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(BigStep)]),
 }
 
 
@@ -199,6 +241,11 @@ def load_library(path: str | None = None):
 def check(code):
     if code != 0:
         raise SrhmcError(code, load_library().srhmc_last_error().decode("utf-8", "replace"))
+
+
+def check_big(code):
+    if code != 0:
+        raise SrhmcError(code, load_library().srhmc_big_last_error().decode("utf-8", "replace"))
 
 
 def dptr(a):

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libstellar_rhmc.so")
-SOURCES = ["stellar_rhmc.cu", "field_kernels_f64.cu", "field_kernels_f32.cu", "chain_kernels.cu", "ls_kernels.cu",
+SOURCES = ["stellar_rhmc.cu", "field_kernels_f64.cu", "field_kernels_f32.cu", "chain_kernels.cu", "ls_kernels.cu", "big_field.cu",
            "misc_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c"]

@@ -1,0 +1,787 @@
+// Large-field RHMC engine: one crowded field too big for a single CTA (BASELINE configs[2] scaled up and configs[4]),
+// optionally one row-strip of a field tiled over several GPUs.
+//
+// State lives in global memory; one leapfrog step is a fixed sequence of small kernels enqueued on the context's
+// stream with no host synchronisation (the only host involvement inside a chain is enqueueing, plus -- when the
+// field is tiled over GPUs -- the collectives between phases, which the caller issues on the same stream):
+//
+//   scatter  one warp per star adds f PSF over its (2r+1)^2 patch into the model image Lambda (FP64 atomics into L2)
+//   pixel    rho = D/Lambda - 1 in place, V = sum(Lambda - D ln Lambda) over the OWNED rows (fixed-order partials)
+//   gather   one warp per star: the three residual-weighted PSF reductions over its patch (shuffle reductions)
+//   scalar   one thread per star: metric, half kicks, both implicit fixed points, reflections, momentum refresh
+//
+// The reference's field-wide stop rule of the fixed-point loops (sampler_RHMC.py:533,543: max over ALL stars) is kept
+// exactly with two phases per loop: phase A iterates every star to its own convergence and takes the maximum count
+// (atomicMax; across GPUs an all-reduce(max) by the caller), phase B continues every star to that count.  The
+// per-star iterations are contractions, so a star that met the tolerance stays within it (same result as iterating
+// all stars together).
+//
+// Tiling: a rank owns global rows [own_lo, own_hi) and holds data rows [row0, row0+nrows) (strip + halo).  Owned
+// stars may drift `halo - patch_radius` rows outside the strip; neighbours' stars that can touch the local rows
+// arrive as ghosts (f, x, y) in the gathered boundary buffers and are only rendered, never updated.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/stellar_rhmc.h"
+#include "common.cuh"
+
+using namespace srhmc;
+
+namespace {
+
+thread_local char g_big_err[512] = "";
+
+int bfail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_big_err, sizeof(g_big_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define BCU(expr)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return bfail(SRHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct BigParams {
+    int Rg, C;              // global rows, columns
+    int row0, nrows;        // local data rows [row0, row0 + nrows)
+    int own_lo, own_hi;     // owned rows
+    int rad;
+    int use_prior;
+    double inv2s2, inv_s2, norm;
+    FieldParams F;          // constants for metric_of (B, g0.., f_low, f_lim, alpha, Vpc)
+};
+
+constexpr int kMaxRad = 15;
+constexpr int kScalars = 8;   // [0] V partial, [1] T partial, [2] bad count, [3] spare ... (doubles)
+constexpr int kVBlocks = 1024;
+
+// ------------------------------------------------------------------------------------------------ pixel kernels
+__global__ void big_fill_kernel(double* L, size_t n, double B) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) L[i] = B;
+}
+
+// Patch geometry of a star in LOCAL row indices.  Returns false when the star does not touch the local rows.
+// `clipped_by_data` is set when the patch is cut by the local data window but not by the global image edge.
+__device__ __forceinline__ bool patch_of(const BigParams& P, double x, double y, int& i0, int& i1, int& j0, int& j1,
+                                         int& mi, int& mj, bool& clipped_by_data) {
+    const double fx = floor(x), fy = floor(y);
+    mi = (fx > 0.0) ? ((fx > (double)(P.Rg - 1)) ? P.Rg - 1 : (int)fx) : 0;
+    mj = (fy > 0.0) ? ((fy > (double)(P.C - 1)) ? P.C - 1 : (int)fy) : 0;
+    const int gi0 = max(0, mi - P.rad), gi1 = min(P.Rg - 1, mi + P.rad);
+    j0 = max(0, mj - P.rad);
+    j1 = min(P.C - 1, mj + P.rad);
+    i0 = max(gi0, P.row0);
+    i1 = min(gi1, P.row0 + P.nrows - 1);
+    clipped_by_data = (i0 != gi0) || (i1 != gi1);
+    return i0 <= i1;
+}
+
+// One warp per star (own stars first, then the two ghost lists).  ghost list layout: [0] = count, then f,x,y triples.
+__global__ void big_scatter_kernel(const BigParams P, const double* q, int n_own, const double* ghost_a,
+                                   const double* ghost_b, double* L, int* err) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int na = ghost_a ? (int)ghost_a[0] : 0, nb = ghost_b ? (int)ghost_b[0] : 0;
+    const long long total = (long long)n_own + na + nb;
+    for (long long s = warp; s < total; s += nwarps) {
+        const double* src = s < n_own ? q + 3 * s : (s < n_own + na ? ghost_a + 1 + 3 * (s - n_own) : ghost_b + 1 + 3 * (s - n_own - na));
+        const double f = src[0], x = src[1], y = src[2];
+        int i0, i1, j0, j1, mi, mj;
+        bool clipped;
+        if (!patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
+            if (s < n_own && lane == 0) atomicExch(err, 1);  // an owned star left the local data window
+            continue;
+        }
+        if (s < n_own && clipped && lane == 0) atomicExch(err, 1);
+        // lanes own columns j0 + lane (2 rad + 1 <= 31 columns); row factors by shuffle
+        const int j = j0 + lane;
+        const bool okc = j <= j1;
+        const double dy = ((double)j + 0.5) - y;
+        const double ey = okc ? exp(-(dy * dy) * P.inv2s2) * P.norm * f : 0.0;
+        const int irow = i0 + lane;
+        const double dxl = ((double)(irow + 0) + 0.5) - x;
+        const double exl = (irow <= i1) ? exp(-(dxl * dxl) * P.inv2s2) : 0.0;
+        for (int i = i0; i <= i1; ++i) {
+            const double ex = __shfl_sync(0xffffffffu, exl, i - i0);
+            if (okc) atomicAdd(&L[(size_t)(i - P.row0) * P.C + j], ex * ey);
+        }
+    }
+}
+
+// rho = D/Lambda - 1 in place; V over owned rows; per-block partials in fixed order.
+__global__ void big_pixel_kernel(const BigParams P, const double* D, double* L, int want_V, double* vpart) {
+    __shared__ double red[32];
+    const size_t n = (size_t)P.nrows * P.C;
+    const size_t own0 = (size_t)(P.own_lo - P.row0) * P.C, own1 = (size_t)(P.own_hi - P.row0) * P.C;
+    double v = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double lam = L[i], d = D[i];
+        L[i] = d / lam - 1.0;
+        if (want_V && i >= own0 && i < own1) v += lam - d * log(lam);
+    }
+    if (want_V) {
+        double a[1] = {v};
+        block_sum<1>(a, red);
+        if (threadIdx.x == 0) vpart[blockIdx.x] = a[0];
+    }
+}
+
+// sum of the per-block partials in index order (one block) -> scalars[0]
+__global__ void big_vsum_kernel(const double* vpart, int nblocks, double* scalars) {
+    __shared__ double red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += vpart[i];
+    double a[1] = {v};
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) scalars[0] = a[0];
+}
+
+// One warp per OWNED star: g_f = -sum rho PSF, g_x = -(f/s^2) sum rho dx PSF, g_y likewise (sampler_RHMC.py:404-406).
+__global__ void big_gather_kernel(const BigParams P, const double* q, int n_own, const double* L, double* g) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long s = warp; s < n_own; s += nwarps) {
+        const double f = q[3 * s], x = q[3 * s + 1], y = q[3 * s + 2];
+        int i0, i1, j0, j1, mi, mj;
+        bool clipped;
+        double sf = 0.0, sx = 0.0, sy = 0.0;
+        if (patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
+            const int j = j0 + lane;
+            const bool okc = j <= j1;
+            const double dy = ((double)j + 0.5) - y;
+            const double ey = okc ? exp(-(dy * dy) * P.inv2s2) * P.norm : 0.0;
+            const int irow = i0 + lane;
+            const double dxl = ((double)irow + 0.5) - x;
+            const double exl = (irow <= i1) ? exp(-(dxl * dxl) * P.inv2s2) : 0.0;
+            double c0 = 0.0, c1 = 0.0;
+            for (int i = i0; i <= i1; ++i) {
+                const double ex = __shfl_sync(0xffffffffu, exl, i - i0);
+                const double dx = ((double)i + 0.5) - x;
+                const double rho = okc ? L[(size_t)(i - P.row0) * P.C + j] : 0.0;
+                c0 = fma(rho, ex, c0);
+                c1 = fma(rho, ex * dx, c1);
+            }
+            sf = ey * c0;
+            sx = ey * c1;
+            sy = ey * dy * c0;
+        }
+        sf = warp_sum(sf);
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        if (lane == 0) {
+            g[3 * s] = -sf;
+            g[3 * s + 1] = -sx * f * P.inv_s2;
+            g[3 * s + 2] = -sy * f * P.inv_s2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ scalar kernels
+struct BigStep {
+    double h, delta, g_ff2;
+    int counter_max;
+};
+
+__device__ __forceinline__ double dphi_f(const BigParams& P, const Metric& m, double gpix_f, double f) {
+    double gf = gpix_f;
+    if (P.use_prior) gf += P.F.alpha / f;
+    return gf + ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+}
+
+// (1) p -= h dphi/dq; (2) p fixed point, phase A: iterate to this star's own convergence, record the count
+__global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, const double* g,
+                                 double* a1, double* a2, int* cnt) {
+    int local_max = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double f = q[3 * k];
+        const Metric m = metric_of(P.F, f, S.g_ff2);
+        double pf = p[3 * k] - S.h * dphi_f(P, m, g[3 * k], f);
+        p[3 * k + 1] -= S.h * g[3 * k + 1];
+        p[3 * k + 2] -= S.h * g[3 * k + 2];
+        const double rho = pf, kap = -m.dHff / (m.Hff * m.Hff);
+        a1[3 * k] = rho;      // anchor
+        a2[3 * k] = kap;
+        int c = 0;
+        while (c < S.counter_max) {
+            const double pn = rho - S.h * (((pf * pf) * kap) / 2.0);
+            const bool more = fabs(pf - pn) > S.delta;
+            pf = pn;
+            ++c;
+            if (!more) break;
+        }
+        p[3 * k] = pf;
+        a1[3 * k + 1] = (double)c;  // own count
+        local_max = max(local_max, c);
+    }
+    if (local_max) atomicMax(cnt, local_max);
+}
+
+// p fixed point phase B (continue to the global count), then (3) q fixed point phase A
+__global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, double* a1, double* a2,
+                                     const int* cnt_p, int* cnt_q) {
+    const int target = *cnt_p;
+    int local_max = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double pf = p[3 * k];
+        const double rho = a1[3 * k], kap = a2[3 * k];
+        for (int c = (int)a1[3 * k + 1]; c < target; ++c) pf = rho - S.h * (((pf * pf) * kap) / 2.0);
+        p[3 * k] = pf;
+        // q' = sigma + h (p/H(sigma) + p/H(q))
+        const double sf = q[3 * k], sx = q[3 * k + 1], sy = q[3 * k + 2];
+        const double px = p[3 * k + 1], py = p[3 * k + 2];
+        const Metric m0 = metric_of(P.F, sf, S.g_ff2);
+        const double bf = pf / m0.Hff, bx = px / m0.Hxx, by = py / m0.Hxx;
+        double qf = sf, qx = sx, qy = sy;
+        int c = 0;
+        while (c < S.counter_max) {
+            const Metric m = metric_of(P.F, qf, S.g_ff2);
+            const double nf = sf + S.h * (bf + pf / m.Hff);
+            const double nx = sx + S.h * (bx + px / m.Hxx);
+            const double ny = sy + S.h * (by + py / m.Hxx);
+            const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
+            qf = nf; qx = nx; qy = ny;
+            ++c;
+            if (!(d > S.delta)) break;
+        }
+        a1[3 * k] = sf; a1[3 * k + 1] = sx; a1[3 * k + 2] = sy;   // sigma
+        a2[3 * k] = bf; a2[3 * k + 1] = bx; a2[3 * k + 2] = by;   // p/H(sigma)
+        q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
+        // own count rides in the sign-free spare: store in g-independent slot via a2? keep it in a separate array
+        // (written below through cnt_own)
+        local_max = max(local_max, c);
+        // stash own count in the low bits of nothing: use p-array neighbour? -> dedicated array in launcher (a3)
+        reinterpret_cast<int*>(a2 + 3 * (size_t)n)[k] = c;
+    }
+    if (local_max) atomicMax(cnt_q, local_max);
+}
+
+// q fixed point phase B, then (4) p -= h dtau/dq at the new q
+__global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
+                                     const double* a2, const int* cnt_q) {
+    const int target = *cnt_q;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
+        const double bf = a2[3 * k], bx = a2[3 * k + 1], by = a2[3 * k + 2];
+        const double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
+        double qf = q[3 * k], qx = q[3 * k + 1], qy = q[3 * k + 2];
+        for (int c = reinterpret_cast<const int*>(a2 + 3 * (size_t)n)[k]; c < target; ++c) {
+            const Metric m = metric_of(P.F, qf, S.g_ff2);
+            qf = sf + S.h * (bf + pf / m.Hff);
+            qx = sx + S.h * (bx + px / m.Hxx);
+            qy = sy + S.h * (by + py / m.Hxx);
+        }
+        q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
+        const Metric m = metric_of(P.F, qf, S.g_ff2);
+        p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+    }
+}
+
+// (5) p -= h dphi/dq at the new q; (6) reflections
+__global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, const double* g) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
+        const Metric m = metric_of(P.F, f, S.g_ff2);
+        double pf = p[3 * k] - S.h * dphi_f(P, m, g[3 * k], f);
+        double px = p[3 * k + 1] - S.h * g[3 * k + 1];
+        double py = p[3 * k + 2] - S.h * g[3 * k + 2];
+        if (f < P.F.f_lim) pf *= -1.0;
+        if ((x < 0.0) || (x > P.Rg - 1.0)) px *= -1.0;
+        if ((y < 0.0) || (y > P.C - 1.0)) py *= -1.0;
+        p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
+    }
+}
+
+// momentum refresh p = z sqrt(H) (sampler_RHMC.py:1021-1022) with device Philox keyed by the GLOBAL star id, or
+// injected normals; saves the iteration's start state
+__global__ void big_momentum_kernel(const BigParams P, double g_ff2, int n, const double* q, double* p, const double* g,
+                                    double* q0, double* g0, const long long* gid, unsigned long long seed, int iter,
+                                    const double* normals /* [n,3] for this iteration, or nullptr */) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const Metric m = metric_of(P.F, q[3 * k], g_ff2);
+        double z[3];
+        if (normals) {
+            z[0] = normals[3 * k]; z[1] = normals[3 * k + 1]; z[2] = normals[3 * k + 2];
+        } else {
+            philox_normals3(seed, 0u, (uint32_t)iter, (uint32_t)gid[k], z);
+        }
+        p[3 * k] = z[0] * sqrt(m.Hff);
+        p[3 * k + 1] = z[1] * sqrt(m.Hxx);
+        p[3 * k + 2] = z[2] * sqrt(m.Hxx);
+        for (int c = 0; c < 3; ++c) {
+            q0[3 * k + c] = q[3 * k + c];
+            g0[3 * k + c] = g[3 * k + c];
+        }
+    }
+}
+
+// scalars[1] = sum (p^2/H + ln|H|)/2, scalars[2] = # stars outside the support, scalars[3] = prior potential
+// (fixed-order: one block)
+__global__ void big_energy_kernel(const BigParams P, double g_ff2, int f_pos, int n, const double* q, const double* p,
+                                  double* scalars) {
+    __shared__ double red[4 * 32];
+    double v[4] = {0, 0, 0, 0};
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
+        const Metric m = metric_of(P.F, f, g_ff2);
+        const double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
+        v[0] += pf * pf / m.Hff + px * px / m.Hxx + py * py / m.Hxx;
+        v[1] += log(fabs(m.Hff)) + 2.0 * log(fabs(m.Hxx));
+        if (P.use_prior) v[2] += P.F.alpha * log(f) + P.F.Vpc;
+        const bool bad = (f_pos && f < P.F.f_lim) || (x < -1.0) || (x > P.Rg + 1.0) || (y < -1.0) || (y > P.C + 1.0);
+        v[3] += bad ? 1.0 : 0.0;
+    }
+    block_sum<4>(v, red);
+    if (threadIdx.x == 0) {
+        scalars[1] = (v[0] + v[1]) / 2.0;
+        scalars[2] = v[3];
+        scalars[3] = v[2];
+    }
+}
+
+// E = V + T from the (all-reduced) scalars: slot 4 <- E (kept as E0 when `first`), accept test otherwise
+__global__ void big_accept_kernel(int phase /*0: record E0, 1: accept*/, const double* scalars /* global sums */,
+                                  const double* local_scalars, double* state,
+                                  unsigned long long seed, int iter, const double* lnu_in, int n, double* q, double* g,
+                                  const double* q0, const double* g0, double* E_chain, double* V_chain, double* T_chain,
+                                  unsigned char* A_chain) {
+    // every thread evaluates the same scalars; thread 0 of block 0 writes the records
+    const double V = (scalars[2] > 0.0) ? CUDART_INF : scalars[0] + scalars[3];
+    const double T = scalars[1];
+    const double E = V + T;
+    if (phase == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            state[0] = E;              // E0
+            state[1] = local_scalars[0];  // this rank's pixel potential at the start (restored on rejection)
+            if (E_chain) E_chain[iter] = E;
+            if (V_chain) V_chain[iter] = V;
+            if (T_chain) T_chain[iter] = T;
+        }
+        return;
+    }
+    const double dE = E - state[0];
+    const double lnu = lnu_in ? lnu_in[iter] : philox_lnu(seed, 0u, (uint32_t)iter);
+    const bool accept = (dE < 0.0) || (lnu < -dE);
+    if (!accept) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) {
+            q[i] = q0[i];
+            g[i] = g0[i];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (A_chain) A_chain[iter] = accept ? 1 : 0;
+        state[2] = accept ? 1.0 : 0.0;
+        state[3] += accept ? 1.0 : 0.0;
+    }
+}
+// the pixel potential must follow the state on rejection: separate tiny kernel so that it runs after every block of
+// big_accept_kernel has read scalars[0]
+__global__ void big_restore_v_kernel(double* local_scalars, const double* state) {
+    if (state[2] == 0.0) local_scalars[0] = state[1];
+}
+
+// boundary stars for the neighbours: list 0 = stars with x < lo_edge (for the rank below), list 1 = x >= hi_edge.
+// Layout per list: [0] = count, then triples.  Order follows the star index (single block, ballot compaction).
+__global__ void big_pack_kernel(int n, const double* q, double lo_edge, double hi_edge, double* send, int cap, int* err) {
+    __shared__ int base[2];
+    if (threadIdx.x == 0) base[0] = base[1] = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        bool lo = false, hi = false;
+        double f = 0, x = 0, y = 0;
+        if (k < n) {
+            f = q[3 * k]; x = q[3 * k + 1]; y = q[3 * k + 2];
+            lo = x < lo_edge;
+            hi = x >= hi_edge;
+        }
+        // block-wide ordered compaction: per-warp ballots + serial warp offsets
+        __shared__ int wcount[2][32];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
+        if (lane == 0) { wcount[0][w] = __popc(blo); wcount[1][w] = __popc(bhi); }
+        __syncthreads();
+        int off_lo = base[0], off_hi = base[1];
+        for (int i = 0; i < w; ++i) { off_lo += wcount[0][i]; off_hi += wcount[1][i]; }
+        const unsigned lt = (1u << lane) - 1u;
+        if (lo) {
+            const int o = off_lo + __popc(blo & lt);
+            if (o < cap) { double* d = send + 1 + 3 * (size_t)o; d[0] = f; d[1] = x; d[2] = y; } else atomicExch(err, 2);
+        }
+        if (hi) {
+            const int o = off_hi + __popc(bhi & lt);
+            if (o < cap) { double* d = send + (1 + 3 * (size_t)cap) + 1 + 3 * (size_t)o; d[0] = f; d[1] = x; d[2] = y; } else atomicExch(err, 2);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < nw; ++i) { base[0] += wcount[0][i]; base[1] += wcount[1][i]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        send[0] = (double)min(base[0], cap);
+        send[1 + 3 * (size_t)cap] = (double)min(base[1], cap);
+    }
+}
+
+struct BBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        if (cudaMalloc(&ptr, bytes) != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(ptr); }
+};
+
+}  // namespace
+
+struct srhmc_big {
+    srhmc_big_config cfg;
+    BigParams P;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int n = 0;  // owned stars
+    int sm_count = 0;
+    int64_t launches = 0;
+    BBuf D, L, q, p, g, a1, a2, q0, g0, gid, vpart, scalars, gscalars, state, counters, send, recv, err, normals, lnu, E, V, T, A;
+    int world = 1, rank = 0;
+    bool have_data = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern "C" {
+
+const char* srhmc_big_last_error(void) { return g_big_err; }
+
+int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
+    if (!cfg || !out) return bfail(SRHMC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SRHMC_ABI_VERSION) return bfail(SRHMC_ERR_INVALID, "ABI version mismatch");
+    if (cfg->rows_global < 1 || cfg->cols < 1 || cfg->nrows < 1 || cfg->max_stars < 1)
+        return bfail(SRHMC_ERR_INVALID, "rows_global, cols, nrows, max_stars must be >= 1");
+    if (cfg->patch_radius < 1 || cfg->patch_radius > kMaxRad) return bfail(SRHMC_ERR_INVALID, "patch_radius must be 1..15");
+    if (cfg->row0 < 0 || cfg->row0 + cfg->nrows > cfg->rows_global || cfg->own_lo < cfg->row0 ||
+        cfg->own_hi > cfg->row0 + cfg->nrows || cfg->own_lo >= cfg->own_hi)
+        return bfail(SRHMC_ERR_INVALID, "inconsistent row ranges");
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return bfail(SRHMC_ERR_INVALID, "bad rank / world_size");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return bfail(SRHMC_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return bfail(SRHMC_ERR_INVALID, "device out of range");
+    BCU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    BCU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return bfail(SRHMC_ERR_NO_DEVICE, "device is sm_%d%d; the kernels are built for sm_100a only", prop.major, prop.minor);
+    srhmc_big* b = new (std::nothrow) srhmc_big();
+    if (!b) return bfail(SRHMC_ERR_INVALID, "out of host memory");
+    b->cfg = *cfg;
+    b->sm_count = prop.multiProcessorCount;
+    b->world = cfg->world_size;
+    b->rank = cfg->rank;
+    BigParams& P = b->P;
+    std::memset(&P, 0, sizeof(P));
+    P.Rg = cfg->rows_global; P.C = cfg->cols; P.row0 = cfg->row0; P.nrows = cfg->nrows;
+    P.own_lo = cfg->own_lo; P.own_hi = cfg->own_hi; P.rad = cfg->patch_radius; P.use_prior = cfg->use_prior ? 1 : 0;
+    const double sigma = cfg->psf_fwhm_pix / 2.354;
+    P.inv2s2 = 1.0 / (2.0 * sigma * sigma);
+    P.inv_s2 = 1.0 / (sigma * sigma);
+    P.norm = 1.0 / (M_PI * 2.0 * sigma * sigma);
+    P.F.B = cfg->B_count; P.F.f_lim = cfg->f_lim; P.F.f_low = cfg->f_low;
+    P.F.g0 = cfg->g0; P.F.g1 = cfg->g1; P.F.g2 = cfg->g2; P.F.g_xx = cfg->g_xx; P.F.g_ff = cfg->g_ff;
+    P.F.alpha = cfg->alpha; P.F.Vpc = cfg->V_prior_const;
+    const size_t npix = (size_t)cfg->nrows * cfg->cols, S = 3 * (size_t)cfg->max_stars;
+    const size_t list = 1 + 3 * (size_t)std::max(1, cfg->max_ghosts);
+    int rc = 0;
+    rc |= b->D.ensure(npix * 8); rc |= b->L.ensure(npix * 8);
+    rc |= b->q.ensure(S * 8); rc |= b->p.ensure(S * 8); rc |= b->g.ensure(S * 8);
+    rc |= b->a1.ensure(S * 8); rc |= b->a2.ensure(S * 8 + (size_t)cfg->max_stars * 4 + 8);
+    rc |= b->q0.ensure(S * 8); rc |= b->g0.ensure(S * 8); rc |= b->gid.ensure((size_t)cfg->max_stars * 8);
+    rc |= b->vpart.ensure(kVBlocks * 8); rc |= b->scalars.ensure(kScalars * 8); rc |= b->gscalars.ensure(kScalars * 8); rc |= b->state.ensure(8 * 8);
+    rc |= b->counters.ensure(4 * 4); rc |= b->err.ensure(4);
+    rc |= b->send.ensure(2 * list * 8); rc |= b->recv.ensure((size_t)cfg->world_size * 2 * list * 8);
+    if (rc) { srhmc_big_destroy(b); return SRHMC_ERR_CUDA; }
+    cudaMemset(b->scalars.ptr, 0, kScalars * 8);
+    cudaMemset(b->gscalars.ptr, 0, kScalars * 8);
+    cudaMemset(b->state.ptr, 0, 64);
+    cudaMemset(b->counters.ptr, 0, 16);
+    cudaMemset(b->err.ptr, 0, 4);
+    cudaMemset(b->send.ptr, 0, 2 * list * 8);
+    cudaMemset(b->recv.ptr, 0, (size_t)cfg->world_size * 2 * list * 8);
+    if (cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
+        srhmc_big_destroy(b);
+        return bfail(SRHMC_ERR_CUDA, "stream/event creation failed");
+    }
+    b->stream = b->own_stream;
+    *out = b;
+    return 0;
+}
+
+int srhmc_big_destroy(srhmc_big* b) {
+    if (!b) return 0;
+    cudaSetDevice(b->cfg.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
+                   &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A};
+    for (BBuf* x : all) x->release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    delete b;
+    return 0;
+}
+
+int srhmc_big_set_stream(srhmc_big* b, void* s) {
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    BCU(cudaSetDevice(b->cfg.device));
+    BCU(cudaStreamSynchronize(b->stream));
+    b->stream = s ? reinterpret_cast<cudaStream_t>(s) : b->own_stream;
+    return 0;
+}
+
+int srhmc_big_synchronize(srhmc_big* b) {
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    BCU(cudaSetDevice(b->cfg.device));
+    BCU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int64_t srhmc_big_launch_count(srhmc_big* b) { return b ? b->launches : 0; }
+
+int srhmc_big_set_data(srhmc_big* b, const double* D_local) {
+    if (!b || !D_local) return bfail(SRHMC_ERR_INVALID, "null argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    BCU(cudaMemcpyAsync(b->D.ptr, D_local, (size_t)b->cfg.nrows * b->cfg.cols * 8, cudaMemcpyHostToDevice, b->stream));
+    BCU(cudaStreamSynchronize(b->stream));
+    b->have_data = true;
+    return 0;
+}
+
+int srhmc_big_set_stars(srhmc_big* b, const double* q, const int64_t* global_ids, int32_t n) {
+    if (!b || (n > 0 && (!q || !global_ids))) return bfail(SRHMC_ERR_INVALID, "null argument");
+    if (n < 0 || n > b->cfg.max_stars) return bfail(SRHMC_ERR_INVALID, "%d stars exceed max_stars = %d", n, b->cfg.max_stars);
+    BCU(cudaSetDevice(b->cfg.device));
+    if (n) {
+        BCU(cudaMemcpyAsync(b->q.ptr, q, (size_t)n * 24, cudaMemcpyHostToDevice, b->stream));
+        BCU(cudaMemcpyAsync(b->gid.ptr, global_ids, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
+    }
+    BCU(cudaMemsetAsync(b->p.ptr, 0, 3 * (size_t)b->cfg.max_stars * 8, b->stream));
+    BCU(cudaStreamSynchronize(b->stream));
+    b->n = n;
+    return 0;
+}
+
+int srhmc_big_get_stars(srhmc_big* b, double* q, double* p, double* grad) {
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    BCU(cudaSetDevice(b->cfg.device));
+    if (b->n) {
+        if (q) BCU(cudaMemcpyAsync(q, b->q.ptr, (size_t)b->n * 24, cudaMemcpyDeviceToHost, b->stream));
+        if (p) BCU(cudaMemcpyAsync(p, b->p.ptr, (size_t)b->n * 24, cudaMemcpyDeviceToHost, b->stream));
+        if (grad) BCU(cudaMemcpyAsync(grad, b->g.ptr, (size_t)b->n * 24, cudaMemcpyDeviceToHost, b->stream));
+    }
+    BCU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int srhmc_big_set_momenta(srhmc_big* b, const double* p) {
+    if (!b || !p) return bfail(SRHMC_ERR_INVALID, "null argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    if (b->n) BCU(cudaMemcpyAsync(b->p.ptr, p, (size_t)b->n * 24, cudaMemcpyHostToDevice, b->stream));
+    BCU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int srhmc_big_buffers(srhmc_big* b, srhmc_big_buffers_t* out) {
+    if (!b || !out) return bfail(SRHMC_ERR_INVALID, "null argument");
+    const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
+    out->ghost_send = b->send.ptr;
+    out->ghost_send_doubles = (int64_t)(2 * list);
+    out->ghost_recv = b->recv.ptr;
+    out->ghost_recv_doubles = (int64_t)((size_t)b->world * 2 * list);
+    out->scalars = b->scalars.ptr;
+    out->global_scalars = b->gscalars.ptr;
+    out->n_scalars = kScalars;
+    out->counters = b->counters.ptr;
+    out->n_counters = 4;
+    return 0;
+}
+
+int srhmc_big_set_draws(srhmc_big* b, const double* normals, const double* lnu, int32_t n_iters) {
+    // normals [n_iters, n, 3] for the owned stars (parity mode) and lnu [n_iters]; either may be NULL (device Philox)
+    if (!b || n_iters < 0) return bfail(SRHMC_ERR_INVALID, "bad argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    b->normals.release();
+    b->lnu.release();
+    if (normals && b->n && n_iters) {
+        if (int rc = b->normals.ensure((size_t)n_iters * b->n * 24)) return rc;
+        BCU(cudaMemcpyAsync(b->normals.ptr, normals, (size_t)n_iters * b->n * 24, cudaMemcpyHostToDevice, b->stream));
+    }
+    if (lnu && n_iters) {
+        if (int rc = b->lnu.ensure((size_t)n_iters * 8)) return rc;
+        BCU(cudaMemcpyAsync(b->lnu.ptr, lnu, (size_t)n_iters * 8, cudaMemcpyHostToDevice, b->stream));
+    }
+    BCU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int srhmc_big_alloc_chains(srhmc_big* b, int32_t n_iters) {
+    if (!b || n_iters < 1) return bfail(SRHMC_ERR_INVALID, "bad argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    if (int rc = b->E.ensure((size_t)n_iters * 8)) return rc;
+    if (int rc = b->V.ensure((size_t)n_iters * 8)) return rc;
+    if (int rc = b->T.ensure((size_t)n_iters * 8)) return rc;
+    if (int rc = b->A.ensure((size_t)n_iters)) return rc;
+    BCU(cudaMemsetAsync(b->E.ptr, 0, (size_t)n_iters * 8, b->stream));
+    BCU(cudaMemsetAsync(b->V.ptr, 0, (size_t)n_iters * 8, b->stream));
+    BCU(cudaMemsetAsync(b->T.ptr, 0, (size_t)n_iters * 8, b->stream));
+    BCU(cudaMemsetAsync(b->A.ptr, 0, (size_t)n_iters, b->stream));
+    BCU(cudaMemsetAsync(b->state.ptr, 0, 64, b->stream));
+    return 0;
+}
+
+int srhmc_big_read_chains(srhmc_big* b, int32_t n_iters, double* E, double* V, double* T, uint8_t* A, double* n_accepted,
+                          int32_t* error_flag) {
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    BCU(cudaSetDevice(b->cfg.device));
+    if (E) BCU(cudaMemcpyAsync(E, b->E.ptr, (size_t)n_iters * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (V) BCU(cudaMemcpyAsync(V, b->V.ptr, (size_t)n_iters * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (T) BCU(cudaMemcpyAsync(T, b->T.ptr, (size_t)n_iters * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (A) BCU(cudaMemcpyAsync(A, b->A.ptr, (size_t)n_iters, cudaMemcpyDeviceToHost, b->stream));
+    double st[8] = {0};
+    int err = 0;
+    BCU(cudaMemcpyAsync(st, b->state.ptr, 64, cudaMemcpyDeviceToHost, b->stream));
+    BCU(cudaMemcpyAsync(&err, b->err.ptr, 4, cudaMemcpyDeviceToHost, b->stream));
+    BCU(cudaStreamSynchronize(b->stream));
+    if (n_accepted) *n_accepted = st[3];
+    if (error_flag) *error_flag = err;
+    return 0;
+}
+
+int srhmc_big_read_scalars(srhmc_big* b, double* scalars /* [8] local partial sums */) {
+    if (!b || !scalars) return bfail(SRHMC_ERR_INVALID, "null argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    BCU(cudaMemcpyAsync(scalars, b->scalars.ptr, kScalars * 8, cudaMemcpyDeviceToHost, b->stream));
+    BCU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+// Enqueue one phase on the context's stream (no synchronisation).  See srhmc_big_phase_id in the header.
+int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
+    if (!b || !s) return bfail(SRHMC_ERR_INVALID, "null argument");
+    if (!b->have_data) return bfail(SRHMC_ERR_STATE, "srhmc_big_set_data has not been called");
+    BCU(cudaSetDevice(b->cfg.device));
+    const BigParams& P = b->P;
+    const int n = b->n;
+    BigStep S;
+    S.h = s->dt / 2.0; S.delta = s->delta; S.g_ff2 = s->g_ff2; S.counter_max = s->counter_max;
+    const int tb = 128, gs = std::max(1, std::min((n + tb - 1) / tb, 4 * b->sm_count));
+    const size_t npix = (size_t)P.nrows * P.C;
+    const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
+    int* cnt = b->counters.as<int>();
+    cudaStream_t st = b->stream;
+    switch (phase) {
+        case SRHMC_BIG_PACK: {
+            // boundary lists for the neighbours: everything that can touch their data rows
+            const double reach = (double)(b->cfg.nrows_halo + P.rad + 1);
+            const double lo_edge = (b->rank > 0) ? (double)P.own_lo + reach : -1e300;
+            const double hi_edge = (b->rank < b->world - 1) ? (double)P.own_hi - reach : 1e300;
+            big_pack_kernel<<<1, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->send.as<double>(),
+                                                std::max(1, b->cfg.max_ghosts), b->err.as<int>());
+            b->launches += 1;
+            break;
+        }
+        case SRHMC_BIG_EVAL:
+        case SRHMC_BIG_EVAL_V: {
+            const int want_V = phase == SRHMC_BIG_EVAL_V;
+            const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
+            big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
+            const double* ga = (b->world > 1 && b->rank > 0) ? b->recv.as<double>() + ((size_t)(b->rank - 1) * 2 + 1) * list : nullptr;
+            const double* gb = (b->world > 1 && b->rank < b->world - 1) ? b->recv.as<double>() + ((size_t)(b->rank + 1) * 2 + 0) * list : nullptr;
+            const int total = n + 2 * std::max(1, b->cfg.max_ghosts);
+            const int sg = std::max(1, std::min((total * 32 + 255) / 256, 16 * b->sm_count));
+            big_scatter_kernel<<<sg, 256, 0, st>>>(P, b->q.as<double>(), n, ga, gb, b->L.as<double>(), b->err.as<int>());
+            big_pixel_kernel<<<pg, 256, 0, st>>>(P, b->D.as<double>(), b->L.as<double>(), want_V, b->vpart.as<double>());
+            if (want_V) big_vsum_kernel<<<1, 256, 0, st>>>(b->vpart.as<double>(), pg, b->scalars.as<double>());
+            const int gg = std::max(1, std::min((n * 32 + 255) / 256, 16 * b->sm_count));
+            big_gather_kernel<<<gg, 256, 0, st>>>(P, b->q.as<double>(), n, b->L.as<double>(), b->g.as<double>());
+            b->launches += want_V ? 5 : 4;
+            break;
+        }
+        case SRHMC_BIG_KICK1:
+            BCU(cudaMemsetAsync(cnt, 0, 8, st));
+            big_kick1_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(),
+                                                b->a1.as<double>(), b->a2.as<double>(), cnt);
+            b->launches += 1;
+            break;
+        case SRHMC_BIG_PFIX_QFIX:
+            big_pfix_qfix_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
+                                                    b->a2.as<double>(), cnt, cnt + 1);
+            b->launches += 1;
+            break;
+        case SRHMC_BIG_QFIX_KICK:
+            big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
+                                                    b->a2.as<double>(), cnt + 1);
+            b->launches += 1;
+            break;
+        case SRHMC_BIG_KICK2:
+            big_kick2_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>());
+            b->launches += 1;
+            break;
+        case SRHMC_BIG_MOMENTUM: {
+            const double* z = b->normals.ptr ? b->normals.as<double>() + (size_t)s->iteration * n * 3 : nullptr;
+            big_momentum_kernel<<<gs, tb, 0, st>>>(P, s->g_ff2, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(),
+                                                   b->q0.as<double>(), b->g0.as<double>(), b->gid.as<long long>(), s->seed,
+                                                   s->iteration, z);
+            b->launches += 1;
+            break;
+        }
+        case SRHMC_BIG_ENERGY:
+            big_energy_kernel<<<1, 512, 0, st>>>(P, s->g_ff2, s->f_pos, n, b->q.as<double>(), b->p.as<double>(),
+                                                 b->scalars.as<double>());
+            b->launches += 1;
+            break;
+        case SRHMC_BIG_RECORD_E0:
+        case SRHMC_BIG_ACCEPT: {
+            const int ph = phase == SRHMC_BIG_ACCEPT ? 1 : 0;
+            // single rank: the global sums are the local ones; otherwise the caller has all-reduced `scalars` into
+            // `global_scalars` on this stream before this phase
+            if (b->world == 1)
+                BCU(cudaMemcpyAsync(b->gscalars.ptr, b->scalars.ptr, kScalars * 8, cudaMemcpyDeviceToDevice, st));
+            big_accept_kernel<<<gs, tb, 0, st>>>(ph, b->gscalars.as<double>(), b->scalars.as<double>(), b->state.as<double>(), s->seed, s->iteration,
+                                                 b->lnu.ptr ? b->lnu.as<double>() : nullptr, n, b->q.as<double>(),
+                                                 b->g.as<double>(), b->q0.as<double>(), b->g0.as<double>(),
+                                                 b->E.ptr ? b->E.as<double>() : nullptr, b->V.ptr ? b->V.as<double>() : nullptr,
+                                                 b->T.ptr ? b->T.as<double>() : nullptr,
+                                                 b->A.ptr ? b->A.as<unsigned char>() : nullptr);
+            if (ph == 1) big_restore_v_kernel<<<1, 1, 0, st>>>(b->scalars.as<double>(), b->state.as<double>());
+            b->launches += 1 + ph;
+            break;
+        }
+        default:
+            return bfail(SRHMC_ERR_INVALID, "unknown phase %d", phase);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "phase %d launch failed: %s", phase, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -115,6 +115,10 @@ int configure(srhmc_ctx* c) {
     int threads = 256;
     if ((size_t)R * C >= 4096 || N > 256) threads = 512;
     if ((size_t)R * C <= 256 && N <= 64) threads = 128;
+    if (const char* env = std::getenv("SRHMC_FIELD_THREADS")) {  // tuning / experiments
+        const int t = std::atoi(env);
+        if (t == 128 || t == 256 || t == 512) threads = t;
+    }
     c->threads = threads;
     c->kc = pick_kernel(R, C, threads / 32);
     P.sx = ((R + 8 * c->kc.mr - 1) / (8 * c->kc.mr)) * 8 * c->kc.mr;
@@ -128,8 +132,13 @@ int configure(srhmc_ctx* c) {
         if (base + per + 64 > budget) return 0;
         return (int)std::min<size_t>((size_t)nwant, (budget - base - 64) / per);
     };
-    int kc = fit(112 * 1024, true);
+    size_t budget = 112 * 1024;
+    if (const char* env = std::getenv("SRHMC_FIELD_SMEM_KB")) budget = (size_t)std::max(16, std::atoi(env)) * 1024;
+    int kc = fit(budget, true);
     bool dsm = true;
+    if (const char* env = std::getenv("SRHMC_FIELD_D_GLOBAL")) {
+        if (env[0] == '1') { dsm = false; kc = fit(budget, false); }
+    }
     if (kc < std::min(nwant, 24)) kc = fit(kSmemMax, true);
     if (kc < std::min(nwant, 8)) {
         const int kg = fit(kSmemMax, false);

@@ -244,6 +244,89 @@ int srhmc_philox_draws_ids(srhmc_ctx* ctx, uint64_t seed, int32_t niter, int32_t
  * 2: rcp_fast(x)) so the test-suite can bound its error against libm. */
 int srhmc_test_device_math(srhmc_ctx* ctx, int32_t which, const double* x, double* y, int32_t n);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Large-field engine: one crowded field too big for a single CTA, optionally one row-strip of a field tiled over the
+ * GPUs of a node (BASELINE configs[2] scaled up, configs[4]).  Same physics as srhmc_step / srhmc_run with use_Vc = 0
+ * and a PSF truncated to (2r+1)^2 pixels; replaces the same reference methods (sampler_RHMC.py:229-566, 1009-1083).
+ *
+ * A rank owns the global rows [own_lo, own_hi) and holds data rows [row0, row0+nrows) = strip + `nrows_halo` rows on
+ * each interior side.  One leapfrog step is the phase sequence
+ *     KICK1 -> [max-reduce counters] -> PFIX_QFIX -> [max-reduce counters] -> QFIX_KICK -> PACK -> [all-gather
+ *     ghost_send into ghost_recv] -> EVAL | EVAL_V -> KICK2
+ * and one Metropolis iteration is
+ *     MOMENTUM -> ENERGY -> [sum-reduce scalars into global_scalars] -> RECORD_E0 -> nsteps x step -> ENERGY ->
+ *     [sum-reduce] -> ACCEPT.
+ * Every phase only ENQUEUES kernels on the context's stream; the bracketed collectives are issued by the caller on the
+ * same stream (torch.distributed / NCCL on tensors wrapping the buffers of srhmc_big_buffers) and are skipped for
+ * world_size = 1.  hmc_stellar_toy_model_b200/bigfield.py is the reference orchestration. */
+typedef struct srhmc_big srhmc_big;
+
+typedef struct srhmc_big_config {
+    int32_t abi_version;
+    int32_t device;
+    int32_t rows_global, cols;   /* gym.num_rows, gym.num_cols of the whole field */
+    int32_t own_lo, own_hi;      /* owned global rows */
+    int32_t row0, nrows;         /* local data rows (strip + halo) */
+    int32_t nrows_halo;          /* halo rows per interior side (>= patch_radius; the excess is the drift allowance) */
+    int32_t max_stars;           /* capacity for owned stars */
+    int32_t max_ghosts;          /* capacity of each boundary list */
+    int32_t patch_radius;        /* PSF truncation radius r (1..15); r = 12 is within 3e-13 of the full-image PSF */
+    int32_t use_prior;
+    int32_t world_size, rank;
+    double psf_fwhm_pix, B_count, f_lim, f_low, g0, g1, g2, g_xx, g_ff, alpha, V_prior_const;
+} srhmc_big_config;
+
+typedef enum srhmc_big_phase_id {
+    SRHMC_BIG_PACK = 0,       /* boundary stars -> ghost_send */
+    SRHMC_BIG_EVAL = 1,       /* model image, residual, per-star pixel gradient (a2) */
+    SRHMC_BIG_EVAL_V = 2,     /* same + pixel potential of the owned rows -> scalars[0] (a3) */
+    SRHMC_BIG_KICK1 = 3,      /* p -= h dphi/dq; p fixed point phase A -> counters[0] (a7 steps 1-2) */
+    SRHMC_BIG_PFIX_QFIX = 4,  /* p fixed point phase B; q fixed point phase A -> counters[1] (a7 steps 2-3) */
+    SRHMC_BIG_QFIX_KICK = 5,  /* q fixed point phase B; p -= h dtau/dq (a7 steps 3-4) */
+    SRHMC_BIG_KICK2 = 6,      /* p -= h dphi/dq at the new q; reflections (a7 steps 5-6) */
+    SRHMC_BIG_MOMENTUM = 7,   /* p = z sqrt(H); remember the iteration's start state (a8) */
+    SRHMC_BIG_ENERGY = 8,     /* scalars[1..3] = T, #stars outside the support, prior potential (a3, a5) */
+    SRHMC_BIG_RECORD_E0 = 9,  /* E0 from global_scalars; chain row */
+    SRHMC_BIG_ACCEPT = 10     /* Metropolis test on global_scalars; restore on rejection; chain row (a8) */
+} srhmc_big_phase_id;
+
+typedef struct srhmc_big_step {
+    double dt, delta, g_ff2;
+    int32_t counter_max, f_pos;
+    int32_t iteration;       /* Metropolis iteration index (RNG counter, chain row) */
+    int32_t reserved;
+    uint64_t seed;
+} srhmc_big_step;
+
+/* Device pointers of the buffers the caller's collectives operate on (sizes in elements). */
+typedef struct srhmc_big_buffers_t {
+    void* ghost_send;  int64_t ghost_send_doubles;   /* [2][1 + 3*max_ghosts]: count, then f,x,y triples */
+    void* ghost_recv;  int64_t ghost_recv_doubles;   /* [world][2][1 + 3*max_ghosts] (all-gather of ghost_send) */
+    void* scalars;                                   /* double[n_scalars]: this rank's partial sums */
+    void* global_scalars;                            /* double[n_scalars]: the all-reduced sums */
+    int64_t n_scalars;
+    void* counters;    int64_t n_counters;           /* int32[n_counters]: fixed-point iteration counts (max-reduce) */
+} srhmc_big_buffers_t;
+
+const char* srhmc_big_last_error(void);
+int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out);
+int srhmc_big_destroy(srhmc_big* b);
+int srhmc_big_set_stream(srhmc_big* b, void* cuda_stream);
+int srhmc_big_synchronize(srhmc_big* b);
+int64_t srhmc_big_launch_count(srhmc_big* b);
+int srhmc_big_set_data(srhmc_big* b, const double* D_local /* [nrows, cols] */);
+int srhmc_big_set_stars(srhmc_big* b, const double* q /* [n,3] */, const int64_t* global_ids /* [n] */, int32_t n);
+int srhmc_big_get_stars(srhmc_big* b, double* q, double* p, double* grad /* each [n,3], may be NULL */);
+int srhmc_big_set_momenta(srhmc_big* b, const double* p /* [n,3] */);
+int srhmc_big_buffers(srhmc_big* b, srhmc_big_buffers_t* out);
+/* Parity mode: normals [n_iters, n, 3] for the owned stars and/or lnu [n_iters]; NULL -> device Philox (seed). */
+int srhmc_big_set_draws(srhmc_big* b, const double* normals, const double* lnu, int32_t n_iters);
+int srhmc_big_alloc_chains(srhmc_big* b, int32_t n_iters);
+int srhmc_big_read_chains(srhmc_big* b, int32_t n_iters, double* E, double* V, double* T, uint8_t* A, double* n_accepted,
+                          int32_t* error_flag /* 1: an owned star left the local data window; 2: ghost list overflow */);
+int srhmc_big_read_scalars(srhmc_big* b, double* scalars);
+int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* step);
+
 /* Roofline denominator measured on the device itself: a register-resident FMA chain (8 independent chains per
  * thread, all SMs filled) in the given precision (64 or 32).  Returns TFLOP/s (2 flop per FMA) and the launch time. */
 int srhmc_measure_fma_peak(int32_t device, int32_t precision, double* tflops, float* ms);
