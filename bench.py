@@ -115,6 +115,44 @@ def workload_c4(n_fields, seed, nstars=204, size=64):
                 flops_per_unit=flops_per_unit, flops_executed_per_unit=flops_per_unit, desc="%d crowded %dx%d fields x %d stars" % (n_fields, size, size, nstars))
 
 
+def workload_c5(rows, cols, nstars, seed, row0, nrows, rad=12):
+    """One large crowded field (BASELINE configs[4] shape: 1.49e-3 stars/px, flux power law alpha=2 in mag [15,20],
+    prior on, repulsion off).  Every rank calls this with the same seed and gets the same star list; only the rows
+    [row0, row0+nrows) of the data image are rendered (patch-limited) and Poisson-sampled with a per-row stream, so
+    overlapping halo rows agree between ranks."""
+    k = exp_constants()
+    rng = np.random.RandomState(seed)
+    alpha = 2.0
+    fmin = 10 ** (0.4 * (22.5 - 20)) * k["flux_to_count"]
+    fmax = 10 ** (0.4 * (22.5 - 15)) * k["flux_to_count"]
+    u = rng.random_sample(nstars)
+    fl = np.exp(np.log(fmin ** (1 - alpha) + u * (fmax ** (1 - alpha) - fmin ** (1 - alpha))) / (1 - alpha))
+    x = rng.random_sample(nstars) * (rows - 2.0) + 1.0
+    y = rng.random_sample(nstars) * (cols - 2.0) + 1.0
+    q0 = np.stack([fl * 1.05, x + 0.1 * rng.randn(nstars), y + 0.1 * rng.randn(nstars)], axis=1)
+    sigma = k["psf_fwhm_pix"] / 2.354
+    lam = np.full((nrows, cols), k["B_count"])
+    near = np.nonzero((x > row0 - rad - 1) & (x < row0 + nrows + rad + 1))[0]
+    for s in near:
+        i0, i1 = max(row0, int(x[s]) - rad), min(row0 + nrows - 1, int(x[s]) + rad)
+        j0, j1 = max(0, int(y[s]) - rad), min(cols - 1, int(y[s]) + rad)
+        if i0 > i1:
+            continue
+        ex = np.exp(-((np.arange(i0, i1 + 1) + 0.5 - x[s]) ** 2) / (2 * sigma**2))
+        ey = np.exp(-((np.arange(j0, j1 + 1) + 0.5 - y[s]) ** 2) / (2 * sigma**2)) / (2 * np.pi * sigma**2)
+        lam[i0 - row0:i1 - row0 + 1, j0:j1 + 1] += fl[s] * ex[:, None] * ey[None, :]
+    D = np.empty_like(lam)
+    for i in range(nrows):
+        D[i] = np.random.RandomState((seed * 1000003 + row0 + i) % (2**32)).poisson(lam[i])
+    vpc = np.log(float(rows) * cols) - np.log((1 - alpha) / (fmax ** (1 - alpha) - fmin ** (1 - alpha)))
+    consts = dict(g_xx=0.05, g_ff=4.0, use_prior=True, alpha=alpha, V_prior_const=float(vpc),
+                  **{n: k[n] for n in ("psf_fwhm_pix", "B_count", "f_lim", "f_low", "g0", "g1", "g2")})
+    run = dict(nsteps=10, dt=5e-2, g_ff2=4.0, delta=1e-6, counter_max=1000, f_pos=True)
+    A = rows * cols / float(nstars)
+    return dict(D=D, q0=q0, consts=consts, run=run, flops_per_unit=9 * (2 * rad + 1) ** 2 + 2 * A,
+                bytes_per_unit=8.0 * A + 96.0)
+
+
 # ----------------------------------------------------------------------------------------------- CPU arm (oracle port)
 def _cpu_worker(task):
     """One oracle chain on one host core.  Returns (units, seconds)."""
@@ -384,6 +422,114 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_big(args):
+    """BASELINE configs[4]-shaped workload: ONE large field, row strips over the ranks, ghost-star all-gather and the
+    energy / fixed-point all-reduces through NCCL on the compute stream."""
+    import torch
+    import torch.distributed as dist
+
+    from hmc_stellar_toy_model_b200 import bigfield as bf
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the RHMC path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rows, cols = args.rows * (world if args.weak else 1), args.cols
+    nstars = int(args.stars * (world if args.weak else 1))
+    rad, halo = 12, 24
+    lo, hi = bf.strip_bounds(rows, world)[rank]
+    row0, nrows = bf.data_window(rows, lo, hi, halo)
+    wl = workload_c5(rows, cols, nstars, 77, row0, nrows, rad)
+    strip = bf.BigFieldStrip(rows=rows, cols=cols, rank=rank, world=world, device=local, max_stars=nstars,
+                             max_ghosts=max(1024, int(4 * nstars * (halo + rad + 1) / max(1, hi - lo))), patch_radius=rad,
+                             halo=halo, **wl["consts"])
+    stream = torch.cuda.Stream()   # kernels, NCCL collectives and the timing events all ride on this stream
+    torch.cuda.set_stream(stream)
+    strip.set_stream(stream.cuda_stream)
+    eng = bf.BigFieldRHMC([strip], bf.TorchDistComm(dist) if world > 1 else bf.NoComm())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    niter = args.niter
+    units = nstars * (niter + 1) * wl["run"]["nsteps"]
+    strip.set_data_window(wl["D"])
+    launches0 = None
+    for w in range(args.warmup):
+        strip.set_stars(wl["q0"])
+        eng.run(niter, seed=100 + w, **wl["run"])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    acc = 0.0
+    launches0 = strip.launch_count
+    t_e2e = 0.0
+    for s in range(args.steps):
+        strip.set_stars(wl["q0"])
+        barrier()
+        ev0.record(stream)
+        out = eng.run(niter, seed=1000 + s, **wl["run"])  # read_chains synchronises
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        times.append(ev0.elapsed_time(ev1))
+        acc = out["accept_rate"]
+    launches = strip.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: host buffers in, final stars out
+    for s in range(max(1, min(args.steps, args.e2e_steps))):
+        barrier()
+        t0 = time.perf_counter()
+        strip.set_data_window(wl["D"])
+        strip.set_stars(wl["q0"])
+        eng.run(niter, seed=2000 + s, **wl["run"])
+        strip.get_stars()
+        barrier()
+        t_e2e += time.perf_counter() - t0
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t = torch.tensor([sum(times), t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, t_e2e = [float(v) for v in t.tolist()]
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        ms_per_step = total_ms / args.steps
+        value = units * args.steps / (total_ms * 1e-3)
+        gbs = wl["bytes_per_unit"] * units / world / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c5_tiled_field_%dx%d_%dstars" % (rows, cols, nstars), "rows": rows, "cols": cols,
+                       "stars": nstars, "niter": niter, "nsteps": wl["run"]["nsteps"], "dt": wl["run"]["dt"],
+                       "patch_radius": rad, "halo_rows": halo, "rng": "device Philox4x32-10",
+                       "l2": "data window of %.0f MB per rank exceeds nothing smaller than L2 only when > 126 MB; "
+                             "no flush between launches" % (wl["D"].nbytes / 1e6),
+                       "parallelism": "row strips over %d GPU(s); per step: 1 all-gather of boundary stars, 2 max "
+                                      "all-reduces; per iteration: 2 sum all-reduces of 8 doubles (NCCL)" % world},
+            "clocks": clocks,
+            "e2e": {"value": units * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(wl["D"].nbytes + wl["q0"].nbytes),
+                    "d2h_bytes_per_step": int(3 * wl["q0"].nbytes // max(1, world)), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "peak_source": peak_src, "bytes_per_unit": wl["bytes_per_unit"], "traffic": None,
+                         "note": "per GPU; algorithmic bytes = the data strip read once per gradient + star state"},
+            "cpu_baseline": None, "accept_rate": acc,
+        }
+        print(json.dumps(out))
+    strip.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path (NumPy oracle port; the Python-2 reference itself cannot
     travel to the GPU box) on all host cores, same config/metric.  Rank 0 only."""
@@ -417,7 +563,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--rows", type=int, default=2048, help="c5: image rows (per GPU with --weak)")
+    ap.add_argument("--cols", type=int, default=2048)
+    ap.add_argument("--stars", type=float, default=6250, help="c5: stars (per GPU with --weak); 1.49e-3 per pixel")
+    ap.add_argument("--weak", action="store_true", help="c5: grow the field with the GPU count")
     ap.add_argument("--chains-per-mag", type=int, default=1000)
     ap.add_argument("--fields", type=int, default=592)
     ap.add_argument("--niter", type=int, default=1000)
@@ -429,6 +579,10 @@ def main():
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        if args.niter == 1000:
+            args.niter = 4
+        run_big(args)
     else:
         run_ours(args)
 

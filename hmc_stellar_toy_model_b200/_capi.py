@@ -189,6 +189,7 @@ SIGNATURES = {
     "srhmc_big_create": (C.c_int, [C.POINTER(BigConfig), C.POINTER(C.c_void_p)]),
     "srhmc_big_destroy": (C.c_int, [C.c_void_p]),
     "srhmc_big_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srhmc_big_adopt_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "srhmc_big_synchronize": (C.c_int, [C.c_void_p]),
     "srhmc_big_launch_count": (C.c_int64, [C.c_void_p]),
     "srhmc_big_set_data": (C.c_int, [C.c_void_p, c_double_p]),

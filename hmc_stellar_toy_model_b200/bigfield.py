@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import check_big as check
 
 PHASE = dict(PACK=0, EVAL=1, EVAL_V=2, KICK1=3, PFIX_QFIX=4, QFIX_KICK=5, KICK2=6, MOMENTUM=7, ENERGY=8, RECORD_E0=9,
-             ACCEPT=10)
+             ACCEPT=10, RESET_ITER=11)
 
 
 # ----------------------------------------------------------------------------------------------- host-side geometry
@@ -113,6 +113,9 @@ class BigFieldStrip:
 
     def set_stream(self, ptr):
         check(self._lib.srhmc_big_set_stream(self._h, C.c_void_p(ptr)))
+
+    def adopt_stream(self, ptr):
+        check(self._lib.srhmc_big_adopt_stream(self._h, C.c_void_p(ptr)))
 
     def synchronize(self):
         check(self._lib.srhmc_big_synchronize(self._h))
@@ -308,11 +311,28 @@ class BigFieldRHMC:
         for _ in range(nsteps):
             self.leapfrog(st, False)
 
+    def _iteration(self, st, nsteps):
+        self._all("MOMENTUM", st)
+        self._all("ENERGY", st)
+        if self.multi:
+            self.comm.sum_scalars(self.strips)
+        self._all("RECORD_E0", st)
+        for t in range(nsteps):
+            self.leapfrog(st, t == nsteps - 1)
+        self._all("ENERGY", st)
+        if self.multi:
+            self.comm.sum_scalars(self.strips)
+        self._all("ACCEPT", st)
+
     def run(self, niter, nsteps, dt, delta=1e-6, counter_max=1000, f_pos=True, g_ff2=1.0, seed=0, normals=None, lnu=None,
-            schedule_g_ff2=None):
+            schedule_g_ff2=None, use_graph=None):
         """Move-0 leg of multi_gym.run_RHMC (sampler_RHMC.py:1009-1083) for iterations 0..niter, all enqueued on
         the stream; `normals` [niter+1, N_global, 3] / `lnu` [niter+1] inject the reference's draws (parity mode),
-        otherwise device Philox keyed by global star id."""
+        otherwise device Philox keyed by global star id.
+
+        use_graph: capture ONE Metropolis iteration (all its phases and, when tiled, its NCCL collectives) into a CUDA
+        graph and replay it niter+1 times -- the chain row and RNG counter then come from a device-side iteration
+        counter.  Default: on for an untiled field without a g_ff2 schedule."""
         L = niter + 1
         for s in self.strips:
             s.set_draws(None if normals is None else np.asarray(normals)[:, s.ids, :], lnu, L)
@@ -322,22 +342,39 @@ class BigFieldRHMC:
             self._all("PACK", st0)
             self.comm.gather_ghosts(self.strips)
         self._all("EVAL_V", st0)
-        for l in range(L):
-            g = g_ff2
-            if schedule_g_ff2 is not None and len(schedule_g_ff2):
-                g = float(schedule_g_ff2[min(l, len(schedule_g_ff2) - 1)])
-            st = self._step_struct(dt, delta, g, counter_max, f_pos, l, seed)
-            self._all("MOMENTUM", st)
-            self._all("ENERGY", st)
-            if self.multi:
-                self.comm.sum_scalars(self.strips)
-            self._all("RECORD_E0", st)
-            for t in range(nsteps):
-                self.leapfrog(st, t == nsteps - 1)
-            self._all("ENERGY", st)
-            if self.multi:
-                self.comm.sum_scalars(self.strips)
-            self._all("ACCEPT", st)
+        has_sched = schedule_g_ff2 is not None and len(schedule_g_ff2) > 0
+        dist_comm = isinstance(self.comm, TorchDistComm)
+        if use_graph is None:
+            use_graph = not has_sched and L >= 3 and not dist_comm
+        if use_graph and dist_comm:
+            # measured on 2 x B200 (torch 2.11, NCCL 2.28.9): replaying a graph that contains the captured
+            # collectives dead-locked; the tiled path therefore enqueues its phases eagerly
+            raise ValueError("CUDA-graph replay is not available with torch.distributed collectives")
+        if use_graph and has_sched:
+            raise ValueError("a g_ff2 schedule changes a launch parameter every iteration: run with use_graph=False")
+        if use_graph:
+            import torch
+
+            self._all("RESET_ITER", st0)
+            stg = self._step_struct(dt, delta, g_ff2, counter_max, f_pos, -1, seed)
+            run_stream = torch.cuda.current_stream()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                cap = torch.cuda.current_stream().cuda_stream
+                for s in self.strips:
+                    s.adopt_stream(cap)
+                self._iteration(stg, nsteps)
+            for s in self.strips:
+                s.adopt_stream(run_stream.cuda_stream)
+            for _ in range(L):
+                graph.replay()
+            self._graph = graph  # keep alive until the results are read
+        else:
+            for l in range(L):
+                g = g_ff2
+                if has_sched:
+                    g = float(schedule_g_ff2[min(l, len(schedule_g_ff2) - 1)])
+                self._iteration(self._step_struct(dt, delta, g, counter_max, f_pos, l, seed), nsteps)
         out = self.strips[0].read_chains(L)
         for s in self.strips[1:]:
             s.read_chains(L)  # synchronises and surfaces per-strip errors

@@ -308,8 +308,10 @@ __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, cons
 // momentum refresh p = z sqrt(H) (sampler_RHMC.py:1021-1022) with device Philox keyed by the GLOBAL star id, or
 // injected normals; saves the iteration's start state
 __global__ void big_momentum_kernel(const BigParams P, double g_ff2, int n, const double* q, double* p, const double* g,
-                                    double* q0, double* g0, const long long* gid, unsigned long long seed, int iter,
-                                    const double* normals /* [n,3] for this iteration, or nullptr */) {
+                                    double* q0, double* g0, const long long* gid, unsigned long long seed, int iter_host,
+                                    const int* iter_dev, const double* normals_all /* [iters,n,3] or nullptr */) {
+    const int iter = iter_dev ? *iter_dev : iter_host;
+    const double* normals = normals_all ? normals_all + (size_t)iter * n * 3 : nullptr;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const Metric m = metric_of(P.F, q[3 * k], g_ff2);
         double z[3];
@@ -355,10 +357,12 @@ __global__ void big_energy_kernel(const BigParams P, double g_ff2, int f_pos, in
 // E = V + T from the (all-reduced) scalars: slot 4 <- E (kept as E0 when `first`), accept test otherwise
 __global__ void big_accept_kernel(int phase /*0: record E0, 1: accept*/, const double* scalars /* global sums */,
                                   const double* local_scalars, double* state,
-                                  unsigned long long seed, int iter, const double* lnu_in, int n, double* q, double* g,
+                                  unsigned long long seed, int iter_host, const int* iter_dev, const double* lnu_in, int n,
+                                  double* q, double* g,
                                   const double* q0, const double* g0, double* E_chain, double* V_chain, double* T_chain,
                                   unsigned char* A_chain) {
     // every thread evaluates the same scalars; thread 0 of block 0 writes the records
+    const int iter = iter_dev ? *iter_dev : iter_host;
     const double V = (scalars[2] > 0.0) ? CUDART_INF : scalars[0] + scalars[3];
     const double T = scalars[1];
     const double E = V + T;
@@ -389,8 +393,9 @@ __global__ void big_accept_kernel(int phase /*0: record E0, 1: accept*/, const d
 }
 // the pixel potential must follow the state on rejection: separate tiny kernel so that it runs after every block of
 // big_accept_kernel has read scalars[0]
-__global__ void big_restore_v_kernel(double* local_scalars, const double* state) {
+__global__ void big_restore_v_kernel(double* local_scalars, const double* state, int* iter_dev) {
     if (state[2] == 0.0) local_scalars[0] = state[1];
+    if (iter_dev) *iter_dev += 1;  // the next replay of a captured iteration works on the next chain row
 }
 
 // boundary stars for the neighbours: list 0 = stars with x < lo_edge (for the rank below), list 1 = x >= hi_edge.
@@ -554,7 +559,14 @@ int srhmc_big_set_stream(srhmc_big* b, void* s) {
     if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
     BCU(cudaSetDevice(b->cfg.device));
     BCU(cudaStreamSynchronize(b->stream));
-    b->stream = s ? reinterpret_cast<cudaStream_t>(s) : b->own_stream;
+    b->stream = reinterpret_cast<cudaStream_t>(s);  // NULL is the CUDA default stream (torch's default stream)
+    return 0;
+}
+
+int srhmc_big_adopt_stream(srhmc_big* b, void* s) {
+    // like srhmc_big_set_stream but without synchronising the previous stream (legal during CUDA-graph capture)
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    b->stream = reinterpret_cast<cudaStream_t>(s);
     return 0;
 }
 
@@ -726,6 +738,9 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += want_V ? 5 : 4;
             break;
         }
+        case SRHMC_BIG_RESET_ITER:
+            BCU(cudaMemsetAsync(cnt + 2, 0, 4, st));
+            break;
         case SRHMC_BIG_KICK1:
             BCU(cudaMemsetAsync(cnt, 0, 8, st));
             big_kick1_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(),
@@ -747,10 +762,10 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_MOMENTUM: {
-            const double* z = b->normals.ptr ? b->normals.as<double>() + (size_t)s->iteration * n * 3 : nullptr;
+            const double* z = b->normals.ptr ? b->normals.as<double>() : nullptr;
             big_momentum_kernel<<<gs, tb, 0, st>>>(P, s->g_ff2, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(),
                                                    b->q0.as<double>(), b->g0.as<double>(), b->gid.as<long long>(), s->seed,
-                                                   s->iteration, z);
+                                                   s->iteration, s->iteration < 0 ? cnt + 2 : nullptr, z);
             b->launches += 1;
             break;
         }
@@ -767,12 +782,15 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             if (b->world == 1)
                 BCU(cudaMemcpyAsync(b->gscalars.ptr, b->scalars.ptr, kScalars * 8, cudaMemcpyDeviceToDevice, st));
             big_accept_kernel<<<gs, tb, 0, st>>>(ph, b->gscalars.as<double>(), b->scalars.as<double>(), b->state.as<double>(), s->seed, s->iteration,
+                                                 s->iteration < 0 ? cnt + 2 : nullptr,
                                                  b->lnu.ptr ? b->lnu.as<double>() : nullptr, n, b->q.as<double>(),
                                                  b->g.as<double>(), b->q0.as<double>(), b->g0.as<double>(),
                                                  b->E.ptr ? b->E.as<double>() : nullptr, b->V.ptr ? b->V.as<double>() : nullptr,
                                                  b->T.ptr ? b->T.as<double>() : nullptr,
                                                  b->A.ptr ? b->A.as<unsigned char>() : nullptr);
-            if (ph == 1) big_restore_v_kernel<<<1, 1, 0, st>>>(b->scalars.as<double>(), b->state.as<double>());
+            if (ph == 1)
+                big_restore_v_kernel<<<1, 1, 0, st>>>(b->scalars.as<double>(), b->state.as<double>(),
+                                                      s->iteration < 0 ? cnt + 2 : nullptr);
             b->launches += 1 + ph;
             break;
         }

@@ -287,13 +287,15 @@ typedef enum srhmc_big_phase_id {
     SRHMC_BIG_MOMENTUM = 7,   /* p = z sqrt(H); remember the iteration's start state (a8) */
     SRHMC_BIG_ENERGY = 8,     /* scalars[1..3] = T, #stars outside the support, prior potential (a3, a5) */
     SRHMC_BIG_RECORD_E0 = 9,  /* E0 from global_scalars; chain row */
-    SRHMC_BIG_ACCEPT = 10     /* Metropolis test on global_scalars; restore on rejection; chain row (a8) */
+    SRHMC_BIG_ACCEPT = 10,    /* Metropolis test on global_scalars; restore on rejection; chain row (a8) */
+    SRHMC_BIG_RESET_ITER = 11 /* zero the device-side iteration counter used when step.iteration < 0 */
 } srhmc_big_phase_id;
 
 typedef struct srhmc_big_step {
     double dt, delta, g_ff2;
     int32_t counter_max, f_pos;
-    int32_t iteration;       /* Metropolis iteration index (RNG counter, chain row) */
+    int32_t iteration;       /* Metropolis iteration index (RNG counter, chain row); < 0: use the device-side counter,
+                                which ACCEPT advances -- lets one captured CUDA graph of an iteration be replayed */
     int32_t reserved;
     uint64_t seed;
 } srhmc_big_step;
@@ -311,7 +313,9 @@ typedef struct srhmc_big_buffers_t {
 const char* srhmc_big_last_error(void);
 int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out);
 int srhmc_big_destroy(srhmc_big* b);
-int srhmc_big_set_stream(srhmc_big* b, void* cuda_stream);
+int srhmc_big_set_stream(srhmc_big* b, void* cuda_stream);    /* NULL = the CUDA default stream; a new context runs on
+                                                                  its own non-blocking stream until this is called */
+int srhmc_big_adopt_stream(srhmc_big* b, void* cuda_stream);  /* no synchronisation: usable during graph capture */
 int srhmc_big_synchronize(srhmc_big* b);
 int64_t srhmc_big_launch_count(srhmc_big* b);
 int srhmc_big_set_data(srhmc_big* b, const double* D_local /* [nrows, cols] */);

@@ -132,7 +132,12 @@ def _consts(S):
 def _engine(S, q, world=1, rad=12, halo=20, D=None):
     import torch
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit side stream for the engine AND the LocalComm tensor ops (CUDA-graph capture needs a non-default one)
+    global _STREAM
+    if _STREAM is None:
+        _STREAM = torch.cuda.Stream()
+    torch.cuda.set_stream(_STREAM)
+    stream = _STREAM.cuda_stream
     strips = []
     for r in range(world):
         s = bf.BigFieldStrip(rows=S.num_rows, cols=S.num_cols, rank=r, world=world, device=0, max_stars=q.size // 3,
@@ -142,6 +147,9 @@ def _engine(S, q, world=1, rad=12, halo=20, D=None):
         s.set_stars(q.reshape(-1, 3))
         strips.append(s)
     return bf.BigFieldRHMC(strips, bf.LocalComm() if world > 1 else bf.NoComm())
+
+
+_STREAM = None
 
 
 def _grad_close(a, b, tol):
