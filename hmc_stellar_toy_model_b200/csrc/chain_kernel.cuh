@@ -427,15 +427,16 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
     // Work items are (group of GPW chains, chunk of Metropolis iterations); chunk c of a group may run on a different
     // warp than chunk c-1 (the chain state travels through global memory, ordered by a per-group counter), which
     // lets a batch that is not a multiple of the resident warp count finish without a long under-filled tail.
-    const int G = (A.n_fields + GPW - 1) / GPW;
+    const int fb = A.field_begin, fe = A.field_end > 0 ? A.field_end : A.n_fields;
+    const int G = (fe - fb + GPW - 1) / GPW;
     const int n_chunks = (MODE == MODE_RUN && A.n_chunks > 1) ? A.n_chunks : 1;
     const long long n_tasks = (long long)G * n_chunks;
     const long long gw = (long long)blockIdx.x * nw + warp, W = (long long)gridDim.x * nw;
     for (long long task = gw; task < n_tasks; task += W) {
         const int chunk = (int)(task / G);
-        const int base = (int)(task % G) * GPW;
-        const bool live = base + grp < A.n_fields;
-        const int field = live ? base + grp : A.n_fields - 1;  // idle group shadows a valid chain, writes nothing
+        const int base = fb + (int)(task % G) * GPW;
+        const bool live = base + grp < fe;
+        const int field = live ? base + grp : fe - 1;  // idle group shadows a valid chain, writes nothing
         constexpr int n = 1;  // the host routes only exactly-one-star batches to this kernel
         const DT* gD = reinterpret_cast<const DT*>(sizeof(DT) == 8 ? A.D : A.D_int) + (size_t)field * R * C;
         __syncwarp();

@@ -162,7 +162,8 @@ int pick_chunks(long long groups, long long warps, int L) {
 int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const ChainLaunchPlan& plan, int sms, cudaStream_t stream) {
     LaunchArgs A = A_in;
     const int chains_per_block = plan.nw * (32 / plan.lpc);
-    const long long blocks = ((long long)A.n_fields + chains_per_block - 1) / chains_per_block;
+    const int n_range = (A.field_end > 0 ? A.field_end : A.n_fields) - A.field_begin;
+    const long long blocks = ((long long)n_range + chains_per_block - 1) / chains_per_block;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
     const bool minb = u16 && A.mode == MODE_RUN && g_minb > 0;
     const int max_k = minb ? g_minb_blocks

@@ -66,6 +66,8 @@ struct LsArgs {
 struct LaunchArgs {
     int mode;
     int n_fields;
+    int field_begin, field_end;  // chain kernel: this launch covers fields [field_begin, field_end) (0, 0 = all);
+                                 // field_begin is a multiple of the warp group size
     const void* D;          // [n_images, R*C] in the pixel type
     const void* D_int;      // same images as exact unsigned integer counts, or nullptr (chain kernel, lossless)
     int D_int_bytes;        // 4: uint32, 2: uint16 (every count < 65536)
