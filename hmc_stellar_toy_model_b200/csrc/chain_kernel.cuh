@@ -261,7 +261,11 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
     if (!WANT_V) {
-#pragma unroll 4
+#ifndef SRHMC_MAIN_UNROLL
+#define SRHMC_MAIN_UNROLL 2
+#endif
+        constexpr int kMainUnroll = SRHMC_MAIN_UNROLL;
+#pragma unroll kMainUnroll
         for (int i = i_lo; i < i_hi; ++i) {
             const double2 re = rt[i];
 #pragma unroll
