@@ -119,8 +119,7 @@ __device__ __forceinline__ double log1p_small(double t) {
 }
 
 // Image rows [r0, r1), all column slots of the lane (columns sub + LPC c): gradient column sums and, per TIER, the
-// D * log1p(t) part of the potential.  TIER 0: table logarithm; 1: 7-term series (|t| < 2^-7); 2: t - t^2/2
-// (|t| < 2^-18, truncation < 2^-55).
+// D * log1p(t) part of the potential.  TIER 0: table logarithm; 1: 7-term series (|t| < 2^-7).
 template <int TIER, int LPC, typename DT>
 __device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restrict__ sDl, const double2* __restrict__ rt,
                                                const double2* __restrict__ ltab, double B, const double (&fey)[32 / LPC],
@@ -140,11 +139,8 @@ __device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restr
                 const double w = fma(re.x, tb[c], 1.0);
                 bad |= (__double2hiint(w) < 0x00100000);  // Lambda <= 0: ln undefined -> NaN
                 vlog = fma(d, log_pos(w, ltab), vlog);
-            } else if (TIER == 1) {
-                vlog = fma(d, log1p_small(re.x * tb[c]), vlog);
             } else {
-                const double t = re.x * tb[c];
-                vlog = fma(d, fma(-0.5 * t, t, t), vlog);
+                vlog = fma(d, log1p_small(re.x * tb[c]), vlog);
             }
         }
     }
@@ -173,7 +169,7 @@ __device__ __forceinline__ void row_window(float xc, float peak, float thresh, f
 //
 // V is evaluated in the separable form (Lambda_ij = B + a_i b_j with a_i = ex_i, b_j = f ey_j):
 //   sum(Lambda - D ln Lambda) = [R C B - ln B sum(D)] + (sum_i a_i)(sum_j b_j) - sum_ij D_ij log1p(a_i b_j / B)
-// so only the last sum needs per-pixel work; log1p is tiered per row range by the largest |t| = |a_i b_j / B| the
+// so only the last sum needs per-pixel work; log1p is tiered (two tiers) per row range by the largest |t| = |a_i b_j / B| the
 // warp sees there (see rows_all_slots).  Code size matters here: a build that unrolled per-slot tier loops grew the
 // kernel to 30k instructions and spent 31% of its issue slots waiting for instruction fetch, so the kernel is
 // specialised per mode (template MODE) and the tier loops are kept compact.  `vconst` is the bracketed constant of this chain's image.
@@ -278,28 +274,23 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             }
         }
     } else {
-        // row tiers from the largest |t| any lane of the warp can see in a row: [n0, n1) table log, [m0, m1) series
+        // rows [n0, n1) where some lane of the warp can see |t| >= 2^-7 take the table logarithm, the others the
+        // 7-term series.  (A third tier, t - t^2/2 for |t| < 2^-18, was measured SLOWER: its extra loop bodies cost
+        // more in instruction fetch than the shorter series saved.)
         float peak = 0.0f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) peak = fmaxf(peak, fabsf((float)tb[c]));
         peak *= 1.0001f;
         const float xc = (float)(x - 0.5), two_s2 = (float)(1.0 / P.inv2s2);
-        int n0, n1, m0, m1;
-        row_window(xc, peak, 0.0078125f, two_s2, R, n0, n1);          // |t| >= 2^-7
-        row_window(xc, peak, 3.814697265625e-06f, two_s2, R, m0, m1);  // |t| >= 2^-18
+        int n0, n1;
+        row_window(xc, peak, 0.0078125f, two_s2, R, n0, n1);  // |t| >= 2^-7
         n0 = __reduce_min_sync(FULL, n0);
         n1 = __reduce_max_sync(FULL, n1);
-        m0 = __reduce_min_sync(FULL, m0);
-        m1 = __reduce_max_sync(FULL, m1);
-        m0 = min(max(m0, i_lo), i_hi);
-        m1 = min(max(m1, m0), i_hi);
-        n0 = min(max(n0, m0), m1);
-        n1 = min(max(n1, n0), m1);
-        rows_all_slots<2, LPC>(i_lo, m0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
-        rows_all_slots<1, LPC>(m0, n0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        n0 = min(max(n0, i_lo), i_hi);
+        n1 = min(max(n1, n0), i_hi);
+        rows_all_slots<1, LPC>(i_lo, n0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
         rows_all_slots<0, LPC>(n0, n1, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
-        rows_all_slots<1, LPC>(n1, m1, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
-        rows_all_slots<2, LPC>(m1, i_hi, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<1, LPC>(n1, i_hi, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
     }
     __syncwarp();  // row table is rewritten by the next evaluation
     double sf = 0.0, sx = 0.0, sy = 0.0;
@@ -326,6 +317,8 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 
 // V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential and metric
 // (sampler_RHMC.py:294-363).
+// (Making this and the Philox helpers __noinline__ to shrink the kernel was measured slower: the chain state then
+// travels through local memory around every call.)
 __device__ __forceinline__ void chain_energies(const FieldParams& P, const ChainConst& K, const ChainState& s, int f_pos,
                                                double& V, double& T) {
     const double v0 = (s.pf * s.pf) * s.u + (s.px * s.px + s.py * s.py) * s.ihxx;
