@@ -320,9 +320,10 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 // (Making this and the Philox helpers __noinline__ to shrink the kernel was measured slower: the chain state then
 // travels through local memory around every call.)
 __device__ __forceinline__ void chain_energies(const FieldParams& P, const ChainConst& K, const ChainState& s, int f_pos,
-                                               double& V, double& T) {
+                                               const double2* __restrict__ ltab, double& V, double& T) {
     const double v0 = (s.pf * s.pf) * s.u + (s.px * s.px + s.py * s.py) * s.ihxx;
-    const double v1 = -(log(fabs(s.u)) + 2.0 * log(fabs(s.ihxx)));   // ln|H_ff| + 2 ln|H_xx|
+    // ln|H_ff| + 2 ln|H_xx| through the kernel's own table logarithm (half the code of two libm calls)
+    const double v1 = -(log_pos(fabs(s.u), ltab) + 2.0 * log_pos(fabs(s.ihxx), ltab));
     T = (v0 + v1) / 2.0;
     double v = s.Vpix;
     if (P.use_prior) v += P.alpha * log(s.f) + P.Vpc;
@@ -467,7 +468,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V, T;
-            chain_energies(P, K, s, A.f_pos, V, T);
+            chain_energies(P, K, s, A.f_pos, ltab, V, T);
             const Metric m = metric_of(P, s.f, g_ff2);  // reference-order formulas for the reported H, H'
             if (writer) {
                 const size_t o = (size_t)field * 3;
@@ -495,7 +496,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V0, T0;
-            chain_energies(P, K, s, A.f_pos, V0, T0);
+            chain_energies(P, K, s, A.f_pos, ltab, V0, T0);
             if (writer) {
                 const size_t o = (size_t)field * rows * 3;
                 A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
@@ -505,7 +506,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             for (int t = 1; t <= A.nsteps; ++t) {
                 chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
                 double V, T;
-                chain_energies(P, K, s, A.f_pos, V, T);
+                chain_energies(P, K, s, A.f_pos, ltab, V, T);
                 if (writer) {
                     const size_t o = ((size_t)field * rows + t) * 3;
                     A.q_chain[o] = s.f; A.q_chain[o + 1] = s.x; A.q_chain[o + 2] = s.y;
@@ -567,7 +568,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 }
                 const ChainState s0 = s;
                 double V0, T0;
-                chain_energies(P, K, s, A.f_pos, V0, T0);
+                chain_energies(P, K, s, A.f_pos, ltab, V0, T0);
                 const double E0 = V0 + T0;
                 const bool keep = (l % A.chain_stride) == 0;
                 const size_t row = (size_t)field * rows + (size_t)(l / A.chain_stride);
@@ -581,7 +582,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 for (int t = 0; t < A.nsteps; ++t)
                     chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
-                chain_energies(P, K, s, A.f_pos, V1, T1);
+                chain_energies(P, K, s, A.f_pos, ltab, V1, T1);
                 const double dE = (V1 + T1) - E0;
                 const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, A.philox_field(field), (uint32_t)l);
                 const bool accept = (dE < 0.0) || (lnu < -dE);
