@@ -315,6 +315,31 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     }
 }
 
+// The chain kernel's copy of philox_normals3 (common.cuh): same counters and uniforms, Box-Muller radius through the
+// kernel's table logarithm and only the cosine branch for the third normal -- a third of the inlined code of the
+// libm version, values equal to a few ulp.
+__device__ __forceinline__ void philox_normals3_tab(uint64_t seed, uint32_t field, uint32_t iter, uint32_t star,
+                                                    const double2* __restrict__ ltab, double (&z)[3]) {
+    uint32_t r[4];
+    Philox::block(seed, star, iter, field, 0u, r);
+    double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+    double rad = sqrt(-2.0 * log_pos(u1, ltab)), s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z[0] = rad * c;
+    z[1] = rad * s;
+    Philox::block(seed, star, iter, field, 1u, r);
+    u1 = u01(r[0], r[1]);
+    u2 = u01(r[2], r[3]);
+    z[2] = sqrt(-2.0 * log_pos(u1, ltab)) * cospi(2.0 * u2);
+}
+
+__device__ __forceinline__ double philox_lnu_tab(uint64_t seed, uint32_t field, uint32_t iter,
+                                                 const double2* __restrict__ ltab) {
+    uint32_t r[4];
+    Philox::block(seed, 0xFFFFFFFFu, iter, field, 2u, r);
+    return log_pos(u01(r[0], r[1]), ltab);
+}
+
 // V(q, f_pos) and T(p, H(q)) of a one-star field from the cached pixel potential and metric
 // (sampler_RHMC.py:294-363).
 // (Making this and the Philox helpers __noinline__ to shrink the kernel was measured slower: the chain state then
@@ -558,7 +583,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                     const double* zp = A.normals + ((size_t)field * L + l) * 3;
                     z[0] = zp[0]; z[1] = zp[1]; z[2] = zp[2];
                 } else {
-                    philox_normals3(A.seed, A.philox_field(field), (uint32_t)l, 0u, z);
+                    philox_normals3_tab(A.seed, A.philox_field(field), (uint32_t)l, 0u, ltab, z);
                 }
                 {
                     const double sxx = sqrt(rcp_fast(s.ihxx));
@@ -584,7 +609,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, ltab, V1, T1);
                 const double dE = (V1 + T1) - E0;
-                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, A.philox_field(field), (uint32_t)l);
+                const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu_tab(A.seed, A.philox_field(field), (uint32_t)l, ltab);
                 const bool accept = (dE < 0.0) || (lnu < -dE);
                 if (keep && writer && A.A_chain) A.A_chain[row] = accept ? 1 : 0;
                 if (accept) {
