@@ -44,19 +44,6 @@ int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm
     return configure_mode<DT, MODE_SINGLE>(smem, nw, blocks_per_sm);
 }
 
-// EXPERIMENT: register-capped variants of the uint16 run kernel (SRHMC_CHAIN_MINB = 128 | 112 | 104 registers)
-template <int MINB>
-int configure_minb(size_t smem, int& nb) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, unsigned short, MODE_RUN, MINB>, 32, smem);
-    return (int)e;
-}
-int g_minb = 0, g_minb_blocks = 0;
-
 template <typename DT>
 void launch_mode(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
     switch (A.mode) {
@@ -133,18 +120,7 @@ int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
     plan.nw = kWarpsPerBlock;
     if (int rc = configure_one<double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64)) return rc;
     if (int rc = configure_one<unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32)) return rc;
-    if (int rc = configure_one<unsigned short>(P, plan.nw, plan.smem_u16, plan.blocks_per_sm_u16)) return rc;
-    g_minb = 0;
-    if (const char* env = std::getenv("SRHMC_CHAIN_MINB")) {
-        g_minb = std::atoi(env);
-        int rc = 0;
-        if (g_minb == 128) rc = configure_minb<128>(plan.smem_u16, g_minb_blocks);
-        else if (g_minb == 112) rc = configure_minb<112>(plan.smem_u16, g_minb_blocks);
-        else if (g_minb == 104) rc = configure_minb<104>(plan.smem_u16, g_minb_blocks);
-        else g_minb = 0;
-        if (rc) return rc;
-    }
-    return 0;
+    return configure_one<unsigned short>(P, plan.nw, plan.smem_u16, plan.blocks_per_sm_u16);
 }
 
 // Iteration chunks per chain for a MODE_RUN launch of `groups` warp-sized work items on `warps` resident warps.
@@ -165,9 +141,9 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     const int n_range = (A.field_end > 0 ? A.field_end : A.n_fields) - A.field_begin;
     const long long blocks = ((long long)n_range + chains_per_block - 1) / chains_per_block;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
-    const bool minb = u16 && A.mode == MODE_RUN && g_minb > 0;
-    const int max_k = minb ? g_minb_blocks
-                           : (u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64));
+    // 168 registers -> 12 resident warps per SM (3 per scheduler).  Register-capped builds were measured: 128 registers /
+    // 16 warps 1057 M star-steps/s, 112 / 18 warps 892, 104 / 19 warps 843 against 1104 at 168 / 12.
+    const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
     int grid = balanced_grid(max_k, blocks, sms);
     A.n_chunks = 1;
     if (A.mode == MODE_RUN && A.sched_done != nullptr) {
@@ -177,11 +153,7 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
         if (chunks > 1 && !std::getenv("SRHMC_CHAIN_BLOCKS_PER_SM")) grid = full;
         A.n_chunks = pick_chunks(blocks, (long long)grid * plan.nw, A.niter + 1);
     }
-    if (minb) {
-        if (g_minb == 128) chain_kernel<kLPC, unsigned short, MODE_RUN, 128><<<grid, 32, plan.smem_u16, stream>>>(P, A);
-        else if (g_minb == 112) chain_kernel<kLPC, unsigned short, MODE_RUN, 112><<<grid, 32, plan.smem_u16, stream>>>(P, A);
-        else chain_kernel<kLPC, unsigned short, MODE_RUN, 104><<<grid, 32, plan.smem_u16, stream>>>(P, A);
-    } else if (u16) {
+    if (u16) {
         launch_mode<unsigned short>(grid, 32 * plan.nw, plan.smem_u16, stream, P, A);
     } else if (A.D_int != nullptr) {
         launch_mode<unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);

@@ -11,9 +11,6 @@ import sys
 import numpy as np
 import pytest
 
-import stellar_oracle as so
-from helpers import golden, setup_from
-
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
