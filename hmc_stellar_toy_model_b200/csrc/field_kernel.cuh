@@ -84,6 +84,12 @@ template <> struct VecLoad<float, 4> { static __device__ __forceinline__ void ld
 // ---------------------------------------------------------------------------------------------- tables
 // One thread per (star, axis).  Exact recurrence: e(u+1) = e(u) r(u), r(u+1) = r(u) exp(-1/s^2), run outwards
 // from the pixel that contains the star so the rounding error stays at a few ulp where the PSF matters.
+// Measured alternatives (C4, 592 fields x 204 stars): this serial build leaves 80% of the CTA idle at the barriers
+// around it (ncu: 37% of stall samples at the phase boundaries, 8% in the zero fill), but a fully parallel build
+// with one direct exponential per in-span entry was SLOWER (437 vs 588 M star-steps/s): the kernel is also
+// instruction-bound, and 2300 exponentials per chunk cost more issue slots than the idle time they remove.  The
+// next step is a strided recurrence with a few lanes per star-axis (as in chain_kernel.cuh) and a single table
+// build per evaluation.
 template <typename T>
 __device__ void build_tables(const Ctx<T>& c, int k0, int nk, bool scale_f) {
     const FieldParams& P = *c.P;
