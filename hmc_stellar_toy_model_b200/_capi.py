@@ -152,6 +152,7 @@ SIGNATURES = {
     "srhmc_abi_version": (C.c_int, []),
     "srhmc_last_error": (C.c_char_p, []),
     "srhmc_device_count": (C.c_int, []),
+    "srhmc_chain_group_size": (C.c_int, []),
     "srhmc_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "srhmc_destroy": (C.c_int, [C.c_void_p]),
     "srhmc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,7 +1,7 @@
 // Warp-resident one-star chain kernel (sm_100a): BASELINE.json configs[0..1] -- thousands of independent
 // one-star RHMC chains on small images (C <= 32 columns, R <= 64 rows).
 //
-// LPC lanes own one chain (LPC = 16: two chains per warp).  A lane owns the image columns sub, sub+LPC, ...;
+// LPC lanes own one chain (LPC = 4: eight chains per warp).  A lane owns the image columns sub, sub+LPC, ...;
 // the chain's data image sits in shared memory for the whole launch; the star state, momenta, cached gradient
 // and energies live in registers (every lane of the group holds the same copy), so a full
 // (niter+1) x nsteps chain runs without any block-level barrier, global traffic (except chain rows written out)
@@ -180,7 +180,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     constexpr unsigned FULL = 0xffffffffu;
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
-    const double cL = (LPC == 8) ? P.cL8 : P.cL16;  // exp(-LPC^2/s^2)
+    const double cL = P.cL;  // exp(-LPC^2/s^2)
     // All exponentials of this evaluation up front in one straight-line block (four independent Horner chains).
     // rows: anchor at the lane's row nearest the star and recur outwards in both directions, so the anchor never
     // underflows while the star is within ~55 px of the image (beyond that every weight is 0 in double anyway);
@@ -197,7 +197,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     const double w_r = exp_neg(-(2.0 * LPC * P.inv2s2) * us);   // r_up = w cLh, r_dn = cLh / w, cLh = exp(-L^2/2s^2)
     const double e_c = exp_neg(-arg_c);
     const double r_c = exp_neg(-fma(2.0 * LPC, v0, LL) * P.inv2s2);
-    const double cLh = (LPC == 8) ? P.cLh8 : P.cLh16;
+    const double cLh = P.cLh;
     double sa = 0.0;
     if (K > 0) {
         const double es = ok_r ? e_r : 0.0;
@@ -429,7 +429,10 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     if ((s.y < 0.0) || (s.y > P.C - 1.0)) s.py = -s.py;
 }
 
-template <int LPC, typename DT, int MODE, int MAXREG = 168>
+#ifndef SRHMC_CHAIN_MAXREG
+#define SRHMC_CHAIN_MAXREG (LPC <= 4 ? 232 : 168)
+#endif
+template <int LPC, typename DT, int MODE, int MAXREG = SRHMC_CHAIN_MAXREG>
 __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp

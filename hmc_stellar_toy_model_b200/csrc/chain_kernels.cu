@@ -10,7 +10,7 @@ namespace srhmc {
 
 namespace {
 
-constexpr int kLPC = 8;  // lanes per chain: 4 chains per warp (measured faster than 16 lanes / 2 chains)
+constexpr int kLPC = kChainLPC;  // lanes per chain: 8 -> 4 chains per warp (measured faster than 16 lanes / 2 chains)
 constexpr int kWarpsPerBlock = 1;
 
 size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {

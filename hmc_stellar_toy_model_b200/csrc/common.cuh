@@ -7,6 +7,14 @@
 namespace srhmc {
 
 constexpr int kWarp = 32;
+// Lanes per chain of the one-star kernel.  Measured on the headline workload: 16 lanes 734, 8 lanes 1104, 4 lanes
+// 1210 M star-steps/s -- fewer lanes replicate the per-chain scalar work and the table exponentials less; 2 lanes
+// would need more than 255 registers.
+#ifndef SRHMC_LPC
+#define SRHMC_LPC 4
+#endif
+constexpr int kChainLPC = SRHMC_LPC;
+constexpr int kChainGroup = 32 / kChainLPC;   // chains per warp: the unit of its work scheduler
 
 // Problem constants snapshot (host fills it from srhmc_config).
 struct FieldParams {
@@ -25,8 +33,8 @@ struct FieldParams {
     double c2;         // exp(-1/sigma^2): second-order ratio of the Gaussian recurrence
     double B, f_lim, f_low;
     double lnB, invB;  // ln(B), 1/B (chain kernel's separable potential)
-    double cL8, cL16;  // exp(-64/sigma^2), exp(-256/sigma^2): stride-8 / stride-16 Gaussian recurrences
-    double cLh8, cLh16;  // their square roots exp(-L^2/2 sigma^2)
+    double cL, cLh;    // exp(-L^2/sigma^2) and its square root for the chain kernel's stride-L Gaussian recurrences
+                       // (L = lanes per chain, kChainLPC)
     double wcut;       // |i + .5 - x| beyond which exp(-(..)^2/2 sigma^2) < 2^-50
     double g0, g1, g2, g_xx, g_ff;
     double alpha, Vpc, vc_pow;

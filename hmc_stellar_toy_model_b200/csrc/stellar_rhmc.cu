@@ -169,7 +169,7 @@ int launch_field(srhmc_ctx* c, const LaunchArgs& A_in, bool one_star_everywhere)
     const bool chain = c->chain_ok && one_star_everywhere;
     if (chain && A.mode == MODE_RUN) {
         // scheduler state of the chunked chain kernel: completion counters start at 0 for every launch
-        const size_t groups = ((size_t)A.n_fields + 3) / 4;
+        const size_t groups = ((size_t)A.n_fields + kChainGroup - 1) / kChainGroup;
         if (int rc = c->sched_done.ensure(groups * sizeof(int))) return rc;
         if (int rc = c->sched_state.ensure((size_t)A.n_fields * 8 * sizeof(double))) return rc;
         if (int rc = c->sched_err.ensure(sizeof(int))) return rc;
@@ -226,6 +226,8 @@ extern "C" {
 
 int srhmc_abi_version(void) { return SRHMC_ABI_VERSION; }
 const char* srhmc_last_error(void) { return g_err; }
+
+int srhmc_chain_group_size(void) { return kChainGroup; }
 
 int srhmc_device_count(void) {
     int n = 0;
@@ -291,10 +293,8 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.B = cfg->B_count;
     P.lnB = std::log(cfg->B_count);
     P.invB = 1.0 / cfg->B_count;
-    P.cL8 = std::exp(-64.0 / (sigma * sigma));
-    P.cL16 = std::exp(-256.0 / (sigma * sigma));
-    P.cLh8 = std::exp(-32.0 / (sigma * sigma));
-    P.cLh16 = std::exp(-128.0 / (sigma * sigma));
+    P.cL = std::exp(-(double)(kChainLPC * kChainLPC) / (sigma * sigma));
+    P.cLh = std::exp(-(double)(kChainLPC * kChainLPC) / (2.0 * sigma * sigma));
     P.wcut = std::sqrt(50.0 * M_LN2 * 2.0 * sigma * sigma);
     P.f_lim = cfg->f_lim;
     P.f_low = cfg->f_low;
@@ -714,7 +714,7 @@ static int run_sliced(srhmc_ctx* c, const srhmc_run_args* a) {
         }
         CU_TRY(cudaEventCreateWithFlags(&c->slice_go, cudaEventDisableTiming));
     }
-    const size_t groups = (F + 3) / 4;
+    const size_t groups = (F + kChainGroup - 1) / kChainGroup;
     if (int rc = c->sched_done.ensure(groups * sizeof(int))) return rc;
     if (int rc = c->sched_state.ensure(F * 8 * sizeof(double))) return rc;
     if (int rc = c->sched_err.ensure(sizeof(int))) return rc;
@@ -726,7 +726,7 @@ static int run_sliced(srhmc_ctx* c, const srhmc_run_args* a) {
     c->sched_used = true;
     if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
     CU_TRY(cudaEventRecord(c->slice_go, c->stream));
-    const size_t per = ((F + kSlices - 1) / kSlices + 3) / 4 * 4;
+    const size_t per = ((F + kSlices - 1) / kSlices + kChainGroup - 1) / kChainGroup * kChainGroup;
     for (int s = 0; s < kSlices; ++s) {
         const size_t f0 = std::min(F, (size_t)s * per), f1 = std::min(F, f0 + per), nf = f1 - f0;
         cudaStream_t st = c->slice_streams[s];

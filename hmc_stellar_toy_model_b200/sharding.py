@@ -1,7 +1,7 @@
 """Sharding of independent chains / fields over the GPUs of one node (BASELINE configs[1] and [3]).
 
-Independent chains need no data-path collective: the batch is cut into blocks of `BLOCK` = 4 consecutive chains (the
-one-star kernel's warp group) and rank r owns blocks r, r+W, r+2W, ... (`blocks[r::W]`), runs them in ONE resident
+Independent chains need no data-path collective: the batch is cut into blocks of `BLOCK` consecutive chains (the
+one-star kernel's warp group, 8) and rank r owns blocks r, r+W, r+2W, ... (`blocks[r::W]`), runs them in ONE resident
 launch on its own GPU, and the device RNG is keyed by the *global* chain id (`field_ids`), so the sharded run is
 bit-identical to the same batch on one GPU.
 `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used only to gather the per-rank chain arrays; the
@@ -14,7 +14,17 @@ from typing import Callable, Dict
 import numpy as np
 
 
-BLOCK = 4  # chains per warp group of the one-star kernel: shards keep these groups intact
+def _group_size() -> int:
+    """Chains per warp group of the one-star kernel (srhmc_chain_group_size); shards keep these groups intact."""
+    try:
+        from . import _capi
+
+        return int(_capi.load_library().srhmc_chain_group_size())
+    except Exception:  # library not built yet: the value only matters for bit-identity on a GPU
+        return 8
+
+
+BLOCK = _group_size()
 
 
 def shard_ids(n_items: int, rank: int, world: int, block: int = BLOCK) -> np.ndarray:

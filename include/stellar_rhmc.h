@@ -148,9 +148,9 @@ typedef struct srhmc_run_args {
      * ids[rank::world] passes base = rank, stride = world and reproduces the single-GPU run bit for bit. */
     int32_t field_id_base;
     int32_t field_id_stride;
-    /* Optional explicit ids [F] overriding base/stride (any shard map).  Note: the one-star kernel packs 4 consecutive
-     * fields into a warp and its row windows / log tiers are the union over the warp, so bit-identity with an
-     * unsharded run additionally needs shards made of whole groups of 4 consecutive chains (sharding.py does that);
+    /* Optional explicit ids [F] overriding base/stride (any shard map).  Note: the one-star kernel packs
+     * srhmc_chain_group_size() consecutive fields into a warp and its row windows / log tiers are the union over the
+     * warp, so bit-identity with an unsharded run additionally needs shards made of whole groups (sharding.py does that);
      * otherwise results agree to ~1e-15 relative. */
     const int32_t* field_ids;
 } srhmc_run_args;
@@ -158,6 +158,9 @@ typedef struct srhmc_run_args {
 int srhmc_abi_version(void);
 const char* srhmc_last_error(void);
 int srhmc_device_count(void);
+/* Chains the one-star kernel packs into one warp.  Shards of a batch that keep groups of this many consecutive chains
+ * together reproduce the unsharded run bit for bit (see srhmc_run_args.field_ids). */
+int srhmc_chain_group_size(void);
 
 int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out);
 int srhmc_destroy(srhmc_ctx* ctx);

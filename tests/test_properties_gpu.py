@@ -32,7 +32,7 @@ def _bench_module():
 def test_full_batch_determinism_and_position_independence():
     """11 000 chains (the headline batch): two launches with the same seed are bit-identical, and a chain's result
     depends only on its data, start and global id -- not on where it sits in the batch or how the batch is cut into
-    warp groups of four."""
+    warp groups."""
     from hmc_stellar_toy_model_b200 import RHMCContext
 
     wl = _bench_module().workload_c2(1000, 5)
@@ -49,8 +49,10 @@ def test_full_batch_determinism_and_position_independence():
     per_mag = a.accept_rate.reshape(11, 1000).mean(axis=1)
     assert per_mag[0] > per_mag[-1]
     # the same 40 chains, reversed group order and padded to a different batch size, ids kept
-    pick = np.arange(4000, 4040)
-    order = pick.reshape(10, 4)[::-1].ravel()          # whole warp groups, permuted
+    from hmc_stellar_toy_model_b200 import sharding
+
+    pick = np.arange(4000, 4000 + 5 * sharding.BLOCK)
+    order = pick.reshape(5, sharding.BLOCK)[::-1].ravel()   # whole warp groups, permuted
     cfg = dict(wl["cfg"], n_fields=len(order))
     with RHMCContext(**cfg) as ctx:
         ctx.set_data(wl["D"][order])
