@@ -11,8 +11,11 @@ What runs where
                   global np.random stream is consumed in exactly the reference's order (sampler_RHMC.py:1021-1075:
                   randn(3N), one uniform for np.random.choice, one uniform for the accept test, per iteration), so a
                   script that seeds np.random reproduces the reference's chain step for step.
+  host + device   reversible-jump moves (birth/death, split/merge; sampler_RHMC.py:1084-1445): the trans-dimensional
+                  proposal bookkeeping stays on the host as upstream, every RHMC leg / V / H / T around it runs on the
+                  device (one launch per leg).
   not provided    matplotlib diagnostics (no-ops here), the "naive"/"leap_frog" solvers and run_single_HMC (unused by
-                  any script, labelled broken upstream), reversible-jump moves.
+                  any script, labelled broken upstream).
 
 There is no CPU fallback: every numeric method needs the CUDA library and a B200.
 """
@@ -22,7 +25,7 @@ import numpy as np
 
 from .context import RHMCContext
 from .utils import *  # noqa: F401,F403  (the reference star-imports utils into this namespace, sampler_RHMC.py:25)
-from .utils import factors, gauss_PSF, mag2flux, flux2mag, poisson_realization
+from .utils import factors, gauss_PSF, gen_pow_law_sample, mag2flux, flux2mag, poisson_realization
 
 __all__ = ["base_class", "single_gym", "multi_gym"]
 
@@ -188,7 +191,9 @@ class base_class(object):
     def T(self, p, H_diag):
         """(p^T H^-1 p + log|H|)/2 for the diagonal H given (sampler_RHMC.py:353-363)."""
         p = np.asarray(p, dtype=float).ravel()
-        return self._device_ctx(max(1, self._nobjs(p)), need_data=False).kinetic_diag(p, H_diag)
+        # any live context can reduce a diagonal of any length; do not rebuild one just because N changed
+        ctx = self._ctx if self._ctx is not None else self._device_ctx(max(1, self._nobjs(p)), need_data=False)
+        return ctx.kinetic_diag(p, H_diag)
 
     def dVdq(self, q):
         q = np.asarray(q, dtype=float).ravel()
@@ -311,16 +316,15 @@ class multi_gym(base_class):
         q0 = self.format_q(q_model_0)
         L = Niter + 1
 
+        if float(P_move[1]) != 0.0 or float(P_move[2]) != 0.0:
+            return self._run_RHMC_rj(q0, f_pos, delta, counter_max, verbose, schedule_g_ff2, schedule_beta)
+
         # the reference's draws, in the reference's order (sampler_RHMC.py:1022, 1046, 1075)
         normals = np.empty((L, self.d))
         lnu = np.empty(L)
         for l in range(L):
             normals[l] = self.u_sample(self.d)
-            move_type = np.random.choice([0, 1, 2], p=self.P_move, size=1)[0]
-            if move_type != 0:
-                raise NotImplementedError(
-                    "reversible-jump proposals (birth/death, split/merge; sampler_RHMC.py:1084-1181) are not part of "
-                    "the B200 path yet: run with P_move = [1, 0, 0]")
+            np.random.choice([0, 1, 2], p=self.P_move, size=1)
             lnu[l] = np.log(np.random.random(1))[0]
 
         ctx = self._device_ctx(self.Nobjs)
@@ -354,11 +358,225 @@ class multi_gym(base_class):
         print("Finished. Final report.")
         self.R_accept_report(idx_iter=-1, running=False)
 
+    # ------------------------------------------------------------------ reversible-jump leg
+    # The trans-dimensional proposals are host-side bookkeeping exactly as upstream (sampler_RHMC.py:1084-1181,
+    # 1200-1445, same np.random / scipy BETA call order); every RHMC leg, V, H and T run on the device through ONE
+    # context sized for N_max stars with the live count passed per call.
+    def _rj_ctx(self):
+        return self._device_ctx(self.N_max)
+
+    def _pad(self, v):
+        out = np.zeros((1, 3 * self.N_max))
+        out[0, :v.size] = v
+        return out
+
+    def _rj_steps(self, q, p, nsteps, delta, counter_max):
+        n = q.size // 3
+        if n == 0 or nsteps == 0:
+            return np.array(q, dtype=float), np.array(p, dtype=float)
+        qn, pn = self._rj_ctx().step(self._pad(q), self._pad(p), nsteps, self.dt, delta=delta, counter_max=counter_max,
+                                     g_ff2=self.g_ff2, beta=self.beta, nstars=[n])
+        return qn[0, :q.size].copy(), pn[0, :p.size].copy()
+
+    def _rj_VH(self, q, f_pos):
+        n = q.size // 3
+        V, _, H, _ = self._rj_ctx().eval(self._pad(q), nstars=[n], f_pos=f_pos, g_ff2=self.g_ff2, beta=self.beta)
+        return float(V[0]), H[0, :q.size].copy()
+
+    def _run_RHMC_rj(self, q0, f_pos, delta, counter_max, verbose, schedule_g_ff2, schedule_beta):
+        Niter, Nsteps, N_max = self.Niter, self.Nsteps, self.N_max
+        L = Niter + 1
+        self.q_chain = np.zeros((L, N_max * 3))
+        self.p_chain = np.zeros((L, N_max * 3))
+        self.E_chain = np.zeros(L)
+        self.V_chain = np.zeros(L)
+        self.T_chain = np.zeros(L)
+        self.A_chain = np.zeros(L, dtype=bool)
+        self.move_chain = np.zeros(L, dtype=int)
+        self.N_chain = np.zeros(L, dtype=int)
+        q_tmp = np.copy(q0)
+        for l in range(L):
+            if schedule_g_ff2 is not None and l < schedule_g_ff2.size:
+                self.g_ff2 = schedule_g_ff2[l]
+            if schedule_beta is not None and l < schedule_beta.size:
+                self.beta = schedule_beta[l]
+            V_initial, H_diag = self._rj_VH(q_tmp, f_pos)
+            p_tmp = self.u_sample(self.d) * np.sqrt(H_diag)
+            T_initial = self.T(p_tmp, H_diag) if self.d else 0.0
+            E_initial = V_initial + T_initial
+            self.q_chain[l, :self.Nobjs * 3] = q_tmp
+            self.p_chain[l, :self.Nobjs * 3] = p_tmp
+            self.V_chain[l], self.E_chain[l], self.T_chain[l] = V_initial, E_initial, T_initial
+            self.N_chain[l] = self.Nobjs
+            move_type = np.random.choice([0, 1, 2], p=self.P_move, size=1)[0]
+            if move_type == 0:
+                self.move_chain[l] = 0
+                q_tmp, p_tmp = self._rj_steps(q_tmp, p_tmp, Nsteps, delta, counter_max)
+                V_final, H_diag = self._rj_VH(q_tmp, f_pos)
+                dE = V_final + self.T(p_tmp, H_diag) - E_initial
+                lnu = np.log(np.random.random(1))
+                if (dE < 0) or (lnu < -dE):
+                    self.A_chain[l] = 1
+                else:
+                    q_tmp = np.copy(self.q_chain[l, :self.Nobjs * 3])
+            else:
+                grow = bool(np.random.choice([True, False], p=[0.5, 0.5]))
+                if move_type == 1:
+                    self.move_chain[l] = 1 if grow else 2
+                else:
+                    self.move_chain[l] = 3 if grow else 4
+                q_tmp, p_tmp = self._rj_steps(q_tmp, p_tmp, Nsteps, delta, counter_max)
+                p_tmp = -p_tmp
+                if move_type == 1:
+                    q_tmp, p_tmp, factor = self.birth_death_move(q_tmp, p_tmp, birth_death=grow)
+                else:
+                    q_tmp, p_tmp, factor = self.split_merge_move(q_tmp, p_tmp, split_merge=grow)
+                if self.Nobjs > N_max:
+                    raise ValueError("the proposal needs %d stars but N_max = %d" % (self.Nobjs, N_max))
+                q_tmp, p_tmp = self._rj_steps(q_tmp, p_tmp, Nsteps, delta, counter_max)
+                p_tmp = -p_tmp
+                V_final, H_diag = self._rj_VH(q_tmp, f_pos)
+                dE = V_final + (self.T(p_tmp, H_diag) if p_tmp.size else 0.0) - E_initial
+                ln_alpha0 = -dE + factor
+                lnu = np.log(np.random.random(1))
+                if (ln_alpha0 > 0) or (lnu < ln_alpha0):
+                    self.A_chain[l] = 1
+                else:
+                    if grow:
+                        self.Nobjs -= 1
+                        self.d -= 3
+                    else:
+                        self.Nobjs += 1
+                        self.d += 3
+                    q_tmp = np.copy(self.q_chain[l, :self.Nobjs * 3])
+            if verbose and ((l % 50) == 0):
+                print("/---- Completed iteration %d" % l)
+                print("N_objs: %d\n" % self.Nobjs)
+                self.R_accept_report(idx_iter=l, run_window=10)
+                print("\n\n")
+        print("Finished. Final report.")
+        self.R_accept_report(idx_iter=-1, running=False)
+
+    def _one_star(self, q3, p3=None):
+        """H (and T when p3 is given) of a single star: the reference's `self.Nobjs = 1` blocks."""
+        H, _ = self._rj_ctx().metric(np.asarray(q3, dtype=float), self.g_ff2)
+        T = None if p3 is None else self.T(p3, H)
+        return H, T
+
     def birth_death_move(self, q_tmp, p_tmp, birth_death=None):
-        raise NotImplementedError("reversible-jump moves are not part of the B200 path yet (SURVEY.md 8f)")
+        """Birth (True) or death (False) proposal; returns (q, p, factor) (sampler_RHMC.py:1200-1273)."""
+        if (birth_death is None) or (self.alpha is None) or (self.fmin is None) or (self.fmax is None):
+            assert False
+        self._prior_const()
+        if birth_death:
+            q = np.zeros(q_tmp.size + 3)
+            p = np.zeros(q_tmp.size + 3)
+            q[:q_tmp.size] = q_tmp
+            p[:p_tmp.size] = p_tmp
+            x = np.random.random() * (self.num_rows - 2.) + 1.
+            y = np.random.random() * (self.num_cols - 2.) + 1.
+            f = gen_pow_law_sample(self.alpha, self.fmin, self.fmax, 1)[0]
+            q_new = np.array([f, x, y])
+            q[-3:] = q_new
+            H_diag, _ = self._one_star(q_new)
+            p_new = self.u_sample(3) * np.sqrt(H_diag)
+            p[-3:] = p_new
+            factor = self.alpha * np.log(f) - 3 / 2. + self.T(p_new, H_diag) + self.V_prior_const
+            self.d += 3
+            self.Nobjs += 1
+        else:
+            q = np.zeros(q_tmp.size - 3)
+            p = np.zeros(q_tmp.size - 3)
+            i_kill = np.random.randint(0, self.Nobjs, size=1)[0]
+            q_killed = q_tmp[3 * i_kill:3 * i_kill + 3]
+            p_killed = p_tmp[3 * i_kill:3 * i_kill + 3]
+            q[:3 * i_kill] = q_tmp[:3 * i_kill]
+            q[3 * i_kill:] = q_tmp[3 * i_kill + 3:]
+            p[:3 * i_kill] = p_tmp[:3 * i_kill]
+            p[3 * i_kill:] = p_tmp[3 * i_kill + 3:]
+            H_diag, T_killed = self._one_star(q_killed, p_killed)
+            factor = -self.alpha * np.log(q_killed[0]) + 3 / 2. - T_killed - self.V_prior_const
+            self.d -= 3
+            self.Nobjs -= 1
+        return q, p, factor
 
     def split_merge_move(self, q_tmp, p_tmp, split_merge=None):
-        raise NotImplementedError("reversible-jump moves are not part of the B200 path yet (SURVEY.md 8f)")
+        """Split (True) or merge (False) proposal; returns (q, p, factor) (sampler_RHMC.py:1276-1445)."""
+        from scipy.stats import beta as BETA  # utils.py:18-21 of the reference
+
+        if split_merge is None:
+            assert False
+        if split_merge:
+            q = np.zeros(q_tmp.size + 3)
+            p = np.zeros(q_tmp.size + 3)
+            q[:q_tmp.size] = q_tmp
+            p[:p_tmp.size] = p_tmp
+            i_star = np.random.randint(0, self.Nobjs, size=1)[0]
+            f_star, x_star, y_star = q_tmp[3 * i_star:3 * i_star + 3]
+            p_star = np.copy(p_tmp[3 * i_star:3 * i_star + 3])
+            q_star = np.copy(q_tmp[3 * i_star:3 * i_star + 3])
+            dx, dy = np.random.randn(2) * self.K_split
+            dr_sq = dx ** 2 + dy ** 2
+            F = BETA.rvs(self.beta_a, self.beta_b, size=1)[0]
+            q_prime = np.array([F * f_star, x_star + (1 - F) * dx, y_star + (1 - F) * dy])
+            q_dprime = np.array([(1 - F) * f_star, x_star - F * dx, y_star - F * dy])
+            q[3 * i_star:3 * i_star + 3] = q_prime
+            q[-3:] = q_dprime
+            H_diag, _ = self._one_star(q_prime)
+            p_prime = self.u_sample(3) * np.sqrt(H_diag)
+            p[3 * i_star:3 * i_star + 3] = p_prime
+            T_prime = self.T(p_prime, H_diag)
+            H_diag, _ = self._one_star(q_dprime)
+            p_dprime = self.u_sample(3) * np.sqrt(H_diag)
+            p[-3:] = p_dprime
+            T_dprime = self.T(p_dprime, H_diag)
+            _, T_star = self._one_star(q_star, p_star)
+            factor = (-3 / 2.) + np.log(f_star) - BETA.logpdf(F, self.beta_a, self.beta_b) \
+                + np.log(2 * np.pi * self.K_split ** 2) + (dr_sq / (2 * self.K_split ** 2)) \
+                + T_prime + T_dprime - T_star
+            self.d += 3
+            self.Nobjs += 1
+        else:
+            f_vec = np.array(q_tmp[0::3], dtype=float)
+            x_vec = np.array(q_tmp[1::3], dtype=float)
+            y_vec = np.array(q_tmp[2::3], dtype=float)
+            F_matrix = f_vec / (f_vec.reshape((self.Nobjs, 1)) + f_vec)
+            ibool = np.abs(F_matrix - 0.5) < 1e-6
+            BETA_F = BETA.pdf(F_matrix, self.beta_a, self.beta_b)
+            BETA_F[ibool] = 0.
+            R_sq = (x_vec.reshape((self.Nobjs, 1)) - x_vec) ** 2 + (y_vec.reshape((self.Nobjs, 1)) - y_vec) ** 2
+            Q_dxdy = np.exp(-R_sq / (2. * self.K_split ** 2)) / (2. * np.pi * self.K_split ** 2)
+            P_choose = BETA_F * Q_dxdy
+            P_choose /= np.sum(P_choose)
+            pair_num = np.random.choice(range(self.Nobjs ** 2), p=P_choose.ravel())
+            idx_prime = pair_num // self.Nobjs
+            idx_dprime = pair_num % self.Nobjs
+            q_prime = np.copy(q_tmp[3 * idx_prime:3 * idx_prime + 3])
+            p_prime = np.copy(p_tmp[3 * idx_prime:3 * idx_prime + 3])
+            q_dprime = np.copy(q_tmp[3 * idx_dprime:3 * idx_dprime + 3])
+            p_dprime = np.copy(p_tmp[3 * idx_dprime:3 * idx_dprime + 3])
+            f_prime, x_prime, y_prime = q_prime
+            f_dprime, x_dprime, y_dprime = q_dprime
+            F = f_prime / (f_prime + f_dprime)
+            dx = x_prime - x_dprime
+            dy = y_prime - y_dprime
+            dr_sq = dx ** 2 + dy ** 2
+            f_star = f_prime + f_dprime
+            q_star = np.array([f_star, F * x_prime + (1 - F) * x_dprime, F * y_prime + (1 - F) * y_dprime])
+            _, T_prime = self._one_star(q_prime, p_prime)
+            _, T_dprime = self._one_star(q_dprime, p_dprime)
+            H_diag, _ = self._one_star(q_star)
+            p_star = self.u_sample(3) * np.sqrt(H_diag)
+            T_star = self.T(p_star, H_diag)
+            idx_a, idx_b = (idx_prime, idx_dprime) if idx_prime < idx_dprime else (idx_dprime, idx_prime)
+            q = np.concatenate([q_tmp[:3 * idx_a], q_tmp[3 * idx_a + 3:3 * idx_b], q_tmp[3 * idx_b + 3:], q_star])
+            p = np.concatenate([p_tmp[:3 * idx_a], p_tmp[3 * idx_a + 3:3 * idx_b], p_tmp[3 * idx_b + 3:], p_star])
+            factor = (3 / 2.) - np.log(f_star) + BETA.logpdf(F, self.beta_a, self.beta_b) \
+                - np.log(2 * np.pi * self.K_split ** 2) - (dr_sq / (2 * self.K_split ** 2)) \
+                - T_prime - T_dprime + T_star
+            self.d -= 3
+            self.Nobjs -= 1
+        return q, p, factor
 
     def R_accept_report(self, idx_iter, cumulative=True, running=True, run_window=10):
         """Acceptance rate so far broken down by move type (sampler_RHMC.py:1447-1473)."""

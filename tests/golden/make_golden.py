@@ -325,10 +325,42 @@ def best_dt(seed=31, mT=19.0):
                 B_count=np.float64(gym.B_count), PSF_FWHM_pix=np.float64(gym.PSF_FWHM_pix))
 
 
+def rj_chain(seed=77, niter=60, nobj=20, nmodel=5, nsteps=5, dt=5e-2):
+    """RHMC-big-sim4.py flow in miniature: reversible-jump RHMC (birth/death, split/merge around two RHMC legs)."""
+    gym = srhmc.multi_gym(dt=0.0, Nsteps=0, g_xx=0.05, g_ff=4.0, g_ff2=4.0)
+    np.random.seed(seed)
+    gym.num_rows = gym.num_cols = 32
+    q_true = np.zeros((nobj, 3))
+    q_model = np.zeros((nmodel, 3))
+    alpha = 2.0
+    fmin = gym.mag2flux_converter(20.0)
+    fmax = gym.mag2flux_converter(15.0)
+    mag = gym.flux2mag_converter(utils.gen_pow_law_sample(alpha, fmin, fmax, nobj))
+    for i in range(nobj):
+        x = np.random.random() * (gym.num_rows - 2.0) + 1.0
+        y = np.random.random() * (gym.num_cols - 2.0) + 1.0
+        q_true[i] = np.array([mag[i], x, y])
+    gym.fmin, gym.fmax = fmin, fmax
+    gym.K_split, gym.beta_a, gym.beta_b = 1.0, 4.0, 4.0
+    gym.use_prior, gym.alpha = True, alpha
+    mag = gym.flux2mag_converter(utils.gen_pow_law_sample(alpha, fmin, fmax, nmodel))
+    q_model[:, 0] = mag
+    q_model[:, 1] = np.random.random(size=nmodel) * (gym.num_rows - 2.0) + 1.0
+    q_model[:, 2] = np.random.random(size=nmodel) * (gym.num_cols - 2.0) + 1.0
+    gym.gen_mock_data(q_true)
+    with ref_shim.quiet():
+        gym.run_RHMC(np.copy(q_model), f_pos=True, delta=1e-6, Niter=niter, Nsteps=nsteps, dt=dt, save_traj=False,
+                     verbose=False, q_true=q_true, P_move=[0.4, 0.3, 0.3], N_max=30)
+    return dict(D=gym.D, q_true=q_true, q_model=q_model, seed=seed, niter=niter, nsteps=nsteps, dt=dt,
+                q_chain=gym.q_chain, p_chain=gym.p_chain, E_chain=gym.E_chain, V_chain=gym.V_chain, T_chain=gym.T_chain,
+                A_chain=gym.A_chain, move_chain=gym.move_chain, N_chain=gym.N_chain, next_uniform=np.random.random(1),
+                **gym_state(gym))
+
+
 def main():
     only = sys.argv[1:]
     if only:
-        makers = {"light_hess": light_hess, "best_dt": best_dt}
+        makers = {"light_hess": light_hess, "best_dt": best_dt, "rj_chain": rj_chain}
         for name in only:
             arrays = makers[name]()
             path = os.path.join(HERE, name + ".npz")
@@ -350,6 +382,7 @@ def main():
         "light_chains": light_chains(),
         "light_hess": light_hess(),
         "best_dt": best_dt(),
+        "rj_chain": rj_chain(),
     }
     for name, arrays in cases.items():
         path = os.path.join(HERE, name + ".npz")

@@ -61,12 +61,7 @@ def test_mock_data_follows_reference_stream():
     assert np.array_equal(gym.D, g["D"])
 
 
-def test_rj_moves_are_refused_loudly():
-    from hmc_stellar_toy_model_b200.sampler_RHMC import multi_gym
-
-    gym = multi_gym()
-    with pytest.raises(NotImplementedError):
-        gym.birth_death_move(None, None)
+def test_unsupported_solvers_are_refused_loudly():
     s = __import__("hmc_stellar_toy_model_b200.sampler_RHMC", fromlist=["single_gym"]).single_gym()
     with pytest.raises(NotImplementedError):
         s.run_single_RHMC(np.array([[19.0, 8.0, 8.0]]), solver="naive")
@@ -212,3 +207,46 @@ def test_gym_methods_match_reference(name):
     q1, p1 = gym.RHMC_single_step(np.copy(q), np.copy(p), 1e-6, 1000)
     assert relerr(q1, g["q_traj"][1]) < RTOL and relerr(p1, g["p_traj"][1]) < 1e-9
     assert np.isinf(gym.V(np.concatenate([[1.0], q[1:]]), f_pos=True))  # flux below f_lim
+
+
+@pytest.mark.gpu
+def test_reversible_jump_script():
+    """RHMC-big-sim4.py flow in miniature (make_golden.rj_chain): birth/death and split/merge proposals around two
+    device RHMC legs; proposal types, accept decisions, star counts and chains must follow the reference."""
+    from hmc_stellar_toy_model_b200.sampler_RHMC import multi_gym, gen_pow_law_sample
+
+    g = golden("rj_chain")
+    nobj, nmodel = g["q_true"].shape[0], g["q_model"].shape[0]
+    niter, nsteps, dt = int(g["niter"]), int(g["nsteps"]), float(g["dt"])
+    gym = multi_gym(dt=0.0, Nsteps=0, g_xx=0.05, g_ff=4.0, g_ff2=4.0)
+    np.random.seed(int(g["seed"]))
+    gym.num_rows = gym.num_cols = 32
+    q_true = np.zeros((nobj, 3))
+    q_model = np.zeros((nmodel, 3))
+    alpha = 2.0
+    fmin = gym.mag2flux_converter(20.0)
+    fmax = gym.mag2flux_converter(15.0)
+    mag = gym.flux2mag_converter(gen_pow_law_sample(alpha, fmin, fmax, nobj))
+    for i in range(nobj):
+        x = np.random.random() * (gym.num_rows - 2.0) + 1.0
+        y = np.random.random() * (gym.num_cols - 2.0) + 1.0
+        q_true[i] = np.array([mag[i], x, y])
+    gym.fmin, gym.fmax = fmin, fmax
+    gym.K_split, gym.beta_a, gym.beta_b = 1.0, 4.0, 4.0
+    gym.use_prior, gym.alpha = True, alpha
+    mag = gym.flux2mag_converter(gen_pow_law_sample(alpha, fmin, fmax, nmodel))
+    q_model[:, 0] = mag
+    q_model[:, 1] = np.random.random(size=nmodel) * (gym.num_rows - 2.0) + 1.0
+    q_model[:, 2] = np.random.random(size=nmodel) * (gym.num_cols - 2.0) + 1.0
+    gym.gen_mock_data(q_true)
+    assert np.array_equal(gym.D, g["D"]) and np.array_equal(q_model, g["q_model"])
+    with quiet():
+        gym.run_RHMC(np.copy(q_model), f_pos=True, delta=1e-6, Niter=niter, Nsteps=nsteps, dt=dt, save_traj=False,
+                     verbose=False, q_true=q_true, P_move=[0.4, 0.3, 0.3], N_max=30)
+    assert np.array_equal(gym.move_chain, g["move_chain"])
+    assert np.array_equal(gym.N_chain, g["N_chain"])
+    assert np.array_equal(gym.A_chain, g["A_chain"])
+    assert set(np.unique(g["move_chain"])) == {0, 1, 2, 3, 4} and g["N_chain"].max() > g["N_chain"].min()
+    assert relerr(gym.E_chain, g["E_chain"]) < 1e-9
+    assert first_divergence(gym.q_chain, g["q_chain"], 1e-7) == -1
+    assert np.random.random(1)[0] == g["next_uniform"][0]
