@@ -26,11 +26,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "../../include/stellar_rhmc.h"
 #include "common.cuh"
+#include "fastmath.cuh"
 
 using namespace srhmc;
 
@@ -330,13 +332,29 @@ __global__ void big_momentum_kernel(const BigParams P, double g_ff2, int n, cons
     }
 }
 
+// Last-block election for fixed-order two-stage reductions: every block publishes its partials, takes a ticket, and
+// the block that draws the last ticket sums all partials in index order (bit-reproducible, one launch).
+__device__ __forceinline__ bool last_block_ticket(unsigned int* ticket, bool* flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *flag = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (*flag) __threadfence();
+    return *flag;
+}
+
+constexpr int kEnergyBlocks = 256;
+
 // scalars[1] = sum (p^2/H + ln|H|)/2, scalars[2] = # stars outside the support, scalars[3] = prior potential
-// (fixed-order: one block)
+// (per-block partials, summed in block order by the last block)
 __global__ void big_energy_kernel(const BigParams P, double g_ff2, int f_pos, int n, const double* q, const double* p,
-                                  double* scalars) {
+                                  double* part /* [gridDim.x][4] */, unsigned int* ticket, double* scalars) {
     __shared__ double red[4 * 32];
+    __shared__ bool is_last;
     double v[4] = {0, 0, 0, 0};
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
         const Metric m = metric_of(P.F, f, g_ff2);
         const double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
@@ -347,10 +365,18 @@ __global__ void big_energy_kernel(const BigParams P, double g_ff2, int f_pos, in
         v[3] += bad ? 1.0 : 0.0;
     }
     block_sum<4>(v, red);
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 4; ++c) part[4 * blockIdx.x + c] = v[c];
+    if (!last_block_ticket(ticket, &is_last)) return;
+    double w[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        for (int c = 0; c < 4; ++c) w[c] += __ldcg(part + 4 * b + c);
+    block_sum<4>(w, red);
     if (threadIdx.x == 0) {
-        scalars[1] = (v[0] + v[1]) / 2.0;
-        scalars[2] = v[3];
-        scalars[3] = v[2];
+        scalars[1] = (w[0] + w[1]) / 2.0;
+        scalars[2] = w[3];
+        scalars[3] = w[2];
+        *ticket = 0u;
     }
 }
 
@@ -460,6 +486,8 @@ struct BBuf {
 
 }  // namespace
 
+#include "big_tile.cuh"
+
 struct srhmc_big {
     srhmc_big_config cfg;
     BigParams P;
@@ -468,6 +496,11 @@ struct srhmc_big {
     int sm_count = 0;
     int64_t launches = 0;
     BBuf D, L, q, p, g, a1, a2, q0, g0, gid, vpart, scalars, gscalars, state, counters, send, recv, err, normals, lnu, E, V, T, A;
+    // fused tile evaluation (big_tile.cuh): tile grid over the local rows, per-tile star lists, per-star footprint partials
+    BBuf tcnt, tbegin, tcursor, tlist, gpart;
+    BBuf epart, tickets;  // per-block energy partials; last-block tickets [0] energy, [1] tile potential
+    int nty = 0, ntx = 0;
+    bool use_tiles = false;
     int world = 1, rank = 0;
     bool have_data = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -515,13 +548,34 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     P.F.alpha = cfg->alpha; P.F.Vpc = cfg->V_prior_const;
     const size_t npix = (size_t)cfg->nrows * cfg->cols, S = 3 * (size_t)cfg->max_stars;
     const size_t list = 1 + 3 * (size_t)std::max(1, cfg->max_ghosts);
+    b->nty = (cfg->nrows + kTile - 1) / kTile;
+    b->ntx = (cfg->cols + kTile - 1) / kTile;
+    const size_t ntiles = (size_t)b->nty * b->ntx;
+    // Path of the EVAL phases: the fused tile kernel needs enough tiles to fill the GPU; small dense fields keep the
+    // star-parallel scatter/gather kernels.  SRHMC_BIG_PATH=tile|scatter overrides (read when the context is created).
+    b->use_tiles = ntiles >= 2 * (size_t)b->sm_count;
+    if (const char* e = std::getenv("SRHMC_BIG_PATH")) {
+        if (!std::strcmp(e, "tile")) b->use_tiles = true;
+        else if (!std::strcmp(e, "scatter")) b->use_tiles = false;
+    }
     int rc = 0;
-    rc |= b->D.ensure(npix * 8); rc |= b->L.ensure(npix * 8);
+    rc |= b->D.ensure(npix * 8);
+    if (!b->use_tiles) rc |= b->L.ensure(npix * 8);
+    if (b->use_tiles) {
+        const size_t sources = (size_t)cfg->max_stars + 2 * (size_t)std::max(1, cfg->max_ghosts);
+        rc |= b->tcnt.ensure(ntiles * 4); rc |= b->tbegin.ensure(ntiles * 4); rc |= b->tcursor.ensure(ntiles * 4);
+        rc |= b->tlist.ensure(4 * sources * 8); rc |= b->gpart.ensure(12 * (size_t)cfg->max_stars * 8);
+        if (!rc) cudaMemset(b->tcnt.ptr, 0, ntiles * 4);
+        if (!rc && (cudaFuncSetAttribute(big_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess ||
+                    cudaFuncSetAttribute(big_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess))
+            rc = 1;
+    }
     rc |= b->q.ensure(S * 8); rc |= b->p.ensure(S * 8); rc |= b->g.ensure(S * 8);
     rc |= b->a1.ensure(S * 8); rc |= b->a2.ensure(S * 8 + (size_t)cfg->max_stars * 4 + 8);
     rc |= b->q0.ensure(S * 8); rc |= b->g0.ensure(S * 8); rc |= b->gid.ensure((size_t)cfg->max_stars * 8);
-    rc |= b->vpart.ensure(kVBlocks * 8); rc |= b->scalars.ensure(kScalars * 8); rc |= b->gscalars.ensure(kScalars * 8); rc |= b->state.ensure(8 * 8);
+    rc |= b->vpart.ensure(std::max<size_t>(kVBlocks, ntiles) * 8); rc |= b->scalars.ensure(kScalars * 8); rc |= b->gscalars.ensure(kScalars * 8); rc |= b->state.ensure(8 * 8);
     rc |= b->counters.ensure(4 * 4); rc |= b->err.ensure(4);
+    rc |= b->epart.ensure(kEnergyBlocks * 4 * 8); rc |= b->tickets.ensure(2 * 4);
     rc |= b->send.ensure(2 * list * 8); rc |= b->recv.ensure((size_t)cfg->world_size * 2 * list * 8);
     if (rc) { srhmc_big_destroy(b); return SRHMC_ERR_CUDA; }
     cudaMemset(b->scalars.ptr, 0, kScalars * 8);
@@ -529,6 +583,7 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     cudaMemset(b->state.ptr, 0, 64);
     cudaMemset(b->counters.ptr, 0, 16);
     cudaMemset(b->err.ptr, 0, 4);
+    cudaMemset(b->tickets.ptr, 0, 8);
     cudaMemset(b->send.ptr, 0, 2 * list * 8);
     cudaMemset(b->recv.ptr, 0, (size_t)cfg->world_size * 2 * list * 8);
     if (cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -546,7 +601,8 @@ int srhmc_big_destroy(srhmc_big* b) {
     cudaSetDevice(b->cfg.device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
-                   &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A};
+                   &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A,
+                   &b->tcnt, &b->tbegin, &b->tcursor, &b->tlist, &b->gpart, &b->epart, &b->tickets};
     for (BBuf* x : all) x->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -724,10 +780,31 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
         case SRHMC_BIG_EVAL:
         case SRHMC_BIG_EVAL_V: {
             const int want_V = phase == SRHMC_BIG_EVAL_V;
-            const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
-            big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
             const double* ga = (b->world > 1 && b->rank > 0) ? b->recv.as<double>() + ((size_t)(b->rank - 1) * 2 + 1) * list : nullptr;
             const double* gb = (b->world > 1 && b->rank < b->world - 1) ? b->recv.as<double>() + ((size_t)(b->rank + 1) * 2 + 0) * list : nullptr;
+            if (b->use_tiles) {
+                TileSrc S;
+                S.q = b->q.as<double>(); S.ga = ga; S.gb = gb; S.n_own = n; S.cap = std::max(1, b->cfg.max_ghosts);
+                const int ntiles = b->nty * b->ntx;
+                const int sources = n + 2 * S.cap;
+                const int bg = std::max(1, std::min((sources + 255) / 256, 8 * b->sm_count));
+                big_bin_kernel<false><<<bg, 256, 0, st>>>(P, S, b->ntx, b->tcnt.as<int>(), nullptr, b->err.as<int>());
+                big_bin_scan_kernel<<<1, 1024, 0, st>>>(ntiles, b->tcnt.as<int>(), b->tbegin.as<int>(), b->tcursor.as<int>());
+                big_bin_kernel<true><<<bg, 256, 0, st>>>(P, S, b->ntx, b->tcursor.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                if (want_V)
+                    big_tile_kernel<true><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tbegin.as<int>(),
+                        b->tcursor.as<int>(), b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), b->err.as<int>());
+                else
+                    big_tile_kernel<false><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tbegin.as<int>(),
+                        b->tcursor.as<int>(), b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), b->err.as<int>());
+                big_gsum_kernel<<<gs, tb, 0, st>>>(P, b->q.as<double>(), n, b->gpart.as<double>(), b->g.as<double>());
+                b->launches += 5;
+                break;
+            }
+            const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
+            big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
             const int total = n + 2 * std::max(1, b->cfg.max_ghosts);
             const int sg = std::max(1, std::min((total * 32 + 255) / 256, 16 * b->sm_count));
             big_scatter_kernel<<<sg, 256, 0, st>>>(P, b->q.as<double>(), n, ga, gb, b->L.as<double>(), b->err.as<int>());
@@ -770,8 +847,9 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             break;
         }
         case SRHMC_BIG_ENERGY:
-            big_energy_kernel<<<1, 512, 0, st>>>(P, s->g_ff2, s->f_pos, n, b->q.as<double>(), b->p.as<double>(),
-                                                 b->scalars.as<double>());
+            big_energy_kernel<<<std::max(1, std::min((n + 255) / 256, kEnergyBlocks)), 256, 0, st>>>(
+                P, s->g_ff2, s->f_pos, n, b->q.as<double>(), b->p.as<double>(), b->epart.as<double>(),
+                b->tickets.as<unsigned int>(), b->scalars.as<double>());
             b->launches += 1;
             break;
         case SRHMC_BIG_RECORD_E0:

@@ -456,10 +456,12 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
     const int fb = A.field_begin, fe = A.field_end > 0 ? A.field_end : A.n_fields;
     const int G = (fe - fb + GPW - 1) / GPW;
     const int n_chunks = (MODE == MODE_RUN && A.n_chunks > 1) ? A.n_chunks : 1;
-    const long long n_tasks = (long long)G * n_chunks;
+    const int chunk_count = (MODE == MODE_RUN && A.chunk_count > 0) ? A.chunk_count : n_chunks;
+    const int chunk_begin = (MODE == MODE_RUN && A.chunk_count > 0) ? A.chunk_begin : 0;
+    const long long n_tasks = (long long)G * chunk_count;
     const long long gw = (long long)blockIdx.x * nw + warp, W = (long long)gridDim.x * nw;
     for (long long task = gw; task < n_tasks; task += W) {
-        const int chunk = (int)(task / G);
+        const int chunk = chunk_begin + (int)(task / G);
         const int base = fb + (int)(task % G) * GPW;
         const bool live = base + grp < fe;
         const int field = live ? base + grp : fe - 1;  // idle group shadows a valid chain, writes nothing

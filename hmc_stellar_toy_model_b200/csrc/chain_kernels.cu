@@ -135,6 +135,14 @@ int pick_chunks(long long groups, long long warps, int L) {
     return std::max(1, std::min(16, L / 32));
 }
 
+long long chain_kernel_resident_warps(const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, int n_fields) {
+    const int chains_per_block = plan.nw * (32 / plan.lpc);
+    const long long blocks = ((long long)n_fields + chains_per_block - 1) / chains_per_block;
+    const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
+    const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
+    return std::min<long long>(blocks, (long long)max_k * sms) * plan.nw;
+}
+
 int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const ChainLaunchPlan& plan, int sms, cudaStream_t stream) {
     LaunchArgs A = A_in;
     const int chains_per_block = plan.nw * (32 / plan.lpc);
@@ -145,8 +153,11 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     // 16 warps 1057 M star-steps/s, 112 / 18 warps 892, 104 / 19 warps 843 against 1104 at 168 / 12.
     const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
     int grid = balanced_grid(max_k, blocks, sms);
-    A.n_chunks = 1;
-    if (A.mode == MODE_RUN && A.sched_done != nullptr) {
+    if (!(A.mode == MODE_RUN && A.sched_done != nullptr && A.chunk_count > 0)) A.n_chunks = 1;
+    if (A.mode == MODE_RUN && A.sched_done != nullptr && A.chunk_count > 0) {
+        // one launch of a run that the host has cut along the iteration axis: the chunking is fixed by the caller
+        grid = (int)std::min<long long>(blocks, (long long)max_k * sms);
+    } else if (A.mode == MODE_RUN && A.sched_done != nullptr) {
         // with the chunked scheduler a partly filled last round costs little, so run at full residency
         const int full = (int)std::min<long long>(blocks, (long long)max_k * sms);
         const int chunks = pick_chunks(blocks, (long long)full * plan.nw, A.niter + 1);

@@ -111,7 +111,8 @@ struct LaunchArgs {
     int* fp_counts;         // [F,2]
     // chain-kernel work scheduler (MODE_RUN): iteration chunks per chain, per-group completion counters [ceil(F/4)],
     // travelling chain state [F,8], error word
-    int n_chunks;
+    int n_chunks;            // iteration chunks per chain over the whole run
+    int chunk_begin, chunk_count;  // chunks [chunk_begin, chunk_begin + chunk_count) are done by THIS launch (0, 0 = all)
     int* sched_done;
     double* sched_state;
     int* sched_err;

@@ -62,6 +62,8 @@ struct KernelChoice {
     int mr, mc;
 };
 
+constexpr int kMaxParts = 8;  // launches a pipelined run is cut into at most
+
 }  // namespace
 
 struct srhmc_ctx {
@@ -69,8 +71,9 @@ struct srhmc_ctx {
     FieldParams P;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaStream_t slice_streams[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t slice_done[4] = {nullptr, nullptr, nullptr, nullptr}, slice_go = nullptr;
+    // pipelined run (run_pipelined): copy stream, per-part completion events
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t part_done[kMaxParts] = {}, copies_done = nullptr;
     bool have_data = false, timed = false;
     int64_t launches = 0;
     int sm_count = 0;
@@ -352,11 +355,10 @@ int srhmc_destroy(srhmc_ctx* c) {
     for (DevBuf* b : all) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (int s = 0; s < 4; ++s) {
-        if (c->slice_done[s]) cudaEventDestroy(c->slice_done[s]);
-        if (c->slice_streams[s]) cudaStreamDestroy(c->slice_streams[s]);
-    }
-    if (c->slice_go) cudaEventDestroy(c->slice_go);
+    for (int s = 0; s < kMaxParts; ++s)
+        if (c->part_done[s]) cudaEventDestroy(c->part_done[s]);
+    if (c->copies_done) cudaEventDestroy(c->copies_done);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -698,21 +700,22 @@ int srhmc_run_download(srhmc_ctx* c, const srhmc_run_args* a) {
     return 0;
 }
 
-// Large one-star batches: the batch is cut into kSlices field ranges, each with its own stream, so the device-to-host
-// copy of a finished slice's chains overlaps the kernels of the others (the chain rows are ~70 B per iteration per
-// chain: 0.8 GB for the headline workload, 13% of the launch time when copied afterwards).
-static int run_sliced(srhmc_ctx* c, const srhmc_run_args* a) {
-    constexpr int kSlices = 4;
+// Large one-star batches: the run is cut along the ITERATION axis into kParts launches on the compute stream, and the
+// chain rows a finished part produced travel device-to-host (one strided 2-D copy per output array, on a second
+// stream) while the next part computes.  The chain rows are ~73 B per iteration per chain: 0.8 GB for the headline
+// workload, 14.7 ms at the 55 GB/s of the link when copied after a 91.5 ms launch.  (Cutting the batch along the
+// CHAIN axis instead was measured slower than no overlap at all -- 136.6 vs 106.0 ms: four concurrent part-filled
+// grids defeat the chain kernel's work scheduler.)
+static int run_pipelined(srhmc_ctx* c, const srhmc_run_args* a, int n_parts) {
     if (int rc = srhmc_run_upload(c, a)) return rc;
     LaunchArgs A;
     if (int rc = build_run_launch_args(c, a, A)) return rc;
     const size_t F = c->cfg.n_fields, S = 3 * (size_t)c->cfg.max_stars, rows = (size_t)c->run_rows;
-    if (!c->slice_streams[0]) {
-        for (int s = 0; s < kSlices; ++s) {
-            CU_TRY(cudaStreamCreateWithFlags(&c->slice_streams[s], cudaStreamNonBlocking));
-            CU_TRY(cudaEventCreateWithFlags(&c->slice_done[s], cudaEventDisableTiming));
-        }
-        CU_TRY(cudaEventCreateWithFlags(&c->slice_go, cudaEventDisableTiming));
+    const int L = a->niter + 1;
+    if (!c->copy_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < kMaxParts; ++s) CU_TRY(cudaEventCreateWithFlags(&c->part_done[s], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
     }
     const size_t groups = (F + kChainGroup - 1) / kChainGroup;
     if (int rc = c->sched_done.ensure(groups * sizeof(int))) return rc;
@@ -724,38 +727,47 @@ static int run_sliced(srhmc_ctx* c, const srhmc_run_args* a) {
     A.sched_state = c->sched_state.as<double>();
     A.sched_err = c->sched_err.as<int>();
     c->sched_used = true;
-    if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
-    CU_TRY(cudaEventRecord(c->slice_go, c->stream));
-    const size_t per = ((F + kSlices - 1) / kSlices + kChainGroup - 1) / kChainGroup * kChainGroup;
-    for (int s = 0; s < kSlices; ++s) {
-        const size_t f0 = std::min(F, (size_t)s * per), f1 = std::min(F, f0 + per), nf = f1 - f0;
-        cudaStream_t st = c->slice_streams[s];
-        CU_TRY(cudaStreamWaitEvent(st, c->slice_go, 0));
-        if (nf > 0) {
-            A.field_begin = (int)f0;
-            A.field_end = (int)f1;
-            const int rc = chain_kernel_launch(c->P, A, c->chain_plan, c->sm_count, st);
-            if (rc != 0) return fail(SRHMC_ERR_CUDA, "chain kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-            c->launches += 1;
-            auto d2h = [&](void* dst, const DevBuf& b, size_t elem_bytes) -> int {
-                if (!dst || elem_bytes == 0) return 0;
-                CU_TRY(cudaMemcpyAsync((char*)dst + f0 * elem_bytes, (const char*)b.ptr + f0 * elem_bytes, nf * elem_bytes,
-                                       cudaMemcpyDeviceToHost, st));
-                return 0;
-            };
-            if (int rc2 = d2h(a->q_chain, c->qchain, rows * S * 8)) return rc2;
-            if (int rc2 = d2h(a->p_chain, c->pchain, rows * S * 8)) return rc2;
-            if (int rc2 = d2h(a->E_chain, c->E, rows * 8)) return rc2;
-            if (int rc2 = d2h(a->V_chain, c->V, rows * 8)) return rc2;
-            if (int rc2 = d2h(a->T_chain, c->T, rows * 8)) return rc2;
-            if (int rc2 = d2h(a->A_chain, c->A, rows)) return rc2;
-            if (int rc2 = d2h(a->q_final, c->qout, S * 8)) return rc2;
-            if (int rc2 = d2h(a->accept_rate, c->acc, 8)) return rc2;
-        }
-        CU_TRY(cudaEventRecord(c->slice_done[s], st));
+    // iteration chunks per part: the part's (group, chunk) work items should fill whole rounds of the resident warps
+    const long long W = std::max<long long>(1, chain_kernel_resident_warps(A, c->chain_plan, c->sm_count, (int)F));
+    int cpp = 1;
+    double best = -1.0;
+    for (int k = 1; k <= 8; ++k) {
+        if ((long long)L < 16LL * k * n_parts) break;
+        const long long tasks = (long long)groups * k, rounds = (tasks + W - 1) / W;
+        const double eff = (double)tasks / (double)(rounds * W);
+        if (eff > best + 0.01) { best = eff; cpp = k; }
     }
-    for (int s = 0; s < kSlices; ++s) CU_TRY(cudaStreamWaitEvent(c->stream, c->slice_done[s], 0));
+    A.n_chunks = n_parts * cpp;
+    const int Lc = (L + A.n_chunks - 1) / A.n_chunks;  // the kernel's chunk length
+    if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    for (int part = 0; part < n_parts; ++part) {
+        A.chunk_begin = part * cpp;
+        A.chunk_count = cpp;
+        const int rc = chain_kernel_launch(c->P, A, c->chain_plan, c->sm_count, c->stream);
+        if (rc != 0) return fail(SRHMC_ERR_CUDA, "chain kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+        CU_TRY(cudaEventRecord(c->part_done[part], c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->part_done[part], 0));
+        const size_t r0 = std::min<size_t>((size_t)part * cpp * Lc, rows), r1 = std::min<size_t>(r0 + (size_t)cpp * Lc, rows);
+        auto d2h_rows = [&](void* dst, const DevBuf& b, size_t row_bytes) -> int {
+            if (!dst || row_bytes == 0 || r1 <= r0) return 0;
+            CU_TRY(cudaMemcpy2DAsync((char*)dst + r0 * row_bytes, rows * row_bytes, (const char*)b.ptr + r0 * row_bytes,
+                                     rows * row_bytes, (r1 - r0) * row_bytes, F, cudaMemcpyDeviceToHost, c->copy_stream));
+            return 0;
+        };
+        if (int rc2 = d2h_rows(a->q_chain, c->qchain, S * 8)) return rc2;
+        if (int rc2 = d2h_rows(a->p_chain, c->pchain, S * 8)) return rc2;
+        if (int rc2 = d2h_rows(a->E_chain, c->E, 8)) return rc2;
+        if (int rc2 = d2h_rows(a->V_chain, c->V, 8)) return rc2;
+        if (int rc2 = d2h_rows(a->T_chain, c->T, 8)) return rc2;
+    }
     if (c->timed) CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    // byte-wide rows and the per-chain results go in one piece after the last part
+    if (a->A_chain) CU_TRY(cudaMemcpyAsync(a->A_chain, c->A.ptr, F * rows, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (a->q_final && S) CU_TRY(cudaMemcpyAsync(a->q_final, c->qout.ptr, F * S * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (a->accept_rate) CU_TRY(cudaMemcpyAsync(a->accept_rate, c->acc.ptr, F * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU_TRY(cudaEventRecord(c->copies_done, c->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->copies_done, 0));
     int sched_err = 0;
     CU_TRY(cudaMemcpyAsync(&sched_err, c->sched_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -764,8 +776,12 @@ static int run_sliced(srhmc_ctx* c, const srhmc_run_args* a) {
 }
 
 int srhmc_run(srhmc_ctx* c, const srhmc_run_args* a) {
-    if (c && a && c->chain_ok && c->cfg.n_fields >= 4096 && all_one_star(c, a->nstars) && !std::getenv("SRHMC_NO_SLICED_RUN"))
-        return run_sliced(c, a);
+    if (c && a && c->chain_ok && c->cfg.n_fields >= 4096 && a->niter + 1 >= 256 && a->chain_stride == 1 &&
+        all_one_star(c, a->nstars)) {
+        int parts = 8;  // measured on the headline batch: 1 part 106.0 ms, 2: 102.6, 4: 98.9, 8: 97.6 (kernel alone 91.7)
+        if (const char* e = std::getenv("SRHMC_RUN_PARTS")) parts = std::max(1, std::min(kMaxParts, std::atoi(e)));
+        if (parts > 1) return run_pipelined(c, a, parts);
+    }
     if (int rc = srhmc_run_upload(c, a)) return rc;
     if (int rc = srhmc_run_launch(c, a)) return rc;
     return srhmc_run_download(c, a);

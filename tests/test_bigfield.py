@@ -160,9 +160,11 @@ def _grad_close(a, b, tol):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 2])
-def test_bigfield_eval_matches_reference_values(world):
+@pytest.mark.parametrize("path", ["scatter", "tile"])
+def test_bigfield_eval_matches_reference_values(world, path, monkeypatch):
     """204 stars on 64x64 (golden from the reference): V and dV/dq through the scatter / pixel / gather kernels,
     untiled and tiled into 2 strips on one device."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
     g = golden("field_eval_204")
     S = setup_from(g)
     eng = _engine(S, g["q"], world=world, halo=14)
@@ -178,9 +180,11 @@ def test_bigfield_eval_matches_reference_values(world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 2])
-def test_bigfield_steps_match_cta_kernel(world):
+@pytest.mark.parametrize("path", ["scatter", "tile"])
+def test_bigfield_steps_match_cta_kernel(world, path, monkeypatch):
     """Three leapfrog steps of the 204-star field: same q, p as the CTA-resident kernel (which is parity-checked
     against the reference), including the field-wide stop rule of the fixed-point loops via the two-phase scheme."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
     from test_gpu_parity import make_ctx
 
     g = golden("field_eval_204")
@@ -206,9 +210,11 @@ def test_bigfield_steps_match_cta_kernel(world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1])
-def test_bigfield_chain_matches_reference_chain(world):
+@pytest.mark.parametrize("path", ["scatter", "tile"])
+def test_bigfield_chain_matches_reference_chain(world, path, monkeypatch):
     """RHMC-big-sim3-like chain (100 stars, prior, g_ff2 schedule) recorded from the reference: accept decisions and
     energies from the large-field engine with the reference's draws injected."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
     g = golden("chain_multi100")
     S = setup_from(g)
     q0 = so.format_q(S, g["q_model"])
@@ -222,9 +228,11 @@ def test_bigfield_chain_matches_reference_chain(world):
 
 
 @pytest.mark.gpu
-def test_bigfield_philox_chain_tiled_equals_untiled():
+@pytest.mark.parametrize("path", ["scatter", "tile"])
+def test_bigfield_philox_chain_tiled_equals_untiled(path, monkeypatch):
     """Device-RNG chain on a 256x96 field with 700 stars: a 4-strip tiling reproduces the untiled run (same accept
     decisions, energies to 1e-10) because the draws are keyed by global star id."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
     S = so.Setup(num_rows=256, num_cols=96, g_xx=0.05, g_ff=4.0, g_ff2=4.0, use_prior=True, alpha=2.0, V_prior_const=1.0)
     rng = np.random.RandomState(3)
     n = 700
@@ -246,3 +254,56 @@ def test_bigfield_philox_chain_tiled_equals_untiled():
     assert np.array_equal(a[0]["A_chain"], b[0]["A_chain"]) and 0 < a[0]["A_chain"].sum()
     assert relerr(b[0]["E_chain"], a[0]["E_chain"]) < 1e-10
     assert relerr(b[1], a[1]) < 1e-9
+
+
+def _synthetic_field(rows, cols, n, seed):
+    S = so.Setup(num_rows=rows, num_cols=cols, g_xx=0.05, g_ff=4.0, g_ff2=4.0, use_prior=True, alpha=2.0, V_prior_const=1.0)
+    rng = np.random.RandomState(seed)
+    fl = S.mag2flux_converter(rng.uniform(15.5, 20.0, n))
+    q = np.stack([fl, rng.uniform(1, rows - 1, n), rng.uniform(1, cols - 1, n)], axis=1)
+    # a few stars hugging the edges and corners: clipped patches, edge tiles
+    q[:4, 1:] = [[0.2, 0.3], [rows - 0.4, cols - 0.2], [0.7, cols - 0.6], [rows - 0.3, 0.9]]
+    sig = S.PSF_FWHM_pix / 2.354
+    ci, cj = np.arange(0.5, rows), np.arange(0.5, cols)
+    ex = np.exp(-((ci[None] - q[:, 1:2]) ** 2) / (2 * sig ** 2))
+    ey = np.exp(-((cj[None] - q[:, 2:3]) ** 2) / (2 * sig ** 2)) / (2 * np.pi * sig ** 2)
+    lam = S.B_count + np.einsum("k,ki,kj->ij", q[:, 0], ex, ey)
+    D = rng.poisson(lam).astype(float)
+    q0 = q * np.array([1.03, 1.0, 1.0]) + np.array([0.0, 0.05, -0.05])
+    return S, D, q0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,world", [(200, 330, 1), (333, 321, 1), (333, 321, 3)])
+def test_bigfield_tile_kernel_equals_star_parallel_kernels(rows, cols, world, monkeypatch):
+    """The fused tile evaluation (one CTA per 64x64 tile, D read once) against the scatter / pixel / gather kernels on
+    fields whose edges cut tiles (odd column count: unaligned row starts), untiled and as 3 strips: V and dV/dq to
+    1e-12, and the tile path bit-identical run to run (no floating-point atomics)."""
+    S, D, q0 = _synthetic_field(rows, cols, 900, 5)
+    res = {}
+    for path in ("scatter", "tile", "tile2"):
+        monkeypatch.setenv("SRHMC_BIG_PATH", path[:4] if path.startswith("tile") else path)
+        eng = _engine(S, q0.ravel(), world=world, D=D, halo=20)
+        eng.evaluate(want_V=True, g_ff2=4.0)
+        res[path] = (eng.energies()[0], eng.stars(900)[2])
+    assert relerr(res["tile"][0], res["scatter"][0]) < 1e-13
+    assert _grad_close(res["tile"][1], res["scatter"][1], 1e-11)
+    assert res["tile"][0] == res["tile2"][0] and np.array_equal(res["tile"][1], res["tile2"][1])
+
+
+@pytest.mark.gpu
+def test_bigfield_tile_kernel_dense_list_chunks_and_auto_path(monkeypatch):
+    """1600x1600 field (625 tiles > 2 x SM count: the tile path is chosen automatically) and a clump of 300 stars in
+    one tile (38 table chunks): V and dV/dq against the NumPy oracle restatement with the same patch truncation."""
+    monkeypatch.delenv("SRHMC_BIG_PATH", raising=False)
+    S, D, q0 = _synthetic_field(1600, 1600, 2000, 9)
+    rng = np.random.RandomState(2)
+    q0[100:400, 1] = rng.uniform(700, 760, 300)
+    q0[100:400, 2] = rng.uniform(900, 960, 300)
+    eng = _engine(S, q0.ravel(), world=1, D=D, halo=20)
+    eng.evaluate(want_V=True, g_ff2=4.0)
+    V = eng.energies()[0]
+    grad = eng.stars(2000)[2]
+    Vo, go = so.patch_eval(S, D, q0, rad=12)
+    assert relerr(V, Vo) < 1e-12
+    assert _grad_close(grad, go, 1e-10)

@@ -214,3 +214,16 @@ def test_oracle_single_star_background_matches_reference():
     L = so.LightSetup(num_rows=32, num_cols=32, D=g["D"])
     V, grad = so.ls_single(L, g["q0"], g["model_data"])
     assert relerr(V, g["V_single"]) < 1e-14 and relerr(grad, g["dVdq_single"]) < 1e-12
+
+
+def test_patch_limited_restatement_matches_full_image_reference_values():
+    """patch_eval (PSF truncated to 25x25 pixels: what the large-field engine computes) against the reference's
+    full-image V and dV/dq recorded for the 204-star 64x64 field."""
+    g = golden("field_eval_204")
+    S = setup_from(g)
+    V, grad = so.patch_eval(S, S.D, g["q"].reshape(-1, 3), rad=12)
+    gref = g["dVdq"].reshape(-1, 3).copy()
+    gref[:, 0] -= S.alpha / g["q"].reshape(-1, 3)[:, 0]  # the recorded gradient includes the prior term
+    assert relerr(V, g["V"]) < 1e-13
+    scale = np.maximum(np.abs(gref), 1e-3 * np.max(np.abs(gref), axis=0, keepdims=True))
+    assert np.max(np.abs(grad - gref) / scale) < 1e-10

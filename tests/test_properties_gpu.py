@@ -79,3 +79,27 @@ def test_leapfrog_is_time_reversible_at_full_batch():
     err = np.abs(q2 - wl["q0"]) / np.abs(wl["q0"])
     assert np.max(err) < 1e-8, np.max(err)
     assert np.max(np.abs(p2 + p0) / (np.abs(p0) + 1e-3)) < 1e-6
+
+
+@pytest.mark.parametrize("parts", [2, 4, 7])
+def test_pipelined_run_is_bit_identical_to_one_launch(parts, monkeypatch):
+    """srhmc_run cuts a large one-star batch along the iteration axis into several launches whose chain rows are
+    copied to the host while the next part computes (strided 2-D copies): every output array must equal the
+    single-launch run bit for bit, for part counts that do and do not divide the chain length."""
+    from hmc_stellar_toy_model_b200 import RHMCContext
+
+    wl = _bench_module().workload_c2(400, 8)   # 4400 chains: above the 4096-chain threshold of the pipelined path
+    niter = 300
+    res = []
+    for p in (1, parts):
+        monkeypatch.setenv("SRHMC_RUN_PARTS", str(p))
+        with RHMCContext(**wl["cfg"]) as ctx:
+            ctx.set_data(wl["D"])
+            launches0 = ctx.launch_count
+            r = ctx.run(wl["q0"], niter, seed=9, **wl["run"])
+            res.append((r, ctx.launch_count - launches0))
+    (a, la), (b, lb) = res
+    assert la == 1 and lb == parts
+    for name in ("q_chain", "p_chain", "E_chain", "V_chain", "T_chain", "A_chain", "q_final", "accept_rate"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert 0.5 < a.accept_rate.mean() < 1.0 and np.all(np.isfinite(a.E_chain))
