@@ -120,12 +120,12 @@ __device__ __forceinline__ double log1p_small(double t) {
 
 // Image rows [r0, r1), all column slots of the lane (columns sub + LPC c): gradient column sums and, per TIER, the
 // D * log1p(t) part of the potential.  TIER 0: table logarithm; 1: 7-term series (|t| < 2^-7).
-template <int TIER, int LPC, typename DT>
+template <int TIER, int LPC, int NCS, typename DT>
 __device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restrict__ sDl, const double2* __restrict__ rt,
-                                               const double2* __restrict__ ltab, double B, const double (&fey)[32 / LPC],
-                                               const double (&tb)[32 / LPC], double (&c0)[32 / LPC],
-                                               double (&c1)[32 / LPC], double& vlog, int& bad) {
-    constexpr int CPL = 32 / LPC;
+                                               const double2* __restrict__ ltab, double B, const double (&fey)[NCS],
+                                               const double (&tb)[NCS], double (&c0)[NCS],
+                                               double (&c1)[NCS], double& vlog, int& bad) {
+    constexpr int CPL = NCS;
     for (int i = r0; i < r1; ++i) {
         const double2 re = rt[i];
 #pragma unroll
@@ -173,10 +173,11 @@ __device__ __forceinline__ void row_window(float xc, float peak, float thresh, f
 // warp sees there (see rows_all_slots).  Code size matters here: a build that unrolled per-slot tier loops grew the
 // kernel to 30k instructions and spent 31% of its issue slots waiting for instruction fetch, so the kernel is
 // specialised per mode (template MODE) and the tier loops are kept compact.  `vconst` is the bracketed constant of this chain's image.
-template <int LPC, bool WANT_V, typename DT>
+template <int LPC, int NCS, bool WANT_V, typename DT>
 __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
                                            const double2* __restrict__ ltab, int sub, double vconst, ChainState& s) {
-    constexpr int CPL = 32 / LPC;
+    constexpr int CPL = NCS;            // column slots per lane
+    constexpr int WIN = NCS * LPC;      // columns the chain's lanes cover
     constexpr unsigned FULL = 0xffffffffu;
     const int R = P.R, C = P.C;
     const double f = s.f, x = s.x, y = s.y;
@@ -189,7 +190,13 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     const double kf = fmin(fmax(rint((x - 0.5 - (double)sub) * (1.0 / LPC)), 0.0), (double)(K > 0 ? K - 1 : 0));
     const int ks = (int)kf;
     const double us = ((double)(sub + LPC * ks) + 0.5) - x;
-    const double v0 = ((double)sub + 0.5) - y;
+    // column window: the WIN columns starting at the first one within WIN/2 pixels of the star (kept inside the image)
+    int jb = sub;
+    if (WIN < kChainCS) {
+        const double a = ceil(y - (0.5 + 0.5 * WIN));
+        jb += (int)fmin(fmax(a, 0.0), (double)max(C - WIN, 0));
+    }
+    const double v0 = ((double)jb + 0.5) - y;
     const double arg_r = (us * us) * P.inv2s2, arg_c = (v0 * v0) * P.inv2s2;
     const bool ok_r = arg_r < 690.0, ok_c = arg_c < 690.0;
     const double LL = (double)(LPC * LPC);
@@ -229,7 +236,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
         double r = ok_c ? r_c : 0.0;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-            const bool in = sub + LPC * c < C;
+            const bool in = jb + LPC * c < C;
             ey[c] = in ? e : 0.0;
             fey[c] = f * ey[c];
             eydy[c] = ey[c] * v;
@@ -267,7 +274,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const double lam = fma(re.x, fey[c], P.B);
-                const double d = ld_pix(sD + i * kChainCS + sub + LPC * c);
+                const double d = ld_pix(sD + i * kChainCS + jb + LPC * c);
                 const double rho = fma(d, rcp_pix(lam), -1.0);
                 c0[c] = fma(rho, re.x, c0[c]);
                 c1[c] = fma(rho, re.y, c1[c]);
@@ -288,9 +295,9 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
         n1 = __reduce_max_sync(FULL, n1);
         n0 = min(max(n0, i_lo), i_hi);
         n1 = min(max(n1, n0), i_hi);
-        rows_all_slots<1, LPC>(i_lo, n0, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
-        rows_all_slots<0, LPC>(n0, n1, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
-        rows_all_slots<1, LPC>(n1, i_hi, sD + sub, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<1, LPC, NCS>(i_lo, n0, sD + jb, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<0, LPC, NCS>(n0, n1, sD + jb, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
+        rows_all_slots<1, LPC, NCS>(n1, i_hi, sD + jb, rt, ltab, P.B, fey, tb, c0, c1, vlog, bad);
     }
     __syncwarp();  // row table is rewritten by the next evaluation
     double sf = 0.0, sx = 0.0, sy = 0.0;
@@ -358,7 +365,7 @@ __device__ __forceinline__ void chain_energies(const FieldParams& P, const Chain
 
 // base_class.RHMC_single_step for a one-star field, state in registers (sampler_RHMC.py:522-566).
 // Requires s.g*, s.u, s.kap, s.ihxx, s.tphi valid at s.f on entry; leaves them valid on exit.
-template <int LPC, typename DT>
+template <int LPC, int NCS, typename DT>
 __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const DT* sD, double2* rt,
                                            const double2* ltab, int sub, double vconst, ChainState& s, int counter_max,
                                            bool want_V, int& cnt_p, int& cnt_q) {
@@ -413,9 +420,9 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     s.pf = fma(-(K.hh * s.kap), s.pf * s.pf, s.pf);
     // (5) gradient at the new q and last half kick
     if (want_V)
-        chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+        chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
     else
-        chain_eval<LPC, false>(P, sD, rt, ltab, sub, vconst, s);
+        chain_eval<LPC, NCS, false>(P, sD, rt, ltab, sub, vconst, s);
     {
         double gf = s.gf + s.tphi;
         if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
@@ -432,7 +439,7 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
 #ifndef SRHMC_CHAIN_MAXREG
 #define SRHMC_CHAIN_MAXREG (LPC <= 4 ? 232 : 168)
 #endif
-template <int LPC, typename DT, int MODE, int MAXREG = SRHMC_CHAIN_MAXREG>
+template <int LPC, typename DT, int MODE, int NCS, int MAXREG = SRHMC_CHAIN_MAXREG>
 __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
@@ -495,7 +502,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
         int cp = 0, cq = 0;
 
         if (MODE == MODE_EVAL) {
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V, T;
             chain_energies(P, K, s, A.f_pos, ltab, V, T);
@@ -512,9 +519,9 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
         } else if (MODE == MODE_STEP) {
-            chain_eval<LPC, false>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, false>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
-            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
@@ -523,7 +530,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             }
         } else if (MODE == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
-            chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V0, T0;
             chain_energies(P, K, s, A.f_pos, ltab, V0, T0);
@@ -534,7 +541,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
             }
             for (int t = 1; t <= A.nsteps; ++t) {
-                chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
+                chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
                 double V, T;
                 chain_energies(P, K, s, A.f_pos, ltab, V, T);
                 if (writer) {
@@ -555,7 +562,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             const int grp_id = base / GPW;
             int n_acc = 0;
             if (chunk == 0) {
-                chain_eval<LPC, true>(P, sD, rt, ltab, sub, vconst, s);
+                chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
             } else {
                 // wait until the previous chunk of this group has published its state (bounded spin: a scheduler
                 // fault must not hang the device)
@@ -610,7 +617,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                     if (A.T_chain) A.T_chain[row] = T0;
                 }
                 for (int t = 0; t < A.nsteps; ++t)
-                    chain_step<LPC>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
+                    chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, ltab, V1, T1);
                 const double dE = (V1 + T1) - E0;

@@ -12,6 +12,23 @@ namespace {
 
 constexpr int kLPC = kChainLPC;  // lanes per chain: 8 -> 4 chains per warp (measured faster than 16 lanes / 2 chains)
 constexpr int kWarpsPerBlock = 1;
+// Column slots per lane: the full 32-column image, or a 24-column window around the star when the PSF weight of
+// every dropped column is below 2^-46 of its peak (sigma <= 1.50 px: |dy| >= 12 px).  SRHMC_CHAIN_WINDOW=0 at run time
+// forces the full width (A/B measurements).
+constexpr int kSlotsFull = 32 / kLPC;
+#ifndef SRHMC_CHAIN_WIN_COLS
+#define SRHMC_CHAIN_WIN_COLS 24
+#endif
+constexpr int kWinCols = SRHMC_CHAIN_WIN_COLS;
+constexpr int kSlotsWin = (kWinCols % kLPC == 0 && kWinCols / kLPC < kSlotsFull) ? kWinCols / kLPC : kSlotsFull;
+
+bool use_column_window(const FieldParams& P) {
+    if (kSlotsWin == kSlotsFull) return false;
+    if (const char* env = std::getenv("SRHMC_CHAIN_WINDOW"))
+        if (std::atoi(env) == 0) return false;
+    const double half = 0.5 * kWinCols;
+    return half * half * P.inv2s2 >= 46.0 * M_LN2;
+}
 
 size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     const size_t gpw = 32 / lpc;
@@ -19,39 +36,53 @@ size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-template <typename DT, int MODE>
+template <typename DT, int MODE, int NCS>
 int configure_mode(size_t smem, int nw, int& blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE, NCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE, NCS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT, MODE>, 32 * nw, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT, MODE, NCS>, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
     blocks_per_sm = blocks_per_sm == 0 ? nb : std::min(blocks_per_sm, nb);
     return 0;
 }
 
+template <typename DT, int NCS>
+int configure_slots(size_t smem, int nw, int& blocks_per_sm) {
+    if (int rc = configure_mode<DT, MODE_EVAL, NCS>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_STEP, NCS>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_RUN, NCS>(smem, nw, blocks_per_sm)) return rc;
+    return configure_mode<DT, MODE_SINGLE, NCS>(smem, nw, blocks_per_sm);
+}
+
 template <typename DT>
 int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
     smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT));
     blocks_per_sm = 0;
-    if (int rc = configure_mode<DT, MODE_EVAL>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<DT, MODE_STEP>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<DT, MODE_RUN>(smem, nw, blocks_per_sm)) return rc;
-    return configure_mode<DT, MODE_SINGLE>(smem, nw, blocks_per_sm);
+    if (use_column_window(P)) return configure_slots<DT, kSlotsWin>(smem, nw, blocks_per_sm);
+    return configure_slots<DT, kSlotsFull>(smem, nw, blocks_per_sm);
+}
+
+template <typename DT, int NCS>
+void launch_slots(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
+    switch (A.mode) {
+        case MODE_EVAL: chain_kernel<kLPC, DT, MODE_EVAL, NCS><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_STEP: chain_kernel<kLPC, DT, MODE_STEP, NCS><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_SINGLE: chain_kernel<kLPC, DT, MODE_SINGLE, NCS><<<grid, threads, smem, stream>>>(P, A); break;
+        default: chain_kernel<kLPC, DT, MODE_RUN, NCS><<<grid, threads, smem, stream>>>(P, A); break;
+    }
 }
 
 template <typename DT>
 void launch_mode(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
-    switch (A.mode) {
-        case MODE_EVAL: chain_kernel<kLPC, DT, MODE_EVAL><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_STEP: chain_kernel<kLPC, DT, MODE_STEP><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_SINGLE: chain_kernel<kLPC, DT, MODE_SINGLE><<<grid, threads, smem, stream>>>(P, A); break;
-        default: chain_kernel<kLPC, DT, MODE_RUN><<<grid, threads, smem, stream>>>(P, A); break;
-    }
+    if (use_column_window(P))
+        launch_slots<DT, kSlotsWin>(grid, threads, smem, stream, P, A);
+    else
+        launch_slots<DT, kSlotsFull>(grid, threads, smem, stream, P, A);
 }
 
 // Grid = (blocks per SM) x SMs with the per-SM count chosen so that every SM runs the same number of equally long

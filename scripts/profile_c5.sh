@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu evidence for the large-field engine (run under gpurun, one GPU).  Usage: scripts/profile_c5.sh <tag> [bench args]
+set -u
+TAG=${1:-r1}; shift
+CMD="python bench.py --workload c5 --steps 2 --warmup 3 --e2e-steps 1 --niter 2 $*"
+$CMD > gpurun_out/c5_plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv --log-file gpurun_out/c5_launches_$TAG.csv $CMD > gpurun_out/c5_ncu_launches_$TAG.log 2>&1
+tail -2 gpurun_out/c5_plain_$TAG.log | cut -c1-300
