@@ -564,9 +564,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
-    ap.add_argument("--rows", type=int, default=2048, help="c5: image rows (per GPU with --weak)")
-    ap.add_argument("--cols", type=int, default=2048)
-    ap.add_argument("--stars", type=float, default=6250, help="c5: stars (per GPU with --weak); 1.49e-3 per pixel")
+    ap.add_argument("--rows", type=int, default=8192, help="c5: image rows (per GPU with --weak); BASELINE configs[4] is 8192 x 8192")
+    ap.add_argument("--cols", type=int, default=8192)
+    ap.add_argument("--stars", type=float, default=100000, help="c5: stars (per GPU with --weak); 1.49e-3 per pixel")
     ap.add_argument("--weak", action="store_true", help="c5: grow the field with the GPU count")
     ap.add_argument("--chains-per-mag", type=int, default=1000)
     ap.add_argument("--fields", type=int, default=592)

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRHMC_LIB") or os.path.join(_HERE, "libstellar_rhmc.so")  # SRHMC_LIB: experimental builds
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -162,6 +162,11 @@ SIGNATURES = {
     "srhmc_host_alloc": (C.c_void_p, [C.c_uint64]),
     "srhmc_host_free": (C.c_int, [C.c_void_p]),
     "srhmc_set_data": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
+    "srhmc_gen_model": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, c_double_p]),
+    "srhmc_gen_mock_data": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, C.c_uint64, C.c_int64, c_double_p]),
+    "srhmc_convergence_stats": (C.c_int, [C.c_int32, c_double_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, c_double_p, c_double_p]),
+    "srhmc_run_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "srhmc_eval": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_double,
                              c_double_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_metric": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_double, c_double_p, c_double_p]),
@@ -194,6 +199,7 @@ SIGNATURES = {
     "srhmc_big_synchronize": (C.c_int, [C.c_void_p]),
     "srhmc_big_launch_count": (C.c_int64, [C.c_void_p]),
     "srhmc_big_set_data": (C.c_int, [C.c_void_p, c_double_p]),
+    "srhmc_big_mock_data": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_uint64, c_double_p]),
     "srhmc_big_set_stars": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int32]),
     "srhmc_big_get_stars": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_big_set_momenta": (C.c_int, [C.c_void_p, c_double_p]),

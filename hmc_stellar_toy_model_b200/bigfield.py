@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import check_big as check
 
 PHASE = dict(PACK=0, EVAL=1, EVAL_V=2, KICK1=3, PFIX_QFIX=4, QFIX_KICK=5, KICK2=6, MOMENTUM=7, ENERGY=8, RECORD_E0=9,
-             ACCEPT=10, RESET_ITER=11)
+             ACCEPT=10, RESET_ITER=11, EVAL_KICK2=12, EVAL_V_KICK2=13, EVAL_KICK2_KICK1=14)
 
 
 # ----------------------------------------------------------------------------------------------- host-side geometry
@@ -131,6 +131,15 @@ class BigFieldStrip:
 
     def set_data(self, D_global):
         self.set_data_window(np.asarray(D_global)[self.row0:self.row0 + self.nrows])
+
+    def gen_mock_data(self, q_true, seed=0, return_data=False):
+        """Device-side gen_mock_data (sampler_RHMC.py:77-99) for this strip's data window.  q_true [N,3] (f, x, y) is the
+        truth list of the WHOLE field, the same on every rank; the Philox counter of a pixel is its global index, so the
+        halo rows of neighbouring strips (and an untiled run) get identical counts."""
+        q = np.ascontiguousarray(np.asarray(q_true, dtype=np.float64).reshape(-1, 3))
+        out = np.empty((self.nrows, self.cols)) if return_data else None
+        check(self._lib.srhmc_big_mock_data(self._h, _capi.dptr(q), len(q), int(seed), _capi.dptr(out)))
+        return out
 
     def set_stars(self, q_global):
         """Take the stars of the global list [N,3] (f, x, y) whose row coordinate falls in this strip."""
@@ -286,9 +295,9 @@ class BigFieldRHMC:
         if self.multi:
             self.comm.sum_scalars(self.strips)
 
-    def leapfrog(self, st, want_V):
-        """One RHMC_single_step (sampler_RHMC.py:522-566); needs the gradient at the current q."""
-        self._all("KICK1", st)
+    def _advance(self, st):
+        """Steps (2)-(4) of RHMC_single_step after the first half kick, up to the point where the gradient at the new
+        position is needed (ghost exchange included)."""
         if self.multi:
             self.comm.max_counters(self.strips)
         self._all("PFIX_QFIX", st)
@@ -298,8 +307,26 @@ class BigFieldRHMC:
         if self.multi:
             self._all("PACK", st)
             self.comm.gather_ghosts(self.strips)
-        self._all("EVAL_V" if want_V else "EVAL", st)
-        self._all("KICK2", st)
+
+    def leapfrog(self, st, want_V):
+        """One RHMC_single_step (sampler_RHMC.py:522-566); needs the gradient at the current q."""
+        self._all("KICK1", st)
+        self._advance(st)
+        self._all("EVAL_V_KICK2" if want_V else "EVAL_KICK2", st)
+
+    def trajectory(self, st, nsteps, want_V_last):
+        """nsteps leapfrog steps.  The last half kick of a step and the first half kick of the next one use the same
+        gradient, so inside the trajectory they ride in one fused phase behind the evaluation (EVAL_KICK2_KICK1):
+        four kernels per step on one GPU."""
+        if nsteps <= 0:
+            return
+        self._all("KICK1", st)
+        for t in range(nsteps):
+            self._advance(st)
+            if t < nsteps - 1:
+                self._all("EVAL_KICK2_KICK1", st)
+            else:
+                self._all("EVAL_V_KICK2" if want_V_last else "EVAL_KICK2", st)
 
     def steps(self, nsteps, dt, delta=1e-6, counter_max=1000, g_ff2=1.0):
         """nsteps leapfrog steps from the current (q, p) (srhmc_step semantics)."""
@@ -308,8 +335,7 @@ class BigFieldRHMC:
             self._all("PACK", st)
             self.comm.gather_ghosts(self.strips)
         self._all("EVAL", st)
-        for _ in range(nsteps):
-            self.leapfrog(st, False)
+        self.trajectory(st, nsteps, False)
 
     def _iteration(self, st, nsteps):
         self._all("MOMENTUM", st)
@@ -317,8 +343,7 @@ class BigFieldRHMC:
         if self.multi:
             self.comm.sum_scalars(self.strips)
         self._all("RECORD_E0", st)
-        for t in range(nsteps):
-            self.leapfrog(st, t == nsteps - 1)
+        self.trajectory(st, nsteps, True)
         self._all("ENERGY", st)
         if self.multi:
             self.comm.sum_scalars(self.strips)

@@ -97,6 +97,33 @@ class RHMCContext:
         D = D.reshape(n_img, self.cfg.num_rows, self.cfg.num_cols)
         check(self._lib.srhmc_set_data(self._h, dptr(D), n_img))
 
+    def gen_model(self, q, nstars=None):
+        """Model image B + sum f PSF of every field, rendered on the device (base_class.gen_model,
+        sampler_RHMC.py:101-117).  q [F, S] with f in counts -> [F, R, C]."""
+        q = as_f64(q, (self.F, self.S))
+        ns = self._nstars(nstars)
+        out = np.empty((self.F, self.cfg.num_rows, self.cfg.num_cols))
+        check(self._lib.srhmc_gen_model(self._h, dptr(q), iptr(ns), dptr(out)))
+        return out
+
+    def gen_mock_data(self, q_true, nstars=None, seed=0, field_id_base=0, return_data=True):
+        """Poisson mock data of every field generated on the device and installed as the context's data
+        (base_class.gen_mock_data, sampler_RHMC.py:77-99): counter-based Philox, pixel p of field i draws with the
+        counter (field_id_base + i) * R * C + p, so sharded batches reproduce the unsharded images."""
+        q = as_f64(q_true, (self.F, self.S))
+        ns = self._nstars(nstars)
+        out = np.empty((self.F, self.cfg.num_rows, self.cfg.num_cols)) if return_data else None
+        check(self._lib.srhmc_gen_mock_data(self._h, dptr(q), iptr(ns), int(seed), int(field_id_base), dptr(out)))
+        return out
+
+    def run_stats(self, n_groups=1, thin_rate=5, warm_up_num=0):
+        """(R, n_eff) [n_groups, S] of utils.convergence_stats over the q_chain of the last launched run, computed
+        from the chains still resident on the device (no chain download needed)."""
+        R = np.empty((int(n_groups), self.S))
+        n_eff = np.empty((int(n_groups), self.S))
+        check(self._lib.srhmc_run_stats(self._h, int(n_groups), int(thin_rate), int(warm_up_num), dptr(R), dptr(n_eff)))
+        return R, n_eff
+
     # ------------------------------------------------------------------ a2-a4: V, dVdq, H
     def eval(self, q, nstars=None, f_pos=False, g_ff2=1.0, beta=1.0):
         q = as_f64(q, (self.F, self.S))

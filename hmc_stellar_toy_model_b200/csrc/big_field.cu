@@ -33,6 +33,7 @@
 #include "../../include/stellar_rhmc.h"
 #include "common.cuh"
 #include "fastmath.cuh"
+#include "poisson.cuh"
 
 using namespace srhmc;
 
@@ -89,6 +90,25 @@ __device__ __forceinline__ bool patch_of(const BigParams& P, double x, double y,
     clipped_by_data = (i0 != gi0) || (i1 != gi1);
     return i0 <= i1;
 }
+
+// Last-block election for fixed-order two-stage reductions: every block publishes its partials, takes a ticket, and
+// the block that draws the last ticket sums all partials in index order (bit-reproducible, one launch).
+__device__ __forceinline__ bool last_block_ticket(unsigned int* ticket, bool* flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *flag = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (*flag) __threadfence();
+    return *flag;
+}
+
+}  // namespace
+
+#include "big_tile.cuh"
+
+namespace {
 
 // One warp per star (own stars first, then the two ghost lists).  ghost list layout: [0] = count, then f,x,y triples.
 __global__ void big_scatter_kernel(const BigParams P, const double* q, int n_own, const double* ghost_a,
@@ -272,8 +292,9 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
 }
 
 // q fixed point phase B, then (4) p -= h dtau/dq at the new q
+// and -- tile path -- the pair records of the star's final position for the coming evaluation (bin_star, big_tile.cuh)
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
-                                     const double* a2, const int* cnt_q) {
+                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err) {
     const int target = *cnt_q;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
@@ -289,6 +310,7 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
         q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
         const Metric m = metric_of(P.F, qf, S.g_ff2);
         p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+        if (tcnt) bin_star(P, ntx, k, qx, qy, true, tcnt, tlist, err);
     }
 }
 
@@ -305,6 +327,54 @@ __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, cons
         if ((y < 0.0) || (y > P.C - 1.0)) py *= -1.0;
         p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
     }
+}
+
+// Tail of a leapfrog step in ONE per-star kernel: [tile path: g = sum of the footprint partials (gsum_star)] ->
+// (5) p -= h dphi/dq at the new q -> (6) reflections -> [NEXT: steps (1) and (2, phase A) of the following leapfrog
+// step, which start from the same q and the same gradient].  Same operations in the same order as big_gsum_kernel,
+// big_kick2_kernel and big_kick1_kernel run back to back.
+template <bool NEXT>
+__global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, double* g,
+                                const double* gpart, double* a1, double* a2, int* cnt) {
+    int local_max = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
+        double gf, gx, gy;
+        if (gpart) {
+            gsum_star(P, k, f, x, y, gpart, gf, gx, gy);
+            g[3 * k] = gf; g[3 * k + 1] = gx; g[3 * k + 2] = gy;
+        } else {
+            gf = g[3 * k]; gx = g[3 * k + 1]; gy = g[3 * k + 2];
+        }
+        const Metric m = metric_of(P.F, f, S.g_ff2);
+        const double dphi = dphi_f(P, m, gf, f);
+        double pf = p[3 * k] - S.h * dphi;
+        double px = p[3 * k + 1] - S.h * gx;
+        double py = p[3 * k + 2] - S.h * gy;
+        if (f < P.F.f_lim) pf *= -1.0;
+        if ((x < 0.0) || (x > P.Rg - 1.0)) px *= -1.0;
+        if ((y < 0.0) || (y > P.C - 1.0)) py *= -1.0;
+        if (NEXT) {
+            pf = pf - S.h * dphi;
+            px -= S.h * gx;
+            py -= S.h * gy;
+            const double rho = pf, kap = -m.dHff / (m.Hff * m.Hff);
+            a1[3 * k] = rho;
+            a2[3 * k] = kap;
+            int c = 0;
+            while (c < S.counter_max) {
+                const double pn = rho - S.h * (((pf * pf) * kap) / 2.0);
+                const bool more = fabs(pf - pn) > S.delta;
+                pf = pn;
+                ++c;
+                if (!more) break;
+            }
+            a1[3 * k + 1] = (double)c;
+            local_max = max(local_max, c);
+        }
+        p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
+    }
+    if (NEXT && local_max) atomicMax(cnt, local_max);
 }
 
 // momentum refresh p = z sqrt(H) (sampler_RHMC.py:1021-1022) with device Philox keyed by the GLOBAL star id, or
@@ -330,19 +400,6 @@ __global__ void big_momentum_kernel(const BigParams P, double g_ff2, int n, cons
             g0[3 * k + c] = g[3 * k + c];
         }
     }
-}
-
-// Last-block election for fixed-order two-stage reductions: every block publishes its partials, takes a ticket, and
-// the block that draws the last ticket sums all partials in index order (bit-reproducible, one launch).
-__device__ __forceinline__ bool last_block_ticket(unsigned int* ticket, bool* flag) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        *flag = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (*flag) __threadfence();
-    return *flag;
 }
 
 constexpr int kEnergyBlocks = 256;
@@ -497,7 +554,8 @@ struct srhmc_big {
     int64_t launches = 0;
     BBuf D, L, q, p, g, a1, a2, q0, g0, gid, vpart, scalars, gscalars, state, counters, send, recv, err, normals, lnu, E, V, T, A;
     // fused tile evaluation (big_tile.cuh): tile grid over the local rows, per-tile star lists, per-star footprint partials
-    BBuf tcnt, tbegin, tcursor, tlist, gpart;
+    BBuf tcnt, tlist, gpart;
+    bool own_binned = false;  // the pair records of the owned stars' current positions are already in the tile lists
     BBuf epart, tickets;  // per-block energy partials; last-block tickets [0] energy, [1] tile potential
     int nty = 0, ntx = 0;
     bool use_tiles = false;
@@ -562,12 +620,13 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     rc |= b->D.ensure(npix * 8);
     if (!b->use_tiles) rc |= b->L.ensure(npix * 8);
     if (b->use_tiles) {
-        const size_t sources = (size_t)cfg->max_stars + 2 * (size_t)std::max(1, cfg->max_ghosts);
-        rc |= b->tcnt.ensure(ntiles * 4); rc |= b->tbegin.ensure(ntiles * 4); rc |= b->tcursor.ensure(ntiles * 4);
-        rc |= b->tlist.ensure(4 * sources * 8); rc |= b->gpart.ensure(12 * (size_t)cfg->max_stars * 8);
+        // fixed-capacity pair lists (kTileMaxList records per tile: 8 KB of address space each, only the live records
+        // are ever touched)
+        rc |= b->tcnt.ensure(ntiles * 4);
+        rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(int2)); rc |= b->gpart.ensure(12 * (size_t)cfg->max_stars * 8);
         if (!rc) cudaMemset(b->tcnt.ptr, 0, ntiles * 4);
-        if (!rc && (cudaFuncSetAttribute(big_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess ||
-                    cudaFuncSetAttribute(big_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess))
+        if (!rc && (cudaFuncSetAttribute(big_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess ||
+                    cudaFuncSetAttribute(big_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess))
             rc = 1;
     }
     rc |= b->q.ensure(S * 8); rc |= b->p.ensure(S * 8); rc |= b->g.ensure(S * 8);
@@ -602,7 +661,7 @@ int srhmc_big_destroy(srhmc_big* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
                    &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A,
-                   &b->tcnt, &b->tbegin, &b->tcursor, &b->tlist, &b->gpart, &b->epart, &b->tickets};
+                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets};
     for (BBuf* x : all) x->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -644,6 +703,56 @@ int srhmc_big_set_data(srhmc_big* b, const double* D_local) {
     return 0;
 }
 
+int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t seed, double* D_local_out) {
+    // Device-side gen_mock_data (sampler_RHMC.py:77-99 + utils.poisson_realization, utils.py:488-496) for the local data
+    // window: every rank passes the SAME truth list, renders the stars that touch its rows through the tile kernel (fixed
+    // summation order) and Poisson-samples with the global pixel index as Philox counter, so overlapping halo rows agree
+    // between ranks and with an untiled run bit for bit.
+    if (!b || (n > 0 && !q_true) || n < 0) return bfail(SRHMC_ERR_INVALID, "bad argument");
+    BCU(cudaSetDevice(b->cfg.device));
+    cudaStream_t st = b->stream;
+    const size_t ntiles = (size_t)b->nty * b->ntx;
+    BBuf truth;
+    if (int rc = truth.ensure((1 + 3 * (size_t)std::max(1, n)) * 8)) return rc;
+    int rc = 0;
+    rc |= b->tcnt.ensure(ntiles * 4);
+    rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(int2));
+    if (rc) { truth.release(); return SRHMC_ERR_CUDA; }
+    if (cudaFuncSetAttribute(big_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess) {
+        truth.release();
+        return bfail(SRHMC_ERR_CUDA, "cannot configure the tile kernel");
+    }
+    const double cnt = (double)n;
+    cudaError_t e = cudaMemcpyAsync(truth.ptr, &cnt, 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(truth.as<double>() + 1, q_true, (size_t)n * 24, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->tcnt.ptr, 0, ntiles * 4, st);
+    b->own_binned = false;
+    if (e == cudaSuccess) {
+        TileSrc S;
+        S.q = nullptr; S.ga = truth.as<double>(); S.gb = nullptr; S.n_own = 0; S.cap = std::max(1, n);
+        if (n)
+            big_bin_kernel<<<std::max(1, std::min((n + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
+                b->P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+        big_tile_kernel<2><<<(int)ntiles, kTileThreads, sizeof(TileSmem), st>>>(b->P, S, b->ntx, nullptr, b->tcnt.as<int>(), b->tlist.as<int2>(),
+                                                                                nullptr, nullptr, nullptr, nullptr, nullptr, b->D.as<double>(), seed);
+        b->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && D_local_out)
+        e = cudaMemcpyAsync(D_local_out, b->D.ptr, (size_t)b->cfg.nrows * b->cfg.cols * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    truth.release();
+    if (e != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "mock data generation failed: %s", cudaGetErrorString(e));
+    int err = 0;
+    BCU(cudaMemcpy(&err, b->err.ptr, 4, cudaMemcpyDeviceToHost));
+    if (err == 3) {
+        BCU(cudaMemset(b->err.ptr, 0, 4));
+        return bfail(SRHMC_ERR_TOO_LARGE, "more than %d stars touch one 64x64 tile", kTileMaxList);
+    }
+    b->have_data = true;
+    return 0;
+}
+
 int srhmc_big_set_stars(srhmc_big* b, const double* q, const int64_t* global_ids, int32_t n) {
     if (!b || (n > 0 && (!q || !global_ids))) return bfail(SRHMC_ERR_INVALID, "null argument");
     if (n < 0 || n > b->cfg.max_stars) return bfail(SRHMC_ERR_INVALID, "%d stars exceed max_stars = %d", n, b->cfg.max_stars);
@@ -653,6 +762,10 @@ int srhmc_big_set_stars(srhmc_big* b, const double* q, const int64_t* global_ids
         BCU(cudaMemcpyAsync(b->gid.ptr, global_ids, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
     }
     BCU(cudaMemsetAsync(b->p.ptr, 0, 3 * (size_t)b->cfg.max_stars * 8, b->stream));
+    if (b->own_binned) {  // records of the previous positions
+        BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, b->stream));
+        b->own_binned = false;
+    }
     BCU(cudaStreamSynchronize(b->stream));
     b->n = n;
     return 0;
@@ -778,41 +891,65 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             break;
         }
         case SRHMC_BIG_EVAL:
-        case SRHMC_BIG_EVAL_V: {
-            const int want_V = phase == SRHMC_BIG_EVAL_V;
+        case SRHMC_BIG_EVAL_V:
+        case SRHMC_BIG_EVAL_KICK2:
+        case SRHMC_BIG_EVAL_V_KICK2:
+        case SRHMC_BIG_EVAL_KICK2_KICK1: {
+            const int want_V = (phase == SRHMC_BIG_EVAL_V || phase == SRHMC_BIG_EVAL_V_KICK2) ? 1 : 0;
+            // tail: 0 none, 1 the step's last half kick + reflections, 2 also the next step's first kick + p fixed point A
+            const int tail = phase == SRHMC_BIG_EVAL_KICK2_KICK1 ? 2 : ((phase == SRHMC_BIG_EVAL_KICK2 || phase == SRHMC_BIG_EVAL_V_KICK2) ? 1 : 0);
             const double* ga = (b->world > 1 && b->rank > 0) ? b->recv.as<double>() + ((size_t)(b->rank - 1) * 2 + 1) * list : nullptr;
             const double* gb = (b->world > 1 && b->rank < b->world - 1) ? b->recv.as<double>() + ((size_t)(b->rank + 1) * 2 + 0) * list : nullptr;
+            const double* gpart = nullptr;
             if (b->use_tiles) {
                 TileSrc S;
                 S.q = b->q.as<double>(); S.ga = ga; S.gb = gb; S.n_own = n; S.cap = std::max(1, b->cfg.max_ghosts);
                 const int ntiles = b->nty * b->ntx;
-                const int sources = n + 2 * S.cap;
-                const int bg = std::max(1, std::min((sources + 255) / 256, 8 * b->sm_count));
-                big_bin_kernel<false><<<bg, 256, 0, st>>>(P, S, b->ntx, b->tcnt.as<int>(), nullptr, b->err.as<int>());
-                big_bin_scan_kernel<<<1, 1024, 0, st>>>(ntiles, b->tcnt.as<int>(), b->tbegin.as<int>(), b->tcursor.as<int>());
-                big_bin_kernel<true><<<bg, 256, 0, st>>>(P, S, b->ntx, b->tcursor.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                if (!b->own_binned && n > 0) {
+                    big_bin_kernel<<<std::max(1, std::min((n + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
+                        P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                    b->launches += 1;
+                }
+                if (ga || gb) {
+                    big_bin_kernel<<<std::max(1, std::min((2 * S.cap + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
+                        P, S, b->ntx, n, n + 2 * S.cap, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                    b->launches += 1;
+                }
+                b->own_binned = false;  // the tile kernel consumes the lists and re-zeroes the counters
                 if (want_V)
-                    big_tile_kernel<true><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tbegin.as<int>(),
-                        b->tcursor.as<int>(), b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
-                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), b->err.as<int>());
+                    big_tile_kernel<1><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
+                        b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull);
                 else
-                    big_tile_kernel<false><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tbegin.as<int>(),
-                        b->tcursor.as<int>(), b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
-                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), b->err.as<int>());
-                big_gsum_kernel<<<gs, tb, 0, st>>>(P, b->q.as<double>(), n, b->gpart.as<double>(), b->g.as<double>());
-                b->launches += 5;
-                break;
+                    big_tile_kernel<0><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
+                        b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull);
+                b->launches += 1;
+                if (tail == 0) {
+                    big_gsum_kernel<<<gs, tb, 0, st>>>(P, b->q.as<double>(), n, b->gpart.as<double>(), b->g.as<double>());
+                    b->launches += 1;
+                }
+                gpart = b->gpart.as<double>();
+            } else {
+                const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
+                big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
+                const int total = n + 2 * std::max(1, b->cfg.max_ghosts);
+                const int sg = std::max(1, std::min((total * 32 + 255) / 256, 16 * b->sm_count));
+                big_scatter_kernel<<<sg, 256, 0, st>>>(P, b->q.as<double>(), n, ga, gb, b->L.as<double>(), b->err.as<int>());
+                big_pixel_kernel<<<pg, 256, 0, st>>>(P, b->D.as<double>(), b->L.as<double>(), want_V, b->vpart.as<double>());
+                if (want_V) big_vsum_kernel<<<1, 256, 0, st>>>(b->vpart.as<double>(), pg, b->scalars.as<double>());
+                const int gg = std::max(1, std::min((n * 32 + 255) / 256, 16 * b->sm_count));
+                big_gather_kernel<<<gg, 256, 0, st>>>(P, b->q.as<double>(), n, b->L.as<double>(), b->g.as<double>());
+                b->launches += want_V ? 5 : 4;
+                if (tail == 2) BCU(cudaMemsetAsync(cnt, 0, 8, st));  // the tile kernel does this on the tile path
             }
-            const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
-            big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
-            const int total = n + 2 * std::max(1, b->cfg.max_ghosts);
-            const int sg = std::max(1, std::min((total * 32 + 255) / 256, 16 * b->sm_count));
-            big_scatter_kernel<<<sg, 256, 0, st>>>(P, b->q.as<double>(), n, ga, gb, b->L.as<double>(), b->err.as<int>());
-            big_pixel_kernel<<<pg, 256, 0, st>>>(P, b->D.as<double>(), b->L.as<double>(), want_V, b->vpart.as<double>());
-            if (want_V) big_vsum_kernel<<<1, 256, 0, st>>>(b->vpart.as<double>(), pg, b->scalars.as<double>());
-            const int gg = std::max(1, std::min((n * 32 + 255) / 256, 16 * b->sm_count));
-            big_gather_kernel<<<gg, 256, 0, st>>>(P, b->q.as<double>(), n, b->L.as<double>(), b->g.as<double>());
-            b->launches += want_V ? 5 : 4;
+            if (tail == 1)
+                big_tail_kernel<false><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart,
+                                                          b->a1.as<double>(), b->a2.as<double>(), cnt);
+            else if (tail == 2)
+                big_tail_kernel<true><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart,
+                                                         b->a1.as<double>(), b->a2.as<double>(), cnt);
+            if (tail) b->launches += 1;
             break;
         }
         case SRHMC_BIG_RESET_ITER:
@@ -830,8 +967,12 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_QFIX_KICK:
+            if (b->use_tiles && b->own_binned)  // records nobody consumed (two position updates without an evaluation)
+                BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
-                                                    b->a2.as<double>(), cnt + 1);
+                                                    b->a2.as<double>(), cnt + 1, b->ntx, b->use_tiles ? b->tcnt.as<int>() : nullptr,
+                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>());
+            b->own_binned = b->use_tiles;
             b->launches += 1;
             break;
         case SRHMC_BIG_KICK2:

@@ -3,16 +3,18 @@
 // base_class.dVdq / base_class.V, sampler_RHMC.py:365-425 / 294-351, PSF truncated to the (2r+1)^2 patch) reads
 // the data image from HBM exactly ONCE and never materialises Lambda or rho in global memory:
 //
-//   bin_count  one thread per star (own + ghosts): which 64x64 tiles does its patch touch (<= 2x2)  -> counts
-//   bin_scan   one block: exclusive scan of the tile counts -> [begin, cursor) per tile
-//   bin_fill   one thread per star: append a pair record (star id, box patch x tile, footprint slot) to its tiles' lists
+//   bin        one thread per star (own stars: inside the scalar kernel that finishes the position update; ghosts: a
+//              small kernel after the exchange): append a pair record (star id, box patch x tile, footprint slot) to
+//              the fixed-capacity list of each of the <= 2x2 tiles its patch touches (one atomic per pair)
 //   tile       one CTA per 64x64 tile: sort the tile's list by star id (fixed summation order), render
 //              Lambda = B + sum f PSF for the tile in registers (4x4 pixels per thread; per-star row/column
 //              Gaussian tables in shared memory), read D, rho = D/Lambda - 1 into the shared tile, V partial of
 //              the owned rows, then one warp per owned star of the list: the three residual-weighted PSF
 //              reductions over patch x tile  -> gpart[star][slot of this tile in the star's 2x2 footprint]
-//              (EVAL_V: the last tile to finish sums the per-tile potential partials in tile order)
-//   gsum       one thread per owned star: sum of its footprint slots in fixed order, scale -> g[3n]
+//              (EVAL_V: the last tile to finish sums the per-tile potential partials in tile order); the CTA
+//              re-zeroes its list counter for the next evaluation
+//   gsum       per owned star: sum of its footprint slots in fixed order, scale -> g[3n]; fused into the scalar kernel
+//              that consumes the gradient (big_tail_kernel) or run on its own (big_gsum_kernel)
 //
 // No floating-point atomics anywhere: results are bit-reproducible run to run.
 #pragma once
@@ -59,101 +61,39 @@ __device__ __forceinline__ int pack_box(int ia, int ib, int ja, int jb, int slot
     return ia | (ib << 6) | (ja << 12) | (jb << 18) | (slot << 24);
 }
 
-// FILL = false: count the (star, tile) pairs per tile; FILL = true: append the pair records (cursor starts at begin)
-template <bool FILL>
-__global__ void big_bin_kernel(const BigParams P, const TileSrc S, int ntx, int* cnt_or_cursor, int2* list, int* err) {
-    const int total = S.n_own + 2 * S.cap;
-    for (int sid = blockIdx.x * blockDim.x + threadIdx.x; sid < total; sid += gridDim.x * blockDim.x) {
-        const double* src = tile_source(S, sid);
-        if (!src) continue;
-        const double x = src[1], y = src[2];
-        int i0, i1, j0, j1, mi, mj;
-        bool clipped;
-        if (!patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
-            if (!FILL && sid < S.n_own) atomicExch(err, 1);  // an owned star left the local data window
-            continue;
-        }
-        if (!FILL && sid < S.n_own && clipped) atomicExch(err, 1);
-        const TileSpan t = tile_span(P, i0, i1, j0, j1);
-        for (int ti = t.ti0; ti <= t.ti1; ++ti)
-            for (int tj = t.tj0; tj <= t.tj1; ++tj) {
-                const int pos = atomicAdd(&cnt_or_cursor[ti * ntx + tj], 1);
-                if (FILL) {
-                    const int r0 = P.row0 + ti * kTile, c0 = tj * kTile;
-                    list[pos] = make_int2(sid, pack_box(max(i0, r0) - r0, min(i1, r0 + kTile - 1) - r0, max(j0, c0) - c0,
-                                                        min(j1, c0 + kTile - 1) - c0, (ti - t.ti0) * 2 + (tj - t.tj0)));
-                }
-            }
+// Append the pair records of one source star to the lists of the tiles its patch touches.  `owned`: the star belongs
+// to this rank, so leaving the local data window is an error (flag 1).  List overflow raises flag 3.
+__device__ __forceinline__ void bin_star(const BigParams& P, int ntx, int sid, double x, double y, bool owned, int* cnt,
+                                         int2* list, int* err) {
+    int i0, i1, j0, j1, mi, mj;
+    bool clipped;
+    if (!patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
+        if (owned) atomicExch(err, 1);  // an owned star left the local data window
+        return;
     }
+    if (owned && clipped) atomicExch(err, 1);
+    const TileSpan t = tile_span(P, i0, i1, j0, j1);
+    for (int ti = t.ti0; ti <= t.ti1; ++ti)
+        for (int tj = t.tj0; tj <= t.tj1; ++tj) {
+            const int tile = ti * ntx + tj;
+            const int pos = atomicAdd(&cnt[tile], 1);
+            if (pos >= kTileMaxList) {
+                atomicExch(err, 3);  // list capacity exceeded (density above 0.13 stars/px)
+                continue;
+            }
+            const int r0 = P.row0 + ti * kTile, c0 = tj * kTile;
+            list[(size_t)tile * kTileMaxList + pos] =
+                make_int2(sid, pack_box(max(i0, r0) - r0, min(i1, r0 + kTile - 1) - r0, max(j0, c0) - c0,
+                                        min(j1, c0 + kTile - 1) - c0, (ti - t.ti0) * 2 + (tj - t.tj0)));
+        }
 }
 
-// exclusive scan of the tile counts (one block of 1024 threads, contiguous runs per thread, shuffle scans):
-// begin[t], cursor[t] = begin[t]; the counts are re-zeroed for the next evaluation
-__global__ void __launch_bounds__(1024) big_bin_scan_kernel(int ntiles, int* __restrict__ cnt, int* __restrict__ begin,
-                                                            int* __restrict__ cursor) {
-    __shared__ int wsum[32];
-    constexpr int kRun = 16;  // counts per thread per pass
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    int carry = 0;
-    for (int base = 0; base < ntiles; base += 1024 * kRun) {
-        const int lo = base + t * kRun;
-        const bool full = lo + kRun <= ntiles;  // whole run in range: 16-byte vector accesses (the arrays are 256-byte aligned)
-        int c[kRun], s = 0;
-        if (full) {
-#pragma unroll
-            for (int u = 0; u < kRun; u += 4) {
-                const int4 v = *reinterpret_cast<const int4*>(cnt + lo + u);
-                c[u] = v.x; c[u + 1] = v.y; c[u + 2] = v.z; c[u + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kRun; ++u) c[u] = (lo + u < ntiles) ? cnt[lo + u] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kRun; ++u) s += c[u];
-        int inc = s;  // inclusive scan of the thread sums: warp, then the 32 warp totals
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            int w = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += v;
-            }
-            wsum[lane] = w;
-        }
-        __syncthreads();
-        int run = carry + (warp ? wsum[warp - 1] : 0) + inc - s;
-        carry += wsum[31];
-        if (full) {
-#pragma unroll
-            for (int u = 0; u < kRun; u += 4) {
-                int4 o;
-                o.x = run; run += c[u];
-                o.y = run; run += c[u + 1];
-                o.z = run; run += c[u + 2];
-                o.w = run; run += c[u + 3];
-                *reinterpret_cast<int4*>(begin + lo + u) = o;
-                *reinterpret_cast<int4*>(cursor + lo + u) = o;
-                *reinterpret_cast<int4*>(cnt + lo + u) = make_int4(0, 0, 0, 0);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kRun; ++u)
-                if (lo + u < ntiles) {
-                    begin[lo + u] = run;
-                    cursor[lo + u] = run;
-                    cnt[lo + u] = 0;
-                    run += c[u];
-                }
-        }
-        __syncthreads();  // wsum is reused by the next pass
+// sources [sid0, sid1): own stars are [0, n_own), the ghost lists follow (tile_source)
+__global__ void big_bin_kernel(const BigParams P, const TileSrc S, int ntx, int sid0, int sid1, int* cnt, int2* list, int* err) {
+    for (int sid = sid0 + blockIdx.x * blockDim.x + threadIdx.x; sid < sid1; sid += gridDim.x * blockDim.x) {
+        const double* src = tile_source(S, sid);
+        if (!src) continue;
+        bin_star(P, ntx, sid, src[1], src[2], sid < S.n_own, cnt, list, err);
     }
 }
 
@@ -204,14 +144,17 @@ __device__ __forceinline__ void build_pair_tab(const BigParams& P, const TileSrc
     }
 }
 
-template <bool WANT_V>
+// MODE 0: gradient; 1: gradient + pixel potential; 2: mock data -- the rendered model of the tile is Poisson-sampled
+// (poisson.cuh, counter = global pixel index) into Dout and nothing else happens
+template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_kernel(const BigParams P, const TileSrc S, int ntx,
                                                                 const double* __restrict__ D,
-                                                                const int* __restrict__ begin,
-                                                                const int* __restrict__ end,
+                                                                int* __restrict__ cnt,
                                                                 const int2* __restrict__ list, double* __restrict__ gpart,
                                                                 double* vpart, unsigned int* ticket, double* scalars,
-                                                                int* err) {
+                                                                int* fp_counters, double* __restrict__ Dout,
+                                                                unsigned long long mock_seed) {
+    constexpr bool WANT_V = MODE == 1;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     TileSmem& sm = *reinterpret_cast<TileSmem*>(tile_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -249,14 +192,17 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
 #endif
 
     // ---- the tile's pair list, sorted by star id so that every sum below has a fixed order
-    const int b0 = begin[blockIdx.x];
-    int nl = end[blockIdx.x] - b0;
-    if (nl > kTileMaxList) {
-        if (tid == 0) atomicExch(err, 3);  // list capacity exceeded (density above 0.13 stars/px)
-        nl = kTileMaxList;
+    list += (size_t)blockIdx.x * kTileMaxList;
+    constexpr int b0 = 0;
+    const int nl = min(cnt[blockIdx.x], kTileMaxList);  // an overflow was flagged when the list was filled
+    // the fixed-point iteration counters of the leapfrog step are free between its last reader and the next step
+    if (fp_counters && blockIdx.x == 0 && tid < 2) fp_counters[tid] = 0;
+    // guard entries of the factor tables stay zero for the whole launch; the 32 body entries are rewritten per pair
+    for (int k = tid; k < kTileChunk * 4 * kTabPad; k += kTileThreads) {
+        const int pair = k / (4 * kTabPad), e = k % (4 * kTabPad), side = e / kTabPad, g = e % kTabPad;
+        double2* t = (side & 1) ? sm.tab[pair].colf : sm.tab[pair].rowf;
+        t[(side & 2) ? kTabPad + 32 + g : g] = make_double2(0.0, 0.0);
     }
-    for (int k = tid; k < kTileChunk * (int)(sizeof(PairTab) / sizeof(double)); k += kTileThreads)
-        reinterpret_cast<double*>(sm.tab)[k] = 0.0;  // guards stay zero; the bodies are rewritten per pair
     if (WANT_V && tid < kLogTableSize) {
         // (rc_k, -ln rc_k) with rc_k ~ 1/(bin centre): ln x = e ln2 - ln rc_k + log1p(m rc_k - 1) is an identity for the
         // ROUNDED rc_k, so the table only needs -ln rc_k to double accuracy
@@ -264,16 +210,17 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         sm.ltab[tid] = make_double2(rc, -log(rc));
     }
     if (nl == 1) {
-        if (tid == 0) sm.list[0] = list[b0];
+        if (tid == 0) sm.list[0] = __ldcg(&list[b0]);
     } else if (nl > 1) {
         for (int k = tid; k < nl; k += kTileThreads) {
-            const int2 rec = list[b0 + k];
+            const int2 rec = __ldcg(&list[b0 + k]);
             int r = 0;
-            for (int m = 0; m < nl; ++m) r += list[b0 + m].x < rec.x;
+            for (int m = 0; m < nl; ++m) r += __ldcg(&list[b0 + m].x) < rec.x;
             sm.list[r] = rec;
         }
     }
     __syncthreads();
+    if (tid == 0) cnt[blockIdx.x] = 0;  // every thread has read the count: ready for the next evaluation's binning
 
     // ---- render Lambda = B + sum f PSF over the list, in list order
     double lam[4][4];
@@ -297,6 +244,19 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
                 for (int b = 0; b < 4; ++b) lam[a][b] = fma(ex[a], fy[b], lam[a][b]);
         }
         if (base + kTileChunk < nl) __syncthreads();  // the tables are rewritten by the next chunk
+    }
+
+    if (MODE == 2) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int li = pr + a, lj = pc + b;
+                if (li < vr && lj < vc)
+                    Dout[(size_t)(r0 + li - P.row0) * P.C + c0 + lj] =
+                        poisson_draw(lam[a][b], mock_seed, (unsigned long long)(r0 + li) * (unsigned long long)P.C + (unsigned long long)(c0 + lj));
+            }
+        return;
     }
 
     // ---- residual into the shared tile; pixel potential of the owned rows
@@ -381,26 +341,29 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     }
 }
 
-// g = scaled sum of the footprint slots, in slot order (sampler_RHMC.py:404-406)
-__global__ void big_gsum_kernel(const BigParams P, const double* q, int n_own, const double* gpart, double* g) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_own; k += gridDim.x * blockDim.x) {
-        const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
-        int i0, i1, j0, j1, mi, mj;
-        bool clipped;
-        double sf = 0.0, sx = 0.0, sy = 0.0;
-        if (patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
-            const TileSpan t = tile_span(P, i0, i1, j0, j1);
-            for (int ti = t.ti0; ti <= t.ti1; ++ti)
-                for (int tj = t.tj0; tj <= t.tj1; ++tj) {
-                    const double* o = gpart + ((size_t)k * 4 + (ti - t.ti0) * 2 + (tj - t.tj0)) * 3;
-                    sf += o[0]; sx += o[1]; sy += o[2];
-                }
-        }
-        // the tile kernel's sums carry the factor f (its column table is f ey)
-        g[3 * k] = -sf / f;
-        g[3 * k + 1] = -sx * P.inv_s2;
-        g[3 * k + 2] = -sy * P.inv_s2;
+// g = scaled sum of the footprint slots of star k, in slot order (sampler_RHMC.py:404-406)
+__device__ __forceinline__ void gsum_star(const BigParams& P, int k, double f, double x, double y, const double* gpart,
+                                          double& gf, double& gx, double& gy) {
+    int i0, i1, j0, j1, mi, mj;
+    bool clipped;
+    double sf = 0.0, sx = 0.0, sy = 0.0;
+    if (patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
+        const TileSpan t = tile_span(P, i0, i1, j0, j1);
+        for (int ti = t.ti0; ti <= t.ti1; ++ti)
+            for (int tj = t.tj0; tj <= t.tj1; ++tj) {
+                const double* o = gpart + ((size_t)k * 4 + (ti - t.ti0) * 2 + (tj - t.tj0)) * 3;
+                sf += __ldcg(o); sx += __ldcg(o + 1); sy += __ldcg(o + 2);
+            }
     }
+    // the tile kernel's sums carry the factor f (its column table is f ey)
+    gf = -sf / f;
+    gx = -sx * P.inv_s2;
+    gy = -sy * P.inv_s2;
+}
+
+__global__ void big_gsum_kernel(const BigParams P, const double* q, int n_own, const double* gpart, double* g) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_own; k += gridDim.x * blockDim.x)
+        gsum_star(P, k, q[3 * k], q[3 * k + 1], q[3 * k + 2], gpart, g[3 * k], g[3 * k + 1], g[3 * k + 2]);
 }
 
 }  // namespace

@@ -86,6 +86,8 @@ __device__ __forceinline__ double ld_pix(const double* p) { return *p; }
 // (a MOV plus a DADD on the FP64 pipe)
 __device__ __forceinline__ double ld_pix(const unsigned int* p) { return (double)*p; }
 __device__ __forceinline__ double ld_pix(const unsigned short* p) { return (double)(unsigned int)*p; }
+// (Measured and not adopted: feeding the count as the double 2^52 + d with fma(X, r, -2^52 r) = round(d r) removes the
+// I2F from the pixel loop but costs three integer instructions per pixel: 1422 against 1472 M star-steps/s.)
 #ifdef SRHMC_EXP_NEWTON2
 // EXPERIMENT (not adopted): one quadratic Newton step is 8% faster but its 2^-40 error grows to 1e-8 in q over 30
 // Metropolis iterations, beyond the 1e-9 trajectory tolerance of the parity tests
@@ -186,6 +188,15 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     // rows: anchor at the lane's row nearest the star and recur outwards in both directions, so the anchor never
     // underflows while the star is within ~55 px of the image (beyond that every weight is 0 in double anyway);
     // columns: at most 32 of them, so the first column's weight cannot underflow for a star near the image.
+    // row window of the warp
+    int i_lo, i_hi;
+    {
+        const double xc = x - 0.5;
+        const int lo = (int)fmin(fmax(ceil(xc - P.wcut), 0.0), (double)R);
+        const int hi = (int)fmin(fmax(floor(xc + P.wcut) + 1.0, 0.0), (double)R);
+        i_lo = __reduce_min_sync(FULL, lo);
+        i_hi = __reduce_max_sync(FULL, hi);
+    }
     const int K = (R - sub + LPC - 1) / LPC;  // rows of this lane
     const double kf = fmin(fmax(rint((x - 0.5 - (double)sub) * (1.0 / LPC)), 0.0), (double)(K > 0 ? K - 1 : 0));
     const int ks = (int)kf;
@@ -249,15 +260,6 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             v += (double)LPC;
         }
     }
-    // row window of the warp
-    int i_lo, i_hi;
-    {
-        const double xc = x - 0.5;
-        const int lo = (int)fmin(fmax(ceil(xc - P.wcut), 0.0), (double)R);
-        const int hi = (int)fmin(fmax(floor(xc + P.wcut) + 1.0, 0.0), (double)R);
-        i_lo = __reduce_min_sync(FULL, lo);
-        i_hi = __reduce_max_sync(FULL, hi);
-    }
     __syncwarp();
     double c0[CPL], c1[CPL], vlog = 0.0;
     int bad = 0;
@@ -274,8 +276,7 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const double lam = fma(re.x, fey[c], P.B);
-                const double d = ld_pix(sD + i * kChainCS + jb + LPC * c);
-                const double rho = fma(d, rcp_pix(lam), -1.0);
+                const double rho = fma(ld_pix(sD + i * kChainCS + jb + LPC * c), rcp_pix(lam), -1.0);
                 c0[c] = fma(rho, re.x, c0[c]);
                 c1[c] = fma(rho, re.y, c1[c]);
             }

@@ -35,7 +35,7 @@ struct FieldParams {
     double lnB, invB;  // ln(B), 1/B (chain kernel's separable potential)
     double cL, cLh;    // exp(-L^2/sigma^2) and its square root for the chain kernel's stride-L Gaussian recurrences
                        // (L = lanes per chain, kChainLPC)
-    double wcut;       // |i + .5 - x| beyond which exp(-(..)^2/2 sigma^2) < 2^-50
+    double wcut;       // |i + .5 - x| beyond which exp(-(..)^2/2 sigma^2) < 2^-46
     double g0, g1, g2, g_xx, g_ff;
     double alpha, Vpc, vc_pow;
 };

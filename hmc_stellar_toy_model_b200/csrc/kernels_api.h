@@ -44,6 +44,16 @@ int math_test_launch(cudaStream_t stream, int which, const double* x, double* y,
 int to_counts_launch(cudaStream_t stream, const double* src, unsigned int* dst32, unsigned short* dst16, size_t n,
                      int* flags);
 
+// device-side mock data (mock_kernels.cu): model image of every field, Poisson realisation with counter-based Philox
+int model_launch(cudaStream_t stream, const FieldParams& P, int n_fields, const double* q, const int* nstars,
+                 const double* background, double* out);
+int poisson_launch(cudaStream_t stream, const double* lam, double* D, size_t n, unsigned long long seed,
+                   unsigned long long index_base);
+
+// on-device chain statistics (stats_kernels.cu)
+int conv_stats_launch(cudaStream_t stream, const double* X, long long rows, int d, int n_groups, int cpg, int thin, int warm,
+                      double* means, double* R, double* neff);
+
 // FMA-chain roofline microbenchmark
 int fma_peak_run(int precision, int sms, double* tflops, float* ms);
 

@@ -98,6 +98,8 @@ struct srhmc_ctx {
     // sizes of the last uploaded run
     int run_L = 0, run_rows = 0;
     bool run_has_nstars = false, run_has_normals = false, run_has_lnu = false, run_one_star = false;
+    bool run_has_qchain = false;  // the last launched run recorded q_chain on the device
+    DevBuf st_means, st_R, st_neff;  // chain statistics
 };
 
 namespace {
@@ -298,7 +300,13 @@ int srhmc_create(const srhmc_config* cfg, srhmc_ctx** out) {
     P.invB = 1.0 / cfg->B_count;
     P.cL = std::exp(-(double)(kChainLPC * kChainLPC) / (sigma * sigma));
     P.cLh = std::exp(-(double)(kChainLPC * kChainLPC) / (2.0 * sigma * sigma));
-    P.wcut = std::sqrt(50.0 * M_LN2 * 2.0 * sigma * sigma);
+    {
+        // rows whose Gaussian weight is below 2^-bits of the peak are skipped by the one-star kernel (its 24-column window
+        // cuts at 2^-47 for the default PSF); SRHMC_CHAIN_WCUT_BITS overrides for A/B measurements
+        double bits = 46.0;
+        if (const char* env = std::getenv("SRHMC_CHAIN_WCUT_BITS")) bits = std::max(20.0, std::min(1000.0, std::atof(env)));
+        P.wcut = std::sqrt(bits * M_LN2 * 2.0 * sigma * sigma);
+    }
     P.f_lim = cfg->f_lim;
     P.f_low = cfg->f_low;
     P.g0 = cfg->g0; P.g1 = cfg->g1; P.g2 = cfg->g2;
@@ -350,7 +358,7 @@ int srhmc_destroy(srhmc_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->ls_dt, &c->ls_steps, &c->ls_bg, &c->ls_scratch, &c->ls_d1, &c->ls_d2, &c->ls_d3, &c->field_ids, &c->sched_done, &c->sched_state, &c->sched_err, &c->D32, &c->D16, &c->logtab, &c->flag, &c->D, &c->Dstage, &c->q, &c->p, &c->nstars, &c->normals, &c->lnu, &c->sg, &c->sb, &c->qchain,
-                     &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout,
+                     &c->pchain, &c->E, &c->V, &c->T, &c->A, &c->acc, &c->scratch, &c->qout, &c->pout, &c->Vout, &c->st_means, &c->st_R, &c->st_neff,
                      &c->grad, &c->H, &c->Hg, &c->counts};
     for (DevBuf* b : all) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -390,16 +398,10 @@ int srhmc_last_kernel_ms(srhmc_ctx* c, float* ms) {
 
 int64_t srhmc_launch_count(srhmc_ctx* c) { return c ? c->launches : 0; }
 
-int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
-    if (!c || !D) return fail(SRHMC_ERR_INVALID, "null argument");
-    const int64_t want = c->cfg.shared_data ? 1 : c->cfg.n_fields;
-    if (n_images != want) return fail(SRHMC_ERR_INVALID, "expected %lld image(s), got %lld", (long long)want, (long long)n_images);
-    CU_TRY(cudaSetDevice(c->cfg.device));
-    const size_t n = (size_t)n_images * c->P.R * c->P.C;
-    if (c->cfg.precision == 64) {
-        if (int rc = upload(c, c->D, D, n * 8)) return rc;
-    } else {
-        if (int rc = upload(c, c->Dstage, D, n * 8)) return rc;
+// after the float64 images are in place on the device (c->D for the FP64 build, c->Dstage for the FP32 build): the
+// reduced-precision / exact-integer copies the kernels read
+static int finish_data(srhmc_ctx* c, size_t n) {
+    if (c->cfg.precision != 64) {
         if (int rc = c->D.ensure(n * 4)) return rc;
         const int e = convert_image_launch(c->stream, c->Dstage.as<double>(), c->D.as<float>(), n);
         if (e != 0) return fail(SRHMC_ERR_CUDA, "image conversion failed: %s", cudaGetErrorString((cudaError_t)e));
@@ -426,6 +428,64 @@ int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
     CU_TRY(cudaStreamSynchronize(c->stream));
     c->have_data = true;
     return 0;
+}
+
+int srhmc_set_data(srhmc_ctx* c, const double* D, int64_t n_images) {
+    if (!c || !D) return fail(SRHMC_ERR_INVALID, "null argument");
+    const int64_t want = c->cfg.shared_data ? 1 : c->cfg.n_fields;
+    if (n_images != want) return fail(SRHMC_ERR_INVALID, "expected %lld image(s), got %lld", (long long)want, (long long)n_images);
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)n_images * c->P.R * c->P.C;
+    if (int rc = upload(c, c->cfg.precision == 64 ? c->D : c->Dstage, D, n * 8)) return rc;
+    return finish_data(c, n);
+}
+
+static int upload_nstars(srhmc_ctx* c, const int32_t* nstars);
+
+// model images of all fields into `dst` (device, float64 [F,R,C])
+static int render_models(srhmc_ctx* c, const double* q, const int32_t* nstars, double* dst) {
+    const size_t S = 3 * (size_t)c->cfg.max_stars;
+    if (S) {
+        if (int rc = upload(c, c->q, q, (size_t)c->cfg.n_fields * S * 8)) return rc;
+    } else if (int rc = c->q.ensure(8)) {
+        return rc;
+    }
+    if (int rc = upload_nstars(c, nstars)) return rc;
+    const int e = model_launch(c->stream, c->P, c->cfg.n_fields, c->q.as<double>(), nstars ? c->nstars.as<int>() : nullptr, nullptr, dst);
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "model kernel failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    return 0;
+}
+
+int srhmc_gen_model(srhmc_ctx* c, const double* q, const int32_t* nstars, double* model) {
+    if (!c || !model || (c->cfg.max_stars > 0 && !q)) return fail(SRHMC_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)c->cfg.n_fields * c->P.R * c->P.C;
+    if (int rc = c->scratch.ensure(n * 8)) return rc;
+    if (int rc = render_models(c, q, nstars, c->scratch.as<double>())) return rc;
+    if (int rc = download(c, model, c->scratch, n * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int srhmc_gen_mock_data(srhmc_ctx* c, const double* q_true, const int32_t* nstars, uint64_t seed, int64_t field_id_base,
+                        double* D_out) {
+    if (!c || (c->cfg.max_stars > 0 && !q_true)) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (c->cfg.shared_data) return fail(SRHMC_ERR_INVALID, "mock data are generated per field: not available with shared_data");
+    if (field_id_base < 0) return fail(SRHMC_ERR_INVALID, "field_id_base must be >= 0");
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const size_t npx = (size_t)c->P.R * c->P.C, n = (size_t)c->cfg.n_fields * npx;
+    if (int rc = c->scratch.ensure(n * 8)) return rc;
+    DevBuf& dst = c->cfg.precision == 64 ? c->D : c->Dstage;
+    if (int rc = dst.ensure(n * 8)) return rc;
+    if (int rc = render_models(c, q_true, nstars, c->scratch.as<double>())) return rc;
+    const int e = poisson_launch(c->stream, c->scratch.as<double>(), dst.as<double>(), n, seed, (unsigned long long)field_id_base * npx);
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "Poisson kernel failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (D_out) {
+        if (int rc = download(c, D_out, dst, n * 8)) return rc;
+    }
+    return finish_data(c, n);
 }
 
 static int upload_nstars(srhmc_ctx* c, const int32_t* nstars) {
@@ -620,6 +680,7 @@ static int build_run_launch_args(srhmc_ctx* c, const srhmc_run_args* a, LaunchAr
     if ((int)L != c->run_L) return fail(SRHMC_ERR_STATE, "srhmc_run_launch: niter differs from the uploaded run");
     const size_t rows = (L + a->chain_stride - 1) / a->chain_stride;
     c->run_rows = (int)rows;
+    c->run_has_qchain = a->q_chain != nullptr && S > 0;
     const size_t FS = std::max<size_t>(F * S * 8, 8);
     if (a->q_chain) if (int rc = c->qchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
     if (a->p_chain) if (int rc = c->pchain.ensure(std::max<size_t>(F * rows * S * 8, 8))) return rc;
@@ -986,6 +1047,67 @@ int srhmc_hessian(srhmc_ctx* c, const double* q, const double* p, const int32_t*
         }
     }
     if (E && !d2_only) if (int rc = download(c, E, c->Vout, F * 8)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+
+static int check_stats_args(int64_t n_chains, int64_t rows, int32_t d, int32_t n_groups, int32_t thin, int32_t warm) {
+    if (n_chains < 1 || rows < 1 || d < 1 || n_groups < 1 || thin < 1 || warm < 0) return fail(SRHMC_ERR_INVALID, "bad chain statistics argument");
+    if (n_chains % n_groups) return fail(SRHMC_ERR_INVALID, "%lld chains do not split into %d equal groups", (long long)n_chains, n_groups);
+    if (n_chains / n_groups < 2) return fail(SRHMC_ERR_INVALID, "convergence statistics need at least two chains per group (utils.py:94)");
+    const int64_t Lw = rows - warm, Lc = Lw > 0 ? (Lw + thin - 1) / thin : 0;
+    if (Lc / 2 < 2) return fail(SRHMC_ERR_INVALID, "fewer than two samples per split chain after warm-up and thinning");
+    if (n_chains / n_groups > (1 << 24)) return fail(SRHMC_ERR_INVALID, "too many chains per group");
+    return 0;
+}
+
+int srhmc_convergence_stats(int32_t device, const double* q_chain, int64_t n_chains, int64_t n_iter, int32_t d, int32_t n_groups,
+                            int32_t thin_rate, int32_t warm_up_num, double* R, double* n_eff) {
+    if (!q_chain || !R || !n_eff) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (int rc = check_stats_args(n_chains, n_iter, d, n_groups, thin_rate, warm_up_num)) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRHMC_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(SRHMC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU_TRY(cudaSetDevice(device));
+    const int cpg = (int)(n_chains / n_groups);
+    const size_t nx = (size_t)n_chains * n_iter * d, nout = (size_t)n_groups * d;
+    DevBuf X, means, out;
+    int rc = X.ensure(nx * 8);
+    if (!rc) rc = means.ensure(nout * 2 * cpg * 8);
+    if (!rc) rc = out.ensure(2 * nout * 8);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpy(X.ptr, q_chain, nx * 8, cudaMemcpyHostToDevice);
+    if (!rc && e == cudaSuccess)
+        e = (cudaError_t)conv_stats_launch(nullptr, X.as<double>(), n_iter, d, n_groups, cpg, thin_rate, warm_up_num, means.as<double>(),
+                                           out.as<double>(), out.as<double>() + nout);
+    if (!rc && e == cudaSuccess) e = cudaMemcpy(R, out.ptr, nout * 8, cudaMemcpyDeviceToHost);
+    if (!rc && e == cudaSuccess) e = cudaMemcpy(n_eff, out.as<double>() + nout, nout * 8, cudaMemcpyDeviceToHost);
+    X.release(); means.release(); out.release();
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(SRHMC_ERR_CUDA, "chain statistics failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int srhmc_run_stats(srhmc_ctx* c, int32_t n_groups, int32_t thin_rate, int32_t warm_up_num, double* R, double* n_eff) {
+    if (!c || !R || !n_eff) return fail(SRHMC_ERR_INVALID, "null argument");
+    if (!c->run_has_qchain || c->run_rows == 0)
+        return fail(SRHMC_ERR_STATE, "no resident q_chain: launch a run with q_chain requested first (srhmc_run_launch)");
+    const int d = 3 * c->cfg.max_stars;
+    if (int rc = check_stats_args(c->cfg.n_fields, c->run_rows, d, n_groups, thin_rate, warm_up_num)) return rc;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const int cpg = c->cfg.n_fields / n_groups;
+    const size_t nout = (size_t)n_groups * d;
+    if (int rc = c->st_means.ensure(nout * 2 * cpg * 8)) return rc;
+    if (int rc = c->st_R.ensure(nout * 8)) return rc;
+    if (int rc = c->st_neff.ensure(nout * 8)) return rc;
+    const int e = conv_stats_launch(c->stream, c->qchain.as<double>(), c->run_rows, d, n_groups, cpg, thin_rate, warm_up_num,
+                                    c->st_means.as<double>(), c->st_R.as<double>(), c->st_neff.as<double>());
+    if (e != 0) return fail(SRHMC_ERR_CUDA, "chain statistics kernel failed: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    if (int rc = download(c, R, c->st_R, nout * 8)) return rc;
+    if (int rc = download(c, n_eff, c->st_neff, nout * 8)) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -93,8 +93,17 @@ class base_class(object):
                                                                FWHM=self.PSF_FWHM_pix)
         return model
 
-    def gen_mock_data(self, q_true=None, return_data=False):
-        data = poisson_realization(self.gen_model(q_true))
+    def gen_mock_data(self, q_true=None, return_data=False, device_seed=None):
+        """sampler_RHMC.py:77-99.  By default the image is built like upstream (host PSFs, np.random.poisson from the
+        global legacy stream, so a seeded script gets the reference's image).  device_seed=<int> (new capability) renders
+        and Poisson-samples on the GPU with counter-based Philox instead; the global np.random stream is not touched."""
+        if device_seed is None:
+            data = poisson_realization(self.gen_model(q_true))
+        else:
+            q = self.format_q(np.array(q_true, dtype=float, copy=True))
+            ctx = self._device_ctx(q.size // 3, need_data=False)
+            data = ctx.gen_mock_data(q.reshape(1, -1), seed=device_seed)[0]
+            self._ctx_data = data.copy()  # the context already holds this image
         if return_data:
             return data
         self.D = data

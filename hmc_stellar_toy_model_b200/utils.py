@@ -3,15 +3,15 @@
 Only what the RHMC path's callers need is mirrored here: unit conversions, the Gaussian PSF used to build mock
 data and the frozen Fisher constants, Poisson realisation, power-law sampling and the exponential scheduler.
 These run once at set-up time on the host, exactly as upstream; everything evaluated inside the sampler loops
-runs in the CUDA kernels.  Plotting, NUTS bookkeeping and chain statistics of utils.py are out of scope
-(SURVEY.md section 2).
+runs in the CUDA kernels.  The chain statistics (convergence_stats: SURVEY.md 8f row 4) run on the device as well;
+plotting and NUTS bookkeeping of utils.py are out of scope.
 """
 from __future__ import annotations
 
 import numpy as np
 
 __all__ = ["mag2flux", "flux2mag", "gauss_PSF", "factors", "poisson_realization", "gen_pow_law_sample",
-           "integrate_pow_law", "scheduler", "np"]
+           "integrate_pow_law", "scheduler", "convergence_stats", "acceptance_rate", "np"]
 
 
 def mag2flux(mag):
@@ -67,3 +67,29 @@ def scheduler(val_init, val_final, Niter=10):
     """Exponential schedule val_init -> val_final over Niter values (utils.py:649-660)."""
     c = np.exp(np.log(val_final / float(val_init)) / float(Niter - 1))
     return c ** np.arange(0, Niter, 1) * val_init
+
+
+def convergence_stats(q_chain, thin_rate=5, warm_up_num=0, device=0):
+    """Gelman-Rubin R and effective sample size per variable of q_chain [Nchain, Niter, D] (utils.py:86-167), computed
+    by the CUDA library (srhmc_convergence_stats); the reference's Python-2 `n = L_chain/2` is an integer division.
+    For chains that are still on the device use RHMCContext.run_stats instead."""
+    from . import _capi
+
+    q = np.ascontiguousarray(q_chain, dtype=np.float64)
+    Nchain, Niter, D = q.shape
+    assert Nchain > 1  # utils.py:94
+    lib = _capi.load_library()
+    R, n_eff = np.empty(D), np.empty(D)
+    _capi.check(lib.srhmc_convergence_stats(int(device), _capi.dptr(q), Nchain, Niter, D, 1, int(thin_rate), int(warm_up_num),
+                                            _capi.dptr(R), _capi.dptr(n_eff)))
+    return R, n_eff
+
+
+def acceptance_rate(decision_chain, start=None, end=None):
+    """Fraction of accepted proposals per chain; decision_chain [Nchain, Niter, 1] (utils.py:192-209)."""
+    decision_chain = np.asarray(decision_chain)
+    _, Niter, _ = decision_chain.shape
+    if start is None and end is None:
+        return np.sum(decision_chain, axis=(1, 2)) / Niter
+    Niter = (end - start) if end > 0 else (Niter - start)
+    return np.sum(decision_chain[:, start:end, :], axis=(1, 2)) / Niter

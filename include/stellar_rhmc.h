@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SRHMC_ABI_VERSION 2
+#define SRHMC_ABI_VERSION 3
 
 typedef enum srhmc_status {
     SRHMC_OK = 0,
@@ -180,6 +180,19 @@ int srhmc_host_free(void* p);
 /* gym.D: n_images = n_fields, or 1 when cfg.shared_data. */
 int srhmc_set_data(srhmc_ctx* ctx, const double* D, int64_t n_images);
 
+/* Model image of every field on the device: Lambda = B + sum_s f_s PSF_s.  Replaces base_class.gen_model
+ * (sampler_RHMC.py:101-117).  q [F,S] with f in counts; model [F,R,C] (host, written). */
+int srhmc_gen_model(srhmc_ctx* ctx, const double* q, const int32_t* nstars, double* model);
+
+/* Mock data on the device: model image of q_true, then one Poisson variate per pixel; the images become the context's
+ * data as if passed to srhmc_set_data.  Replaces base_class.gen_mock_data (sampler_RHMC.py:77-99; samplers.py:44-67)
+ * with utils.poisson_realization (utils.py:488-496).  The reference draws from NumPy's global stream; here pixel p of
+ * field i uses Philox4x32-10 with key `seed` and the 64-bit counter (field_id_base + i) * R * C + p, so a batch sharded
+ * over contexts / GPUs gets the same images as an unsharded one (algorithm: NumPy legacy Poisson -- multiplication
+ * method below lambda = 10, Hoermann's PTRS above).  D_out [F,R,C] may be NULL (data stay on the device). */
+int srhmc_gen_mock_data(srhmc_ctx* ctx, const double* q_true, const int32_t* nstars, uint64_t seed, int64_t field_id_base,
+                        double* D_out);
+
 /* One evaluation per field.  Replaces base_class.V (sampler_RHMC.py:294-351), dVdq (:365-425), H with grad
  * (:229-292) and, composed by the caller, dphidq/dtaudq/dtaudp (:448-492); also lightsource_gym.V/dVdq
  * (samplers.py:1108-1150) with use_prior = use_Vc = 0.
@@ -236,6 +249,18 @@ int srhmc_hessian(srhmc_ctx* ctx, const double* q, const double* p, const int32_
 int srhmc_eval_background(srhmc_ctx* ctx, const double* q, const int32_t* nstars, const double* background, double* V,
                           double* grad);
 
+/* Split-chain Gelman-Rubin statistic and effective sample size per variable.  Replaces utils.convergence_stats (with
+ * utils.variogram), utils.py:86-188, including its definitions of W (mean of the within-chain standard deviations) and
+ * of the autocorrelation cut-off.  q_chain [n_chains, n_iter, d] on the host; the chains form n_groups consecutive groups
+ * of n_chains / n_groups chains (one call of the reference per group); R, n_eff [n_groups, d]. */
+int srhmc_convergence_stats(int32_t device, const double* q_chain, int64_t n_chains, int64_t n_iter, int32_t d, int32_t n_groups,
+                            int32_t thin_rate, int32_t warm_up_num, double* R, double* n_eff);
+/* The same statistics over the q_chain of the context's last launched run, which is still resident on the device
+ * (srhmc_run_upload + srhmc_run_launch with q_chain requested; srhmc_run_download is not needed): a batch of thousands of
+ * chains returns 2 * n_groups * 3 * max_stars numbers instead of its chains.  Rows are the stored rows of the run
+ * (chain_stride applied).  R, n_eff [n_groups, 3 * max_stars]. */
+int srhmc_run_stats(srhmc_ctx* ctx, int32_t n_groups, int32_t thin_rate, int32_t warm_up_num, double* R, double* n_eff);
+
 /* Draws of the device generator, for replaying a Philox run through another implementation:
  * normals [F,L,S], lnu [F,L] exactly as srhmc_run would consume them for `seed`. */
 int srhmc_philox_draws(srhmc_ctx* ctx, uint64_t seed, int32_t niter, double* normals, double* lnu);
@@ -256,6 +281,8 @@ int srhmc_test_device_math(srhmc_ctx* ctx, int32_t which, const double* x, doubl
  * each interior side.  One leapfrog step is the phase sequence
  *     KICK1 -> [max-reduce counters] -> PFIX_QFIX -> [max-reduce counters] -> QFIX_KICK -> PACK -> [all-gather
  *     ghost_send into ghost_recv] -> EVAL | EVAL_V -> KICK2
+ * (inside a trajectory "EVAL -> KICK2 -> next step's KICK1" is the single phase EVAL_KICK2_KICK1, and the last step ends
+ * with EVAL_V_KICK2: four kernels per leapfrog step on one GPU)
  * and one Metropolis iteration is
  *     MOMENTUM -> ENERGY -> [sum-reduce scalars into global_scalars] -> RECORD_E0 -> nsteps x step -> ENERGY ->
  *     [sum-reduce] -> ACCEPT.
@@ -291,7 +318,11 @@ typedef enum srhmc_big_phase_id {
     SRHMC_BIG_ENERGY = 8,     /* scalars[1..3] = T, #stars outside the support, prior potential (a3, a5) */
     SRHMC_BIG_RECORD_E0 = 9,  /* E0 from global_scalars; chain row */
     SRHMC_BIG_ACCEPT = 10,    /* Metropolis test on global_scalars; restore on rejection; chain row (a8) */
-    SRHMC_BIG_RESET_ITER = 11 /* zero the device-side iteration counter used when step.iteration < 0 */
+    SRHMC_BIG_RESET_ITER = 11, /* zero the device-side iteration counter used when step.iteration < 0 */
+    /* fused forms (same arithmetic in the same order, fewer launches): */
+    SRHMC_BIG_EVAL_KICK2 = 12,       /* EVAL then KICK2 */
+    SRHMC_BIG_EVAL_V_KICK2 = 13,     /* EVAL_V then KICK2 */
+    SRHMC_BIG_EVAL_KICK2_KICK1 = 14  /* EVAL, KICK2 and the KICK1 of the following leapfrog step (same q, same gradient) */
 } srhmc_big_phase_id;
 
 typedef struct srhmc_big_step {
@@ -322,6 +353,10 @@ int srhmc_big_adopt_stream(srhmc_big* b, void* cuda_stream);  /* no synchronisat
 int srhmc_big_synchronize(srhmc_big* b);
 int64_t srhmc_big_launch_count(srhmc_big* b);
 int srhmc_big_set_data(srhmc_big* b, const double* D_local /* [nrows, cols] */);
+/* Device-side gen_mock_data for the local data window (see srhmc_gen_mock_data): q_true [n,3] (f in counts, x, y) is
+ * the WHOLE field's truth list, identical on every rank; the Philox counter is the global pixel index, so halo rows agree
+ * between ranks.  D_local_out [nrows, cols] may be NULL. */
+int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t seed, double* D_local_out);
 int srhmc_big_set_stars(srhmc_big* b, const double* q /* [n,3] */, const int64_t* global_ids /* [n] */, int32_t n);
 int srhmc_big_get_stars(srhmc_big* b, double* q, double* p, double* grad /* each [n,3], may be NULL */);
 int srhmc_big_set_momenta(srhmc_big* b, const double* p /* [n,3] */);

@@ -77,6 +77,8 @@ def _install_stubs() -> None:
 
 def _py3(src: str) -> str:
     src = src.replace("xrange", "range")
+    # the one Python-2 integer division on a path we pin (utils.convergence_stats, utils.py:111: both operands are ints)
+    src = src.replace("n = L_chain/2 ", "n = L_chain//2 ")
     return _PRINT_RE.sub(lambda m: "%sprint(%s)" % (m.group(1), m.group(2)), src)
 
 

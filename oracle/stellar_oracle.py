@@ -828,6 +828,167 @@ def ls_trial(L: LightSetup, q_start, model_data, dt, normals, steps, lnu, zero_x
     return acc
 
 
+
+# --------------------------------------------------------------------------- mock data
+def philox4x32_10(seed, c0, c1, c2, c3):
+    """Philox4x32-10 (Salmon et al. 2011) of the counter (c0, c1, c2, c3) under the 64-bit key `seed`; vectorised over
+    NumPy arrays.  Same constants and round structure as csrc/common.cuh (the device generator of the chains and of
+    the mock data); returns four uint32 arrays."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    c = [np.asarray(v, dtype=np.uint64) & mask for v in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return [v.astype(np.uint32) for v in c]
+
+
+def philox_u01(a, b):
+    """53-bit uniform in (0, 1) from two Philox words (csrc/common.cuh u01)."""
+    m = ((a.astype(np.uint64) >> np.uint64(5)) << np.uint64(26)) | (b.astype(np.uint64) >> np.uint64(6))
+    return (m.astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def poisson_philox(lam, seed, index_base=0):
+    """One Poisson variate per element of `lam` (utils.poisson_realization, utils.py:488-496, calls np.random.poisson
+    once per pixel) with the sampling algorithm of NumPy's legacy generator -- multiplication method for lam < 10,
+    Hoermann's PTRS transformed rejection (1993) for lam >= 10 (NumPy is an un-vendored, unpinned dependency of the
+    reference: restated from the published algorithm) -- driven by counter-based Philox uniforms exactly as
+    csrc/poisson.cuh consumes them: element i uses the counters (idx_lo, attempt, idx_hi, 3), idx = index_base + i,
+    two uniforms per attempt."""
+    from scipy.special import gammaln
+
+    lam = np.asarray(lam, dtype=float)
+    flat = lam.ravel()
+    out = np.zeros(flat.size)
+    idx = np.uint64(index_base) + np.arange(flat.size, dtype=np.uint64)
+    lo, hi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+
+    def uniforms(sel, attempt):
+        r = philox4x32_10(seed, lo[sel], np.uint64(attempt), hi[sel], np.uint64(3))
+        return philox_u01(r[0], r[1]), philox_u01(r[2], r[3])
+
+    # multiplication method
+    small = np.nonzero((flat > 0) & (flat < 10.0))[0]
+    if small.size:
+        enlam = np.exp(-flat[small])
+        prod = np.ones(small.size)
+        k = np.zeros(small.size)
+        live = np.arange(small.size)
+        attempt = 0
+        while live.size:
+            u, v = uniforms(small[live], attempt)
+            prod[live] *= u
+            done1 = ~(prod[live] > enlam[live])
+            cont = live[~done1]
+            k[cont] += 1
+            prod[cont] *= v[~done1]
+            done2 = ~(prod[cont] > enlam[cont])
+            k[cont[~done2]] += 1
+            live = cont[~done2]
+            attempt += 1
+        out[small] = k
+    # PTRS
+    big = np.nonzero(flat >= 10.0)[0]
+    if big.size:
+        L = flat[big]
+        slam, loglam = np.sqrt(L), np.log(L)
+        b = 0.931 + 2.53 * slam
+        a = -0.059 + 0.02483 * b
+        invalpha = 1.1239 + 1.1328 / (b - 3.4)
+        vr = 0.9277 - 3.6224 / (b - 2.0)
+        res = np.zeros(big.size)
+        live = np.arange(big.size)
+        attempt = 0
+        while live.size:
+            U, V = uniforms(big[live], attempt)
+            U = U - 0.5
+            us = 0.5 - np.abs(U)
+            k = np.floor((2.0 * a[live] / us + b[live]) * U + L[live] + 0.43)
+            acc = (us >= 0.07) & (V <= vr[live])
+            rej = ~acc & ((k < 0.0) | ((us < 0.013) & (V > us)))
+            rest = ~acc & ~rej
+            with np.errstate(invalid="ignore", divide="ignore"):
+                lhs = np.log(V) + np.log(invalpha[live]) - np.log(a[live] / (us * us) + b[live])
+                rhs = -L[live] + k * loglam[live] - gammaln(np.where(k >= 0, k, 0.0) + 1.0)
+            acc = acc | (rest & (lhs <= rhs))
+            res[live[acc]] = k[acc]
+            live = live[~acc]
+            attempt += 1
+        out[big] = res
+    return out.reshape(lam.shape)
+
+
+# --------------------------------------------------------------------------- chain statistics (SURVEY 8f row 4)
+def variogram(chains, var_num, t_lag):
+    """BDA3 (11.7) variogram of `chains` (list of [n, D] arrays) at lag t (utils.py:170-188)."""
+    m = len(chains)
+    n = chains[0].shape[0]
+    V_t = 0.0
+    for i in range(m):
+        c = chains[i][:, var_num]
+        V_t += np.sum(np.square(c[t_lag:] - c[:-t_lag]))
+    return V_t / float(m * (n - t_lag))
+
+
+def convergence_stats(q_chain, thin_rate=5, warm_up_num=0):
+    """Split-chain Gelman-Rubin R and effective sample size per variable (utils.convergence_stats, utils.py:86-167),
+    with the reference's Python-2 integer division `n = L_chain/2` (utils.py:111) and its quirks kept: W is the mean of
+    the within-chain standard DEVIATIONS (np.std, utils.py:120), and the first autocorrelation is tested twice
+    (utils.py:144).  q_chain [Nchain, Niter, D]."""
+    Nchain, Niter, D = q_chain.shape
+    assert Nchain > 1
+    chains = []
+    n = 0
+    for m in range(Nchain):
+        c = q_chain[m, warm_up_num:, :][::thin_rate, :]
+        L_chain = c.shape[0]
+        if L_chain % 2:
+            c = c[: L_chain - 1]
+        n = L_chain // 2
+        chains.append(c[:n])
+        chains.append(c[n:])
+    m = len(chains)
+    W = np.mean(np.array([np.std(c, ddof=1, axis=0) for c in chains]), axis=0)
+    mean_within = np.array([np.mean(c, axis=0) for c in chains])
+    mean_all = np.mean(mean_within, axis=0)
+    B = np.sum(np.square(mean_within - mean_all), axis=0) * n / float(m - 1)
+    var = W * (n - 1) / float(n) + B / float(n)
+    R = np.sqrt(var / W)
+    n_eff = np.zeros(D)
+    for i in range(D):
+        rho_t1 = 1.0 - variogram(chains, i, 1) / (2 * var[i])
+        rho_t2 = 1.0 - variogram(chains, i, 2) / (2 * var[i])
+        if rho_t1 < 5e-2:
+            sum_rho = 0
+        else:
+            rho_t = [rho_t1, rho_t2]
+            t = 1
+            while t < n - 2:
+                rho_t.append(1 - variogram(chains, i, t + 2) / (2 * var[i]))
+                if (t % 2) == 1 and (rho_t[t] + rho_t[t + 1]) < 0:
+                    break
+                t += 1
+            sum_rho = np.sum(rho_t[:t])
+            if sum_rho < 0:
+                sum_rho = 0
+        n_eff[i] = m * n / (1 + 2 * sum_rho)
+    return R, n_eff
+
+
+def acceptance_rate(decision_chain, start=None, end=None):
+    """Fraction of accepted proposals per chain (utils.acceptance_rate, utils.py:192-209); decision_chain [Nchain, Niter, 1]."""
+    _, Niter, _ = decision_chain.shape
+    if start is None and end is None:
+        return np.sum(decision_chain, axis=(1, 2)) / Niter
+    Niter = (end - start) if end > 0 else (Niter - start)
+    return np.sum(decision_chain[:, start:end, :], axis=(1, 2)) / Niter
+
+
 def star_steps(niter_plus_one: int, nsteps: int, nstars: int) -> int:
     """Units of BASELINE.json's metric produced by one run_rhmc call."""
     return niter_plus_one * nsteps * nstars

@@ -357,10 +357,27 @@ def rj_chain(seed=77, niter=60, nobj=20, nmodel=5, nsteps=5, dt=5e-2):
                 **gym_state(gym))
 
 
+def conv_stats():
+    """utils.convergence_stats (utils.py:86-167, Python-2 division restored by the shim) on AR(1) chains with different
+    autocorrelation per variable, and on chains with a short and an odd thinned length."""
+    out = {}
+    for tag, (seed, nchain, niter, thin, warm) in {"a": (3, 8, 600, 5, 0), "b": (4, 5, 333, 2, 51)}.items():
+        rng = np.random.RandomState(seed)
+        phi = np.array([0.2, 0.7, 0.95])
+        x = np.zeros((nchain, niter, 3))
+        eps = rng.randn(nchain, niter, 3)
+        for t in range(1, niter):
+            x[:, t] = phi * x[:, t - 1] + eps[:, t]
+        x += rng.randn(nchain, 1, 3) * 0.1
+        R, neff = utils.convergence_stats(x, thin_rate=thin, warm_up_num=warm)
+        out.update({"chain_" + tag: x, "thin_" + tag: thin, "warm_" + tag: warm, "R_" + tag: R, "neff_" + tag: neff})
+    return out
+
+
 def main():
     only = sys.argv[1:]
     if only:
-        makers = {"light_hess": light_hess, "best_dt": best_dt, "rj_chain": rj_chain}
+        makers = {"light_hess": light_hess, "best_dt": best_dt, "rj_chain": rj_chain, "conv_stats": conv_stats}
         for name in only:
             arrays = makers[name]()
             path = os.path.join(HERE, name + ".npz")
@@ -383,6 +400,7 @@ def main():
         "light_hess": light_hess(),
         "best_dt": best_dt(),
         "rj_chain": rj_chain(),
+        "conv_stats": conv_stats(),
     }
     for name, arrays in cases.items():
         path = os.path.join(HERE, name + ".npz")

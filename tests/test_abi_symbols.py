@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, n), "library does not export %s" % n
         assert n in _capi.SIGNATURES, "ctypes binding lacks %s" % n
     assert set(_capi.SIGNATURES) <= set(names), sorted(set(_capi.SIGNATURES) - set(names))
-    assert lib.srhmc_abi_version() == _capi.ABI_VERSION == 2
+    assert lib.srhmc_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header():
