@@ -103,7 +103,7 @@ __global__ void big_bin_kernel(const BigParams P, const TileSrc S, int ntx, int 
 #define SRHMC_TILE_EARLY_LOAD 0
 #endif
 #ifndef SRHMC_TILE_MIN_CTAS
-#define SRHMC_TILE_MIN_CTAS 3
+#define SRHMC_TILE_MIN_CTAS 4
 #endif
 
 constexpr int kTabPad = 4;                 // zero guard entries on each side of a 32-entry factor table
@@ -111,17 +111,19 @@ constexpr int kTabLen = 32 + 2 * kTabPad;  // a thread reads 4 consecutive entri
 
 // Factor tables of one (star, tile) pair, built by one warp with two warp-wide exponentials (exp_neg: the kernels'
 // own branch-free FP64 exponential, fastmath.cuh) and used by BOTH the render and the gather phase:
-//   rowf[kTabPad + k] = (ex_k, ex_k dx_k)        for row  ia + k of the box,  ex = exp(-(i+.5-x)^2/2s^2)
-//   colf[kTabPad + k] = (f ey_k, f ey_k dy_k)    for column ja + k,           ey = norm exp(-(j+.5-y)^2/2s^2)
-// zero past the box and in the guards.
+//   rowf[kTabPad + k] = ex_k      for row  ia + k of the box,  ex = exp(-(i+.5-x)^2/2s^2)
+//   colf[kTabPad + k] = f ey_k    for column ja + k,           ey = norm exp(-(j+.5-y)^2/2s^2)
+// zero past the box and in the guards; (dx0, dy0) = offsets of the box's first row / column from the star, from which
+// the gather phase forms ex dx and ey dy.
 struct PairTab {
-    double2 rowf[kTabLen];
-    double2 colf[kTabLen];
+    double rowf[kTabLen];
+    double colf[kTabLen];
+    double dx0, dy0;
 };
 
 struct TileSmem {
     double rho[kTile][kTile];          // 32 KB
-    PairTab tab[kTileChunk];           // 1280 B each
+    PairTab tab[kTileChunk];           // 656 B each
     int2 list[kTileMaxList];           // sorted pair records
     int box[kTileChunk][4];
     double red[32];
@@ -135,14 +137,24 @@ __device__ __forceinline__ void build_pair_tab(const BigParams& P, const TileSrc
     const double f = src[0], x = src[1], y = src[2];
     const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
     const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
-    const double ex = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
-    const double fy = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
-    T.rowf[kTabPad + lane] = make_double2(ex, ex * dx);
-    T.colf[kTabPad + lane] = make_double2(fy, fy * dy);
-    if (lane == 0 && box) {
-        box[0] = ia; box[1] = ib; box[2] = ja; box[3] = jb;
+    T.rowf[kTabPad + lane] = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
+    T.colf[kTabPad + lane] = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
+    if (lane == 0) {
+        T.dx0 = dx;
+        T.dy0 = dy;
+        if (box) {
+            box[0] = ia; box[1] = ib; box[2] = ja; box[3] = jb;
+        }
     }
 }
+
+// 16-byte asynchronous copy global -> shared (LDGSTS): no registers held while the data are in flight
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // MODE 0: gradient; 1: gradient + pixel potential; 2: mock data -- the rendered model of the tile is Poisson-sampled
 // (poisson.cuh, counter = global pixel index) into Dout and nothing else happens
@@ -165,31 +177,30 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
 
     const int ty = tid >> 4, tx = tid & 15;
     const int pr = 4 * ty, pc = 4 * tx;  // thread owns the 4x4 pixel block at (pr, pc)
-    double d[4][4];
-    auto load_data = [&]() {
+    // The tile's data pixels first: every thread copies its own 4x4 block asynchronously straight into the rho buffer, so
+    // the HBM latency is covered by the list sort, the table build and the render; the residual later overwrites the
+    // block in place (a thread only ever touches its own block before the barrier that precedes the gather).
+    if (MODE != 2) {
         const bool vec = ((P.C & 1) == 0) && (pc + 3 < vc);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int li = pr + a;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) d[a][b] = 0.0;
             if (li < vr) {
                 const double* row = D + (size_t)(r0 + li - P.row0) * P.C + c0 + pc;
                 if (vec) {
-                    const double2 d0 = __ldg(reinterpret_cast<const double2*>(row));
-                    const double2 d1 = __ldg(reinterpret_cast<const double2*>(row + 2));
-                    d[a][0] = d0.x; d[a][1] = d0.y; d[a][2] = d1.x; d[a][3] = d1.y;
+                    cp_async16(&sm.rho[li][pc], row);
+                    cp_async16(&sm.rho[li][pc + 2], row + 2);
                 } else {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (pc + b < vc) d[a][b] = __ldg(row + b);
+                    for (int b = 0; b < 4; ++b) sm.rho[li][pc + b] = (pc + b < vc) ? __ldg(row + b) : 0.0;
                 }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) sm.rho[li][pc + b] = 0.0;
             }
         }
-    };
-#if SRHMC_TILE_EARLY_LOAD
-    load_data();  // the tile's data pixels issued first, so that the loads fly while the model is rendered
-#endif
+        cp_async_commit();
+    }
 
     // ---- the tile's pair list, sorted by star id so that every sum below has a fixed order
     list += (size_t)blockIdx.x * kTileMaxList;
@@ -200,8 +211,8 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     // guard entries of the factor tables stay zero for the whole launch; the 32 body entries are rewritten per pair
     for (int k = tid; k < kTileChunk * 4 * kTabPad; k += kTileThreads) {
         const int pair = k / (4 * kTabPad), e = k % (4 * kTabPad), side = e / kTabPad, g = e % kTabPad;
-        double2* t = (side & 1) ? sm.tab[pair].colf : sm.tab[pair].rowf;
-        t[(side & 2) ? kTabPad + 32 + g : g] = make_double2(0.0, 0.0);
+        double* t = (side & 1) ? sm.tab[pair].colf : sm.tab[pair].rowf;
+        t[(side & 2) ? kTabPad + 32 + g : g] = 0.0;
     }
     if (WANT_V && tid < kLogTableSize) {
         // (rc_k, -ln rc_k) with rc_k ~ 1/(bin centre): ln x = e ln2 - ln rc_k + log1p(m rc_k - 1) is an identity for the
@@ -235,9 +246,9 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         for (int s = 0; s < nc; ++s) {
             const int ia = sm.box[s][0], ja = sm.box[s][2];
             if (pr + 3 < ia || pr > sm.box[s][1] || pc + 3 < ja || pc > sm.box[s][3]) continue;
-            const double2* te = &sm.tab[s].rowf[kTabPad + pr - ia];  // pr - ia in [-3, 31]: inside the padded table
-            const double2* tf = &sm.tab[s].colf[kTabPad + pc - ja];
-            const double ex[4] = {te[0].x, te[1].x, te[2].x, te[3].x}, fy[4] = {tf[0].x, tf[1].x, tf[2].x, tf[3].x};
+            const double* te = &sm.tab[s].rowf[kTabPad + pr - ia];  // pr - ia in [-3, 31]: inside the padded table
+            const double* tf = &sm.tab[s].colf[kTabPad + pc - ja];
+            const double ex[4] = {te[0], te[1], te[2], te[3]}, fy[4] = {tf[0], tf[1], tf[2], tf[3]};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -260,20 +271,21 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     }
 
     // ---- residual into the shared tile; pixel potential of the owned rows
-#if !SRHMC_TILE_EARLY_LOAD
-    load_data();
-#endif
+    cp_async_wait_all();  // this thread's own copies (it reads nothing else here)
     double v = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int li = pr + a, gi = r0 + li;
         const bool own = WANT_V && li < vr && gi >= P.own_lo && gi < P.own_hi;
+        const double2 d0 = *reinterpret_cast<const double2*>(&sm.rho[li][pc]);
+        const double2 d1 = *reinterpret_cast<const double2*>(&sm.rho[li][pc + 2]);
+        const double d[4] = {d0.x, d0.y, d1.x, d1.y};
         double rho[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const bool in = li < vr && pc + b < vc;
-            rho[b] = in ? fma(d[a][b], rcp_fast(lam[a][b]), -1.0) : 0.0;
-            if (WANT_V && own && pc + b < vc) v += lam[a][b] - d[a][b] * (lam[a][b] >= 2.3e-308 ? log_pos(lam[a][b], sm.ltab) : CUDART_NAN);  // ln of a non-positive model is NaN, as in NumPy
+            rho[b] = in ? fma(d[b], rcp_fast(lam[a][b]), -1.0) : 0.0;
+            if (WANT_V && own && pc + b < vc) v += lam[a][b] - d[b] * (lam[a][b] >= 2.3e-308 ? log_pos(lam[a][b], sm.ltab) : CUDART_NAN);  // ln of a non-positive model is NaN, as in NumPy
         }
         *reinterpret_cast<double2*>(&sm.rho[li][pc]) = make_double2(rho[0], rho[1]);
         *reinterpret_cast<double2*>(&sm.rho[li][pc + 2]) = make_double2(rho[2], rho[3]);
@@ -299,21 +311,23 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
             __syncwarp();
         }
         const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
-        const double2 cf = T.colf[kTabPad + lane];               // (f ey, f ey dy) of this lane's column, 0 past the box
+        const double fy = T.colf[kTabPad + lane];                // f ey of this lane's column, 0 past the box
+        const double dyl = T.dy0 + (double)lane;
         const double* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
-        const double2* rf = &T.rowf[kTabPad];
-        double a0 = 0.0, a1 = 0.0;
+        const double* rf = &T.rowf[kTabPad];
+        double a0 = 0.0, a1 = 0.0, dxk = T.dx0;
         const int nr = ib - ia + 1;
 #pragma unroll 4
         for (int k = 0; k < nr; ++k) {
-            const double2 e = rf[k];
+            const double e = rf[k];
             const double rho = col[k * kTile];
-            a0 = fma(rho, e.x, a0);
-            a1 = fma(rho, e.y, a1);
+            a0 = fma(rho, e, a0);
+            a1 = fma(rho * e, dxk, a1);
+            dxk += 1.0;
         }
         // three warp sums with six shuffles: fold the values onto lane groups first
         if (ja + lane > jb) a0 = a1 = 0.0;  // lanes past the box read a clamped column
-        double sf = cf.x * a0, sx = cf.x * a1, sy = cf.y * a0, sz = 0.0;
+        double sf = fy * a0, sx = fy * a1, sy = (fy * dyl) * a0, sz = 0.0;
         {
             const bool hi = lane & 16;
             const double k0 = hi ? sy : sf, k1 = hi ? sz : sx, t0 = hi ? sf : sy, t1 = hi ? sx : sz;
