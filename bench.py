@@ -73,10 +73,13 @@ def workload_c2(chains_per_mag, seed):
                **{n: k[n] for n in ("psf_fwhm_pix", "B_count", "f_lim", "f_low", "g0", "g1", "g2")})
     run = dict(nsteps=10, dt=0.2, g_ff2=1.0, delta=1e-6, counter_max=1000, f_pos=True)
     flops_per_unit = 9 * R * C + 2 * R * C  # F = 9 P^2 + 2 A with P^2 = A = R*C (full-image PSF)
-    # rows the kernel actually visits for a star at the image centre: |i + .5 - x| <= wcut (ex_i >= 2^-50)
-    wcut = np.sqrt(50 * np.log(2.0) * 2.0) * k["psf_fwhm_pix"] / 2.354
+    # pixels the kernel actually visits for a star at the image centre: rows with |i + .5 - x| <= wcut (ex_i >= 2^-46)
+    # times the 24-column window of the one-star kernel (chain_kernels.cu: use_column_window)
+    sigma = k["psf_fwhm_pix"] / 2.354
+    wcut = np.sqrt(46 * np.log(2.0) * 2.0) * sigma
     rows_kept = int(min(R, np.floor(15.5 + wcut) + 1) - max(0, np.ceil(15.5 - wcut)))
-    flops_executed = 9 * rows_kept * C + 2 * R * C
+    cols_kept = 24 if 144.0 / (2 * sigma**2) >= 46 * np.log(2.0) else C
+    flops_executed = 9 * rows_kept * cols_kept + 2 * R * C
     return dict(name="c2_one_star_32x32", D=D, q0=q0, cfg=cfg, run=run, nstars=1, flops_per_unit=flops_per_unit,
                 flops_executed_per_unit=flops_executed,
                 desc="%d mags x %d one-star 32x32 chains" % (len(MAGS), chains_per_mag))

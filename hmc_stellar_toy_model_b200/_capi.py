@@ -166,6 +166,8 @@ SIGNATURES = {
     "srhmc_gen_mock_data": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, C.c_uint64, C.c_int64, c_double_p]),
     "srhmc_convergence_stats": (C.c_int, [C.c_int32, c_double_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, c_double_p, c_double_p]),
+    "srhmc_find_peaks_descend": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                           c_uint8_p, c_int32_p]),
     "srhmc_run_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "srhmc_eval": (C.c_int, [C.c_void_p, c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_double,
                              c_double_p, c_double_p, c_double_p, c_double_p]),

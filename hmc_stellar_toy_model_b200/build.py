@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libstellar_rhmc.so")
 SOURCES = ["stellar_rhmc.cu", "field_kernels_f64.cu", "field_kernels_f32.cu", "chain_kernels.cu", "ls_kernels.cu", "big_field.cu",
-           "misc_kernels.cu", "mock_kernels.cu", "stats_kernels.cu"]
+           "misc_kernels.cu", "mock_kernels.cu", "stats_kernels.cu", "peaks_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c"]
 LINK_FLAGS = ARCH + ["-shared", "-Xcompiler", "-fPIC"]

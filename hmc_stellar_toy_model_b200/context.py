@@ -116,6 +116,17 @@ class RHMCContext:
         check(self._lib.srhmc_gen_mock_data(self._h, dptr(q), iptr(ns), int(seed), int(field_id_base), dptr(out)))
         return out
 
+    def find_peaks_descend(self, q_seed, nstep, dt_f_coeff, dt_xy_coeff, f_lim):
+        """Independent gradient descent of every seed [n,3] on data image 0 (find_peaks, samplers.py:196-226).
+        Returns (q [n,3], alive [n] bool, steps [n])."""
+        q = np.array(as_f64(q_seed).reshape(-1, 3), copy=True)
+        n = len(q)
+        alive = np.zeros(n, dtype=np.uint8)
+        steps = np.zeros(n, dtype=np.int32)
+        check(self._lib.srhmc_find_peaks_descend(self._h, dptr(q), n, int(nstep), float(dt_f_coeff), float(dt_xy_coeff),
+                                                 float(f_lim), bptr(alive), iptr(steps)))
+        return q, alive.astype(bool), steps
+
     def run_stats(self, n_groups=1, thin_rate=5, warm_up_num=0):
         """(R, n_eff) [n_groups, S] of utils.convergence_stats over the q_chain of the last launched run, computed
         from the chains still resident on the device (no chain download needed)."""

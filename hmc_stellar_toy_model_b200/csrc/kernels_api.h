@@ -54,6 +54,10 @@ int poisson_launch(cudaStream_t stream, const double* lam, double* D, size_t n, 
 int conv_stats_launch(cudaStream_t stream, const double* X, long long rows, int d, int n_groups, int cpg, int thin, int warm,
                       double* means, double* R, double* neff);
 
+// gradient-descent leg of lightsource_gym.find_peaks (peaks_kernels.cu): one warp per seed, image 0 of the context
+int peaks_launch(cudaStream_t stream, const FieldParams& P, const double* D, int n, int nstep, double dt_f_coeff,
+                 double dt_xy_coeff, double f_lim, double* q, unsigned char* alive, int* steps);
+
 // FMA-chain roofline microbenchmark
 int fma_peak_run(int precision, int sms, double* tflops, float* ms);
 

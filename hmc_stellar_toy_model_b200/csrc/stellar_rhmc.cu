@@ -1112,6 +1112,35 @@ int srhmc_run_stats(srhmc_ctx* c, int32_t n_groups, int32_t thin_rate, int32_t w
     return 0;
 }
 
+int srhmc_find_peaks_descend(srhmc_ctx* c, double* q_seed, int32_t n, int32_t nstep, double dt_f_coeff, double dt_xy_coeff,
+                             double f_lim, uint8_t* alive, int32_t* steps_taken) {
+    if (!c || !q_seed || !alive || n < 0 || nstep < 0) return fail(SRHMC_ERR_INVALID, "bad argument");
+    if (!c->have_data) return fail(SRHMC_ERR_STATE, "srhmc_set_data has not been called");
+    if (c->cfg.precision != 64) return fail(SRHMC_ERR_INVALID, "find_peaks runs on FP64 contexts");
+    if (n == 0) return 0;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    DevBuf q, a, st;
+    int rc = q.ensure((size_t)n * 24);
+    if (!rc) rc = a.ensure((size_t)n);
+    if (!rc) rc = st.ensure((size_t)n * 4);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(q.ptr, q_seed, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream);
+    if (!rc && e == cudaSuccess)
+        e = (cudaError_t)peaks_launch(c->stream, c->P, c->D.as<double>(), n, nstep, dt_f_coeff, dt_xy_coeff, f_lim, q.as<double>(),
+                                      a.as<unsigned char>(), st.as<int>());
+    if (!rc && e == cudaSuccess) {
+        c->launches += 1;
+        e = cudaMemcpyAsync(q_seed, q.ptr, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(alive, a.ptr, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (!rc && e == cudaSuccess && steps_taken) e = cudaMemcpyAsync(steps_taken, st.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    q.release(); a.release(); st.release();
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(SRHMC_ERR_CUDA, "find_peaks descent failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 int srhmc_philox_draws(srhmc_ctx* c, uint64_t seed, int32_t niter, double* normals, double* lnu) {
     return srhmc_philox_draws_ids(c, seed, niter, 0, 1, normals, lnu);
 }

@@ -390,8 +390,47 @@ class lightsource_gym(object):
                     dt_xy = dt[1] * 10
             self.dt[3 * l:3 * l + 3] = np.array([dt_f, dt_xy, dt_xy])
 
-    def find_peaks(self, *args, **kwargs):
-        raise NotImplementedError("find_peaks (mode finding) is not part of the B200 path (SURVEY.md 8f, next #2)")
+    def find_peaks(self, linear_pix_density=0.2, dr_tol=1., dmag_tol=0.5, mag_lim=None, Nstep=1000, dt_f_coeff=1e-1,
+                   dt_xy_coeff=1e-1, no_perturb=False):
+        """Likely star positions (samplers.py:129-254): seeds on a jittered grid (np.random.randn in the reference's
+        order), independent gradient descent of all seeds in ONE device launch, then the greedy merge of near-duplicates
+        on the host.  Result in self.q_seed."""
+        if self.num_rows is None or self.D is None:
+            print("The image must be specified first.")
+            assert False
+        if mag_lim is None:
+            mag_lim = self.mB - 1.
+        f_lim = mag2flux(mag_lim) * self.flux_to_count
+        f_seed = mag2flux(mag_lim - 0.5) * self.flux_to_count
+        n_row = int(linear_pix_density * self.num_rows) - 1
+        n_col = int(linear_pix_density * self.num_cols) - 1
+        spacing = 1 / float(linear_pix_density)
+        q_seed = np.zeros((n_row * n_col, 3), dtype=float)
+        for i in range(n_row):
+            for j in range(n_col):
+                x = spacing * (i + 0.5 + 0.1 * np.random.randn())
+                y = spacing * (j + 0.5 + 0.1 * np.random.randn())
+                q_seed[i * n_row + j] = np.array([f_seed, x, y])  # row count as stride, as upstream (samplers.py:176)
+        if no_perturb:
+            self.q_seed = q_seed
+            return
+        q_seed, alive, _ = self._device_ctx(1).find_peaks_descend(q_seed, Nstep, dt_f_coeff, dt_xy_coeff, f_lim)
+        q_seed = q_seed[alive]
+        if q_seed.shape[0] == 0:
+            self.q_seed = q_seed
+            print("No peaks were found.")
+            return
+        kept = []
+        while True:  # greedy reduction (samplers.py:234-252)
+            ref = q_seed[0]
+            kept.append(ref)
+            q_seed = q_seed[1:, :]
+            dist_sq = (q_seed[:, 1] - ref[1]) ** 2 + (q_seed[:, 2] - ref[2]) ** 2
+            dmag = np.abs(flux2mag(ref[0] / self.flux_to_count) - flux2mag(q_seed[:, 0] / self.flux_to_count))
+            q_seed = q_seed[np.logical_or(dist_sq > dr_tol ** 2, dmag > dmag_tol)]
+            if q_seed.shape[0] == 0:
+                break
+        self.q_seed = np.vstack(kept)
 
     def display_data(self, *args, **kwargs):
         return None

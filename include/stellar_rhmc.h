@@ -249,6 +249,14 @@ int srhmc_hessian(srhmc_ctx* ctx, const double* q, const double* p, const int32_
 int srhmc_eval_background(srhmc_ctx* ctx, const double* q, const int32_t* nstars, const double* background, double* V,
                           double* grad);
 
+/* Gradient-descent leg of lightsource_gym.find_peaks (samplers.py:196-226): each of the n seeds q_seed [n,3] (f, x, y;
+ * updated in place) descends independently on the context's data image (field 0) over a pure-background model with the
+ * steps dt_f = f dt_f_coeff, dt_xy = dt_xy_coeff / f, until |dV/V| < 1e-9, nstep steps, or f < f_lim (alive[i] = 0).
+ * V_single / dVdq_single (samplers.py:77-127) are evaluated device-side, one warp per seed, one launch for all seeds.
+ * steps_taken [n] may be NULL.  The grid seeding and the final merge stay with the caller (samplers.py:160-178, 234-252). */
+int srhmc_find_peaks_descend(srhmc_ctx* ctx, double* q_seed, int32_t n, int32_t nstep, double dt_f_coeff, double dt_xy_coeff,
+                             double f_lim, uint8_t* alive, int32_t* steps_taken);
+
 /* Split-chain Gelman-Rubin statistic and effective sample size per variable.  Replaces utils.convergence_stats (with
  * utils.variogram), utils.py:86-188, including its definitions of W (mean of the within-chain standard deviations) and
  * of the autocorrelation cut-off.  q_chain [n_chains, n_iter, d] on the host; the chains form n_groups consecutive groups

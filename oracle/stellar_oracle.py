@@ -801,6 +801,75 @@ def ls_single(L: LightSetup, q_single, model_data):
     return -np.sum(L.D * np.log(lam) - lam), g
 
 
+
+def ls_find_peaks(L: LightSetup, jitter, linear_pix_density=0.2, dr_tol=1.0, dmag_tol=0.5, mag_lim=None, Nstep=1000,
+                  dt_f_coeff=1e-1, dt_xy_coeff=1e-1, no_perturb=False, return_all=False):
+    """lightsource_gym.find_peaks (samplers.py:129-254): seeds on a jittered grid, independent gradient descent of every
+    seed on a pure-background model until V changes by less than 1e-9 relative (seeds fainter than f_lim disappear),
+    then greedy merging of seeds closer than dr_tol pixels and dmag_tol magnitudes.  `jitter` [Nobjs_row*Nobjs_col, 2]
+    are the np.random.randn draws in the reference's order (x then y per seed, row-major over the grid).
+    return_all: also the per-seed descent results (q, alive, steps) before the merge."""
+    if mag_lim is None:
+        mag_lim = L.mB - 1.0
+    f_lim = mag2flux(mag_lim) * L.flux_to_count
+    f_seed = mag2flux(mag_lim - 0.5) * L.flux_to_count
+    n_row = int(linear_pix_density * L.num_rows) - 1
+    n_col = int(linear_pix_density * L.num_cols) - 1
+    spacing = 1 / float(linear_pix_density)
+    q_seed = np.zeros((n_row * n_col, 3))
+    t = 0
+    for i in range(n_row):
+        for j in range(n_col):
+            # samplers.py:176: the flat index uses the ROW count as stride (harmless for square grids)
+            q_seed[i * n_row + j] = [f_seed, spacing * (i + 0.5 + 0.1 * jitter[t, 0]), spacing * (j + 0.5 + 0.1 * jitter[t, 1])]
+            t += 1
+    if no_perturb:
+        return q_seed
+    model_data = np.ones((L.num_rows, L.num_cols)) * L.B_count
+    alive = np.ones(len(q_seed), dtype=bool)
+    steps = np.zeros(len(q_seed), dtype=int)
+    for idx in range(len(q_seed)):
+        f, x, y = q_seed[idx]
+        V_prev, _ = ls_single(L, [f, x, y], model_data)
+        for i in range(Nstep):
+            _, g = ls_single(L, [f, x, y], model_data)
+            dt_f, dt_xy = f * dt_f_coeff, dt_xy_coeff / f
+            f -= g[0] * dt_f
+            x -= g[1] * dt_xy
+            y -= g[2] * dt_xy
+            steps[idx] = i + 1
+            if f < f_lim:
+                alive[idx] = False
+                break
+            V_cur, _ = ls_single(L, [f, x, y], model_data)
+            if np.abs((V_cur - V_prev) / V_prev) < 1e-9:
+                break
+            V_prev = V_cur
+        q_seed[idx] = [f, x, y]
+    descended = q_seed.copy()
+    merged = merge_peaks(L, q_seed[alive], dr_tol, dmag_tol)
+    return (merged, descended, alive, steps) if return_all else merged
+
+
+def merge_peaks(L: LightSetup, q_seed, dr_tol=1.0, dmag_tol=0.5):
+    """Greedy reduction of find_peaks (samplers.py:234-252): keep the first seed, drop every later one within dr_tol
+    pixels AND dmag_tol magnitudes of it, repeat on the rest."""
+    if q_seed.shape[0] == 0:
+        return q_seed
+    final = []
+    while True:
+        ref = q_seed[0]
+        final.append(ref)
+        q_seed = q_seed[1:, :]
+        dist_sq = (q_seed[:, 1] - ref[1]) ** 2 + (q_seed[:, 2] - ref[2]) ** 2
+        mag_seed = flux2mag(q_seed[:, 0] / L.flux_to_count)
+        mag_ref = flux2mag(ref[0] / L.flux_to_count)
+        q_seed = q_seed[np.logical_or(dist_sq > dr_tol**2, np.abs(mag_ref - mag_seed) > dmag_tol)]
+        if q_seed.shape[0] == 0:
+            break
+    return np.vstack(final)
+
+
 def ls_trial(L: LightSetup, q_start, model_data, dt, normals, steps, lnu, zero_xy):
     """One acceptance-rate trial of HMC_find_best_dt (samplers.py:327-370): single-star HMC on model_data whose
     leapfrog kicks all three momenta with the scalar FLUX gradient (dVdq_single's default f_only=True).

@@ -357,6 +357,29 @@ def rj_chain(seed=77, niter=60, nobj=20, nmodel=5, nsteps=5, dt=5e-2):
                 **gym_state(gym))
 
 
+def find_peaks(seed=41):
+    """lightsource_gym.find_peaks (samplers.py:129-254) on a 32x32 image with three stars; the jitter draws are recorded."""
+    np.random.seed(seed)
+    gym = smp.lightsource_gym()
+    gym.num_rows = gym.num_cols = 32
+    fl = lambda m: utils.mag2flux(m) * gym.flux_to_count
+    q_true = np.array([[fl(18.0), 9.3, 11.7], [fl(19.5), 21.2, 20.4], [fl(20.5), 24.6, 7.9]])
+    gym.gen_mock_data(q_true=q_true)
+    state = np.random.get_state()
+    n_side = int(0.25 * 32) - 1
+    jitter = np.random.randn(n_side * n_side, 2)
+    np.random.set_state(state)
+    with ref_shim.quiet():
+        gym.find_peaks(linear_pix_density=0.25, Nstep=400, dt_f_coeff=1e-1, dt_xy_coeff=1e-1)
+    q_final = np.copy(gym.q_seed)
+    np.random.set_state(state)
+    with ref_shim.quiet():
+        gym.find_peaks(linear_pix_density=0.25, no_perturb=True)
+    return dict(D=gym.D, q_true=q_true, jitter=jitter, q_seed0=np.copy(gym.q_seed), q_seed=q_final, seed=seed,
+                next_uniform=np.random.random(1), B_count=np.float64(gym.B_count), PSF_FWHM_pix=np.float64(gym.PSF_FWHM_pix),
+                mB=np.float64(gym.mB), flux_to_count=np.float64(gym.flux_to_count))
+
+
 def conv_stats():
     """utils.convergence_stats (utils.py:86-167, Python-2 division restored by the shim) on AR(1) chains with different
     autocorrelation per variable, and on chains with a short and an odd thinned length."""
@@ -377,7 +400,7 @@ def conv_stats():
 def main():
     only = sys.argv[1:]
     if only:
-        makers = {"light_hess": light_hess, "best_dt": best_dt, "rj_chain": rj_chain, "conv_stats": conv_stats}
+        makers = {"light_hess": light_hess, "best_dt": best_dt, "rj_chain": rj_chain, "conv_stats": conv_stats, "find_peaks": find_peaks}
         for name in only:
             arrays = makers[name]()
             path = os.path.join(HERE, name + ".npz")
@@ -401,6 +424,7 @@ def main():
         "best_dt": best_dt(),
         "rj_chain": rj_chain(),
         "conv_stats": conv_stats(),
+        "find_peaks": find_peaks(),
     }
     for name, arrays in cases.items():
         path = os.path.join(HERE, name + ".npz")

@@ -38,8 +38,11 @@ def test_lightsource_call_surface():
                        [0.035997054345069765, 0.45235232653061236, 0.008141675878296744], rtol=1e-12)
     g.HMC_find_best_dt(np.array([[1000.0, 16.0, 16.0]]), default=True, dt_f_coeff=0.05, dt_xy_coeff=2.0)
     assert np.allclose(g.dt, [50.0, 0.002, 0.002]) and g.d == 3
-    with pytest.raises(NotImplementedError):
-        g.find_peaks()
+    sig = inspect.signature(m.lightsource_gym.find_peaks)
+    assert list(sig.parameters) == ["self", "linear_pix_density", "dr_tol", "dmag_tol", "mag_lim", "Nstep", "dt_f_coeff",
+                                    "dt_xy_coeff", "no_perturb"]
+    with pytest.raises(AssertionError):
+        g.find_peaks()  # no image yet (samplers.py:152-154)
 
 
 @pytest.mark.gpu

@@ -245,3 +245,58 @@ def test_run_stats_on_resident_chains():
         assert relerr(Rg[g], R0) < 1e-11 and relerr(ng[g], n0) < 1e-8
     # positions mix (R ~ 1); the flux means differ between chains because every chain has its own data realisation
     assert np.all(np.isfinite(Rg)) and np.all(Rg[:, 1:] < 1.2) and np.all(ng > 0)
+
+
+# ------------------------------------------------------------------------------------------------------- find_peaks
+def _peaks_setup():
+    from helpers import golden
+
+    g = golden("find_peaks")
+    L = so.LightSetup(num_rows=32, num_cols=32)
+    L.D = g["D"]
+    return g, L
+
+
+def test_find_peaks_oracle_matches_golden():
+    """Fixture recorded from lightsource_gym.find_peaks (samplers.py:129-254) with its own jitter draws."""
+    g, L = _peaks_setup()
+    assert np.array_equal(so.ls_find_peaks(L, g["jitter"], linear_pix_density=0.25, no_perturb=True), g["q_seed0"])
+    got = so.ls_find_peaks(L, g["jitter"], linear_pix_density=0.25, Nstep=400)
+    assert got.shape == g["q_seed"].shape and relerr(got, g["q_seed"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_find_peaks_gym_replays_reference_script():
+    """The drop-in gym with the reference's seed: same jitter draws consumed from the global stream, same surviving and
+    merged peaks, positions and fluxes to 1e-6 (the |dV/V| < 1e-9 stop test may fire one step apart)."""
+    from hmc_stellar_toy_model_b200 import samplers as m
+
+    g, L = _peaks_setup()
+    np.random.seed(int(g["seed"]))
+    gym = m.lightsource_gym()
+    gym.num_rows = gym.num_cols = 32
+    gym.gen_mock_data(q_true=g["q_true"])
+    assert np.array_equal(gym.D, g["D"])
+    state = np.random.get_state()
+    gym.find_peaks(linear_pix_density=0.25, Nstep=400, dt_f_coeff=1e-1, dt_xy_coeff=1e-1)
+    assert gym.q_seed.shape == g["q_seed"].shape
+    assert relerr(gym.q_seed, g["q_seed"]) < 1e-6
+    np.random.set_state(state)
+    gym.find_peaks(linear_pix_density=0.25, no_perturb=True)
+    assert np.array_equal(gym.q_seed, g["q_seed0"])
+    assert np.random.random(1)[0] == g["next_uniform"][0]  # the global stream is where the reference left it
+
+
+@pytest.mark.gpu
+def test_find_peaks_descent_matches_oracle_per_seed():
+    g, L = _peaks_setup()
+    ctx, _ = _ctx(1, 32, 32, 1, B_count=L.B_count, f_lim=0.0, f_low=1.0, g0=1.0, g1=1.0, g2=1.0, enable_hessian=True)
+    ctx.set_data(L.D)
+    f_lim = so.mag2flux(L.mB - 1.0) * L.flux_to_count
+    _, want, alive0, steps0 = so.ls_find_peaks(L, g["jitter"], linear_pix_density=0.25, Nstep=400, return_all=True)
+    q, alive, steps = ctx.find_peaks_descend(g["q_seed0"], 400, 1e-1, 1e-1, f_lim)
+    assert np.array_equal(alive, alive0)
+    assert np.mean(steps == steps0) > 0.9 and np.max(np.abs(steps - steps0)) <= 1
+    same = steps == steps0
+    assert relerr(q[same & alive], want[same & alive]) < 1e-9
+    assert relerr(q[alive], want[alive]) < 1e-6
