@@ -523,8 +523,10 @@ def run_big(args):
                     "d2h_bytes_per_step": int(3 * wl["q0"].nbytes // max(1, world)), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                         "peak_source": peak_src, "bytes_per_unit": wl["bytes_per_unit"], "traffic": None,
-                         "note": "per GPU; algorithmic bytes = the data strip read once per gradient + star state"},
+                         "peak_source": peak_src, "bytes_per_unit": wl["bytes_per_unit"],
+                         "traffic": traffic_from_profile("c5_tiled_field_%dx%d_%dstars" % (rows, cols, nstars)) if world == 1 else None,
+                         "note": "per GPU, over the WHOLE leapfrog step (tile kernel + the three per-star kernels); algorithmic "
+                                 "bytes = the data strip read once per gradient + star state"},
             "cpu_baseline": None, "accept_rate": acc,
         }
         print(json.dumps(out))
