@@ -453,7 +453,13 @@ def run_big(args):
     stream = torch.cuda.Stream()   # kernels, NCCL collectives and the timing events all ride on this stream
     torch.cuda.set_stream(stream)
     strip.set_stream(stream.cuda_stream)
-    eng = bf.BigFieldRHMC([strip], bf.TorchDistComm(dist) if world > 1 else bf.NoComm())
+    if world == 1:
+        comm = bf.NoComm()
+    elif args.comm == "nccl":
+        comm = bf.TorchDistComm(dist)   # NCCL collectives issued by the caller between the phases (eager launches)
+    else:
+        comm = bf.PeerComm([strip], dist)  # the library's own exchange kernels over NVLink peer memory; graph replay
+    eng = bf.BigFieldRHMC([strip], comm)
 
     def barrier():
         if world > 1:
@@ -516,8 +522,11 @@ def run_big(args):
                        "patch_radius": rad, "halo_rows": halo, "rng": "device Philox4x32-10",
                        "l2": "data window of %.0f MB per rank exceeds nothing smaller than L2 only when > 126 MB; "
                              "no flush between launches" % (wl["D"].nbytes / 1e6),
-                       "parallelism": "row strips over %d GPU(s); per step: 1 all-gather of boundary stars, 2 max "
-                                      "all-reduces; per iteration: 2 sum all-reduces of 8 doubles (NCCL)" % world},
+                       "parallelism": "row strips over %d GPU(s); per step: 1 exchange of boundary stars with the two "
+                                      "neighbours, 2 max all-reduces; per iteration: 2 sum all-reduces of 8 doubles (%s)"
+                                      % (world, "none: single GPU" if world == 1 else
+                                         ("own kernels over NVLink peer memory, CUDA-graph replay" if args.comm == "peer"
+                                          else "NCCL via torch.distributed, eager"))},
             "clocks": clocks,
             "e2e": {"value": units * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(wl["D"].nbytes + wl["q0"].nbytes),
                     "d2h_bytes_per_step": int(3 * wl["q0"].nbytes // max(1, world)), "steps": e2e_steps},
@@ -573,6 +582,8 @@ def main():
     ap.add_argument("--cols", type=int, default=8192)
     ap.add_argument("--stars", type=float, default=100000, help="c5: stars (per GPU with --weak); 1.49e-3 per pixel")
     ap.add_argument("--weak", action="store_true", help="c5: grow the field with the GPU count")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="c5 on several GPUs: the library's own peer-memory exchange kernels, or NCCL through torch.distributed")
     ap.add_argument("--chains-per-mag", type=int, default=1000)
     ap.add_argument("--fields", type=int, default=592)
     ap.add_argument("--niter", type=int, default=1000)

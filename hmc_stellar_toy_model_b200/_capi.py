@@ -206,6 +206,8 @@ SIGNATURES = {
     "srhmc_big_get_stars": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "srhmc_big_set_momenta": (C.c_int, [C.c_void_p, c_double_p]),
     "srhmc_big_buffers": (C.c_int, [C.c_void_p, C.POINTER(BigBuffers)]),
+    "srhmc_big_comm_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "srhmc_big_comm_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "srhmc_big_set_draws": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32]),
     "srhmc_big_alloc_chains": (C.c_int, [C.c_void_p, C.c_int32]),
     "srhmc_big_read_chains": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_uint8_p,

@@ -178,6 +178,10 @@ class BigFieldStrip:
                                "more often or enlarge the halo" % self.halo)
         if err.value == 2:
             raise RuntimeError("boundary star list overflow: raise max_ghosts")
+        if err.value == 3:
+            raise RuntimeError("more than 1024 stars touch one 64x64 tile: the fused tile evaluation cannot hold the list")
+        if err.value == 4:
+            raise RuntimeError("peer exchange timed out: a rank of the tiling never delivered its contribution")
         return dict(E_chain=E, V_chain=V, T_chain=T, A_chain=A, n_accepted=float(nacc.value))
 
     def read_scalars(self):
@@ -187,6 +191,20 @@ class BigFieldStrip:
 
     def phase(self, name, step):
         check(self._lib.srhmc_big_phase(self._h, PHASE[name], C.byref(step)))
+
+    def comm_export(self):
+        """(64-byte CUDA IPC handle, raw device pointer) of this strip's peer-exchange mailbox."""
+        handle = C.create_string_buffer(64)
+        raw = C.c_void_p()
+        check(self._lib.srhmc_big_comm_export(self._h, handle, C.byref(raw)))
+        return handle.raw, raw.value
+
+    def comm_import(self, handles=None, raw_ptrs=None):
+        """Map the mailboxes of all ranks: `handles` = world x 64 bytes (other processes) or `raw_ptrs` = world device
+        pointers (strips of this process)."""
+        hb = None if handles is None else C.create_string_buffer(bytes(handles), 64 * self.world)
+        rp = None if raw_ptrs is None else (C.c_void_p * self.world)(*[int(p) for p in raw_ptrs])
+        check(self._lib.srhmc_big_comm_import(self._h, hb, rp))
 
     def views(self):
         """torch views of the communication buffers (needs torch + CUDA)."""
@@ -238,6 +256,43 @@ class TorchDistComm:
         v = s.views()
         v["gscalars"].copy_(v["scalars"])
         self.dist.all_reduce(v["gscalars"], op=self.dist.ReduceOp.SUM)
+
+
+class PeerComm:
+    """The library's own collectives: exchange kernels over peer-mapped memory (NVLink P2P / CUDA IPC) enqueued by the
+    phases themselves (PFIX_QFIX, QFIX_KICK: max of the fixed-point counts; PACK: boundary lists into the neighbours'
+    buffers; RECORD_E0 / ACCEPT: sum of the energy partials) -- no NCCL call on the path, and one strip per process can
+    replay a captured CUDA graph of an iteration.
+
+    PeerComm(strips)            all strips of the tiling live in this process (each on its OWN stream: the exchange kernels
+                                wait for each other), mailboxes shared by raw device pointers;
+    PeerComm([strip], dist)     one strip per process: the 64-byte IPC handles travel once through
+                                torch.distributed.all_gather_object at set-up."""
+
+    def __init__(self, strips, dist=None):
+        strips = list(strips)
+        self.in_process = dist is None
+        if dist is None:
+            assert len(strips) == strips[0].world, "in-process peer exchange needs every strip of the tiling"
+            ptrs = [s.comm_export()[1] for s in sorted(strips, key=lambda s: s.rank)]
+            for s in strips:
+                s.comm_import(raw_ptrs=ptrs)
+        else:
+            (s,) = strips
+            handle, _ = s.comm_export()
+            handles = [None] * s.world
+            dist.all_gather_object(handles, handle)
+            s.comm_import(handles=b"".join(handles))
+            dist.barrier()
+
+    def max_counters(self, strips):
+        pass
+
+    def gather_ghosts(self, strips):
+        pass
+
+    def sum_scalars(self, strips):
+        pass
 
 
 class LocalComm:
@@ -369,8 +424,11 @@ class BigFieldRHMC:
         self._all("EVAL_V", st0)
         has_sched = schedule_g_ff2 is not None and len(schedule_g_ff2) > 0
         dist_comm = isinstance(self.comm, TorchDistComm)
+        peer_in_process = isinstance(self.comm, PeerComm) and self.comm.in_process and len(self.strips) > 1
         if use_graph is None:
-            use_graph = not has_sched and L >= 3 and not dist_comm
+            use_graph = not has_sched and L >= 3 and not dist_comm and not peer_in_process
+        if use_graph and peer_in_process:
+            raise ValueError("strips that exchange through PeerComm inside one process run on separate streams: no graph")
         if use_graph and dist_comm:
             # measured on 2 x B200 (torch 2.11, NCCL 2.28.9): replaying a graph that contains the captured
             # collectives dead-locked; the tiled path therefore enqueues its phases eagerly

@@ -482,22 +482,55 @@ __global__ void big_restore_v_kernel(double* local_scalars, const double* state,
 }
 
 // boundary stars for the neighbours: list 0 = stars with x < lo_edge (for the rank below), list 1 = x >= hi_edge.
-// Layout per list: [0] = count, then triples.  Order follows the star index (single block, ballot compaction).
-__global__ void big_pack_kernel(int n, const double* q, double lo_edge, double hi_edge, double* send, int cap, int* err) {
+// Layout per list: [0] = count, then triples.  Order follows the star index (deterministic): block b owns the stars
+// [b kPackChunk, (b+1) kPackChunk); a first kernel counts its matches, the second one starts at the sum of the counts of
+// the blocks before it and compacts with warp ballots.
+constexpr int kPackChunk = 1024;
+
+__global__ void big_pack_count_kernel(int n, const double* q, double lo_edge, double hi_edge, int2* counts) {
+    __shared__ int c[2];
+    if (threadIdx.x == 0) c[0] = c[1] = 0;
+    __syncthreads();
+    int lo = 0, hi = 0;
+    const int k1 = min(n, (int)(blockIdx.x + 1) * kPackChunk);
+    for (int k = blockIdx.x * kPackChunk + threadIdx.x; k < k1; k += blockDim.x) {
+        const double x = q[3 * k + 1];
+        lo += x < lo_edge;
+        hi += x >= hi_edge;
+    }
+    if (lo) atomicAdd(&c[0], lo);
+    if (hi) atomicAdd(&c[1], hi);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[blockIdx.x] = make_int2(c[0], c[1]);
+}
+
+__global__ void big_pack_kernel(int n, const double* q, double lo_edge, double hi_edge, const int2* counts, double* send, int cap,
+                                int* err) {
     __shared__ int base[2];
+    __shared__ int wcount[2][32];
+    // exclusive prefix of the block counts
+    int plo = 0, phi = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) {
+        const int2 c = counts[b];
+        plo += c.x;
+        phi += c.y;
+    }
     if (threadIdx.x == 0) base[0] = base[1] = 0;
     __syncthreads();
-    for (int k0 = 0; k0 < n; k0 += blockDim.x) {
+    if (plo) atomicAdd(&base[0], plo);
+    if (phi) atomicAdd(&base[1], phi);
+    __syncthreads();
+    const int k_begin = blockIdx.x * kPackChunk, k_end = min(n, k_begin + kPackChunk);
+    for (int k0 = k_begin; k0 < k_end; k0 += blockDim.x) {
         const int k = k0 + threadIdx.x;
         bool lo = false, hi = false;
         double f = 0, x = 0, y = 0;
-        if (k < n) {
+        if (k < k_end) {
             f = q[3 * k]; x = q[3 * k + 1]; y = q[3 * k + 2];
             lo = x < lo_edge;
             hi = x >= hi_edge;
         }
         // block-wide ordered compaction: per-warp ballots + serial warp offsets
-        __shared__ int wcount[2][32];
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
         if (lane == 0) { wcount[0][w] = __popc(blo); wcount[1][w] = __popc(bhi); }
@@ -519,10 +552,130 @@ __global__ void big_pack_kernel(int n, const double* q, double lo_edge, double h
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) {
         send[0] = (double)min(base[0], cap);
         send[1 + 3 * (size_t)cap] = (double)min(base[1], cap);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ peer exchange
+// Collectives of the tiled field done by our own kernels over peer-mapped memory (NVLink P2P between the GPUs of a node;
+// CUDA IPC between their processes) instead of NCCL: every rank owns one PeerBox that all ranks can address.  A
+// contribution is `payload, then tag = epoch` (system-scope fence in between); the receiver spins on the tag.  Slots are
+// double-buffered by epoch parity: a rank can run at most one exchange ahead of a peer, because finishing exchange k+1
+// needs the peer's k+1 contribution, which the peer sends only after it has consumed exchange k.  Epochs live in device
+// memory and are advanced by the kernels themselves, so a captured CUDA graph of an iteration can be replayed.
+constexpr int kMaxWorld = 16;
+
+struct PeerSlot {                 // one small-vector contribution
+    unsigned long long tag;
+    double v[8];
+    double pad[7];                // 128 bytes
+};
+
+struct PeerHeader {
+    PeerSlot ar[2][kMaxWorld];    // [epoch parity][source rank]
+    unsigned long long gtag[2][2];  // ghost mailboxes [parity][side]: tag
+};
+// ghost mailbox payloads follow the header: [parity][side][list doubles]
+
+struct PeerPtrs {
+    unsigned char* box[kMaxWorld];
+};
+
+__device__ __forceinline__ void peer_publish_tag(unsigned long long* tag, unsigned long long e) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(tag) = e;
+}
+
+// spin until *tag >= e; false (and err flag 4) after ~5 s so that a lost peer cannot hang the GPU; once the flag is up
+// every later wait gives up at once
+__device__ __forceinline__ bool peer_wait_tag(const unsigned long long* tag, unsigned long long e, int* err) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned long long*>(tag) < e) {
+        if (*reinterpret_cast<volatile int*>(err) == 4) return false;
+        if (clock64() - t0 > 10000000000LL) {
+            atomicExch(err, 4);
+            return false;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
+// all-reduce of a small vector: op 0 = max of n ints (in place), op 1 = sum of n doubles (in -> out), rank order
+__global__ void big_xchg_small_kernel(const PeerPtrs peers, int rank, int world, int op, int n, int* ivals, const double* din,
+                                      double* dout, unsigned long long* epoch, int* err) {
+    __shared__ int ok;
+    const unsigned long long e = epoch[0] + 1;
+    const int par = (int)(e & 1);
+    const int t = threadIdx.x;
+    if (t == 0) ok = 1;
+    __syncthreads();
+    if (t < world) {
+        PeerSlot* s = &reinterpret_cast<PeerHeader*>(peers.box[t])->ar[par][rank];
+        for (int k = 0; k < n; ++k) s->v[k] = op == 0 ? (double)ivals[k] : din[k];
+        peer_publish_tag(&s->tag, e);
+        const PeerSlot* mine = &reinterpret_cast<const PeerHeader*>(peers.box[rank])->ar[par][t];
+        if (!peer_wait_tag(&mine->tag, e, err)) ok = 0;
+    }
+    __syncthreads();
+    if (t == 0) {
+        const PeerHeader* h = reinterpret_cast<const PeerHeader*>(peers.box[rank]);
+        if (ok) {
+            for (int k = 0; k < n; ++k) {
+                double acc = __ldcv(&h->ar[par][0].v[k]);
+                for (int r = 1; r < world; ++r) {
+                    const double x = __ldcv(&h->ar[par][r].v[k]);
+                    acc = op == 0 ? fmax(acc, x) : acc + x;
+                }
+                if (op == 0) ivals[k] = (int)acc; else dout[k] = acc;
+            }
+        }
+        epoch[0] = e;
+    }
+}
+
+// boundary-star lists straight into the neighbours' mailboxes, then the received lists into the local `recv` layout
+// ([source rank][list][1 + 3 cap]) the evaluation reads: list 1 of rank-1 and list 0 of rank+1
+__global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
+                                      unsigned long long* epoch, int* err) {
+    const unsigned long long e = epoch[1] + 1;
+    const int par = (int)(e & 1);
+    auto mailbox = [&](int r, int side) {
+        return reinterpret_cast<double*>(peers.box[r] + sizeof(PeerHeader)) + ((size_t)par * 2 + side) * list;
+    };
+    auto tagof = [&](int r, int side) { return &reinterpret_cast<PeerHeader*>(peers.box[r])->gtag[par][side]; };
+    // my list 0 (stars near my lower edge) -> side 1 of rank-1's box; my list 1 -> side 0 of rank+1's box
+    for (int dir = 0; dir < 2; ++dir) {
+        const int nb = dir == 0 ? rank - 1 : rank + 1;
+        if (nb < 0 || nb >= world) continue;
+        const double* src = send + (size_t)dir * list;
+        double* dst = mailbox(nb, dir == 0 ? 1 : 0);
+        const int cnt = 1 + 3 * (int)src[0];
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && rank > 0) peer_publish_tag(tagof(rank - 1, 1), e);
+    if (threadIdx.x == 1 && rank < world - 1) peer_publish_tag(tagof(rank + 1, 0), e);
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && rank > 0 && !peer_wait_tag(tagof(rank, 0), e, err)) ok = 0;
+    if (threadIdx.x == 1 && rank < world - 1 && !peer_wait_tag(tagof(rank, 1), e, err)) ok = 0;
+    __syncthreads();
+    for (int side = 0; side < 2; ++side) {
+        const int nb = side == 0 ? rank - 1 : rank + 1;
+        if (nb < 0 || nb >= world) continue;
+        const double* src = mailbox(rank, side);
+        double* dst = recv + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * list;
+        const int cnt = ok ? 1 + 3 * (int)__ldcv(src) : 1;
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = ok ? __ldcv(src + k) : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) epoch[1] = e;
 }
 
 struct BBuf {
@@ -555,7 +708,12 @@ struct srhmc_big {
     BBuf D, L, q, p, g, a1, a2, q0, g0, gid, vpart, scalars, gscalars, state, counters, send, recv, err, normals, lnu, E, V, T, A;
     // fused tile evaluation (big_tile.cuh): tile grid over the local rows, per-tile star lists, per-star footprint partials
     BBuf tcnt, tlist, gpart;
-    bool own_binned = false;  // the pair records of the owned stars' current positions are already in the tile lists
+    bool own_binned = false;
+    // peer exchange (our own collectives over P2P / IPC mapped memory)
+    BBuf peerbox, xepoch, packcnt;
+    PeerPtrs peers{};
+    void* ipc_opened[kMaxWorld] = {};
+    bool peer_enabled = false;  // the pair records of the owned stars' current positions are already in the tile lists
     BBuf epart, tickets;  // per-block energy partials; last-block tickets [0] energy, [1] tile potential
     int nty = 0, ntx = 0;
     bool use_tiles = false;
@@ -635,6 +793,7 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     rc |= b->vpart.ensure(std::max<size_t>(kVBlocks, ntiles) * 8); rc |= b->scalars.ensure(kScalars * 8); rc |= b->gscalars.ensure(kScalars * 8); rc |= b->state.ensure(8 * 8);
     rc |= b->counters.ensure(4 * 4); rc |= b->err.ensure(4);
     rc |= b->epart.ensure(kEnergyBlocks * 4 * 8); rc |= b->tickets.ensure(2 * 4);
+    rc |= b->packcnt.ensure(((size_t)cfg->max_stars / kPackChunk + 2) * sizeof(int2));
     rc |= b->send.ensure(2 * list * 8); rc |= b->recv.ensure((size_t)cfg->world_size * 2 * list * 8);
     if (rc) { srhmc_big_destroy(b); return SRHMC_ERR_CUDA; }
     cudaMemset(b->scalars.ptr, 0, kScalars * 8);
@@ -661,8 +820,11 @@ int srhmc_big_destroy(srhmc_big* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
                    &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A,
-                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets};
+                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets, &b->xepoch, &b->packcnt};
     for (BBuf* x : all) x->release();
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (b->ipc_opened[r]) cudaIpcCloseMemHandle(b->ipc_opened[r]);
+    b->peerbox.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -791,6 +953,54 @@ int srhmc_big_set_momenta(srhmc_big* b, const double* p) {
     return 0;
 }
 
+static size_t peer_box_bytes(const srhmc_big* b) {
+    const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
+    return sizeof(PeerHeader) + 4 * list * 8;
+}
+
+int srhmc_big_comm_export(srhmc_big* b, void* ipc_handle_64, void** raw_ptr) {
+    if (!b) return bfail(SRHMC_ERR_INVALID, "null context");
+    if (b->world > kMaxWorld) return bfail(SRHMC_ERR_INVALID, "peer exchange supports up to %d ranks", kMaxWorld);
+    BCU(cudaSetDevice(b->cfg.device));
+    if (!b->peerbox.ptr) {
+        // a dedicated allocation: cudaIpcGetMemHandle exports the whole cudaMalloc block
+        if (int rc = b->peerbox.ensure(peer_box_bytes(b))) return rc;
+        if (int rc = b->xepoch.ensure(16)) return rc;
+        BCU(cudaMemset(b->peerbox.ptr, 0, peer_box_bytes(b)));
+        BCU(cudaMemset(b->xepoch.ptr, 0, 16));
+    }
+    if (ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        BCU(cudaIpcGetMemHandle(&h, b->peerbox.ptr));
+        std::memcpy(ipc_handle_64, &h, 64);
+    }
+    if (raw_ptr) *raw_ptr = b->peerbox.ptr;
+    return 0;
+}
+
+int srhmc_big_comm_import(srhmc_big* b, const void* ipc_handles, void* const* raw_ptrs) {
+    if (!b || (!ipc_handles && !raw_ptrs)) return bfail(SRHMC_ERR_INVALID, "null argument");
+    if (!b->peerbox.ptr) return bfail(SRHMC_ERR_STATE, "srhmc_big_comm_export has not been called");
+    BCU(cudaSetDevice(b->cfg.device));
+    for (int r = 0; r < b->world; ++r) {
+        if (r == b->rank) {
+            b->peers.box[r] = reinterpret_cast<unsigned char*>(b->peerbox.ptr);
+        } else if (raw_ptrs) {
+            b->peers.box[r] = reinterpret_cast<unsigned char*>(raw_ptrs[r]);   // same process: plain device pointers
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, reinterpret_cast<const unsigned char*>(ipc_handles) + 64 * (size_t)r, 64);
+            void* p = nullptr;
+            BCU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            b->ipc_opened[r] = p;
+            b->peers.box[r] = reinterpret_cast<unsigned char*>(p);
+        }
+    }
+    b->peer_enabled = true;
+    return 0;
+}
+
 int srhmc_big_buffers(srhmc_big* b, srhmc_big_buffers_t* out) {
     if (!b || !out) return bfail(SRHMC_ERR_INVALID, "null argument");
     const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
@@ -885,9 +1095,16 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             const double reach = (double)(b->cfg.nrows_halo + P.rad + 1);
             const double lo_edge = (b->rank > 0) ? (double)P.own_lo + reach : -1e300;
             const double hi_edge = (b->rank < b->world - 1) ? (double)P.own_hi - reach : 1e300;
-            big_pack_kernel<<<1, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->send.as<double>(),
-                                                std::max(1, b->cfg.max_ghosts), b->err.as<int>());
-            b->launches += 1;
+            const int pb = std::max(1, (n + kPackChunk - 1) / kPackChunk);
+            big_pack_count_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>());
+            big_pack_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>(), b->send.as<double>(),
+                                                 std::max(1, b->cfg.max_ghosts), b->err.as<int>());
+            b->launches += 2;
+            if (b->peer_enabled && b->world > 1) {  // the exchange itself: our own kernel over peer memory
+                big_xchg_ghost_kernel<<<1, 256, 0, st>>>(b->peers, b->rank, b->world, b->send.as<double>(), b->recv.as<double>(), list,
+                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             break;
         }
         case SRHMC_BIG_EVAL:
@@ -962,11 +1179,21 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_PFIX_QFIX:
+            if (b->peer_enabled && b->world > 1) {  // field-wide maximum of the p fixed-point counts
+                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
+                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             big_pfix_qfix_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt, cnt + 1);
             b->launches += 1;
             break;
         case SRHMC_BIG_QFIX_KICK:
+            if (b->peer_enabled && b->world > 1) {  // field-wide maximum of the q fixed-point counts
+                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
+                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             if (b->use_tiles && b->own_binned)  // records nobody consumed (two position updates without an evaluation)
                 BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
@@ -998,8 +1225,13 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             const int ph = phase == SRHMC_BIG_ACCEPT ? 1 : 0;
             // single rank: the global sums are the local ones; otherwise the caller has all-reduced `scalars` into
             // `global_scalars` on this stream before this phase
-            if (b->world == 1)
+            if (b->world == 1) {
                 BCU(cudaMemcpyAsync(b->gscalars.ptr, b->scalars.ptr, kScalars * 8, cudaMemcpyDeviceToDevice, st));
+            } else if (b->peer_enabled) {  // sum of the energy partials over the ranks, in rank order on every rank
+                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 1, kScalars, nullptr, b->scalars.as<double>(),
+                                                        b->gscalars.as<double>(), b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             big_accept_kernel<<<gs, tb, 0, st>>>(ph, b->gscalars.as<double>(), b->scalars.as<double>(), b->state.as<double>(), s->seed, s->iteration,
                                                  s->iteration < 0 ? cnt + 2 : nullptr,
                                                  b->lnu.ptr ? b->lnu.as<double>() : nullptr, n, b->q.as<double>(),

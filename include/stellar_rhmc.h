@@ -369,11 +369,23 @@ int srhmc_big_set_stars(srhmc_big* b, const double* q /* [n,3] */, const int64_t
 int srhmc_big_get_stars(srhmc_big* b, double* q, double* p, double* grad /* each [n,3], may be NULL */);
 int srhmc_big_set_momenta(srhmc_big* b, const double* p /* [n,3] */);
 int srhmc_big_buffers(srhmc_big* b, srhmc_big_buffers_t* out);
+/* Peer exchange: the bracketed collectives above done by the library's own kernels over peer-mapped memory (NVLink P2P
+ * between the GPUs of one node) instead of by the caller.  Every rank exports its mailbox (a 64-byte CUDA IPC handle for
+ * other processes and/or the raw device pointer for strips hosted by the same process), the caller distributes the
+ * handles (any transport: they are plain bytes) and every rank imports all `world_size` of them (ipc_handles: world x 64
+ * bytes, or raw_ptrs: world pointers; the own entry is ignored).  From then on PFIX_QFIX and QFIX_KICK all-reduce(max) the
+ * fixed-point counters themselves, PACK also delivers the boundary lists into the neighbours' ghost_recv, and RECORD_E0 /
+ * ACCEPT sum the scalars over the ranks (rank order, identical on every rank): the caller issues no collective, and a
+ * captured CUDA graph of an iteration can be replayed on every rank.  A peer that never arrives raises error flag 4
+ * after ~10 s instead of hanging the device. */
+int srhmc_big_comm_export(srhmc_big* b, void* ipc_handle_64 /* may be NULL */, void** raw_ptr /* may be NULL */);
+int srhmc_big_comm_import(srhmc_big* b, const void* ipc_handles, void* const* raw_ptrs);
 /* Parity mode: normals [n_iters, n, 3] for the owned stars and/or lnu [n_iters]; NULL -> device Philox (seed). */
 int srhmc_big_set_draws(srhmc_big* b, const double* normals, const double* lnu, int32_t n_iters);
 int srhmc_big_alloc_chains(srhmc_big* b, int32_t n_iters);
 int srhmc_big_read_chains(srhmc_big* b, int32_t n_iters, double* E, double* V, double* T, uint8_t* A, double* n_accepted,
-                          int32_t* error_flag /* 1: an owned star left the local data window; 2: ghost list overflow */);
+                          int32_t* error_flag /* 1: an owned star left the local data window; 2: ghost list overflow;
+                                                    3: tile list overflow; 4: peer exchange timed out */);
 int srhmc_big_read_scalars(srhmc_big* b, double* scalars);
 int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* step);
 
