@@ -90,8 +90,11 @@ template <> struct VecLoad<float, 4> { static __device__ __forceinline__ void ld
 // instruction-bound, and 2300 exponentials per chunk cost more issue slots than the idle time they remove.  The
 // next step is a strided recurrence with a few lanes per star-axis (as in chain_kernel.cuh) and a single table
 // build per evaluation.
+// fmode: where the star's flux goes.  0: nowhere (gradient pass of a multi-chunk field), 1: into the row table (render
+// pass), 2: into the COLUMN table -- one build then serves both the render (f ex ey) and the gradient pass, whose sums
+// carry the factor f and are divided by it at the end (grad_chunk<T, true>).
 template <typename T>
-__device__ void build_tables(const Ctx<T>& c, int k0, int nk, bool scale_f) {
+__device__ void build_tables(const Ctx<T>& c, int k0, int nk, int fmode) {
     const FieldParams& P = *c.P;
     for (int t = threadIdx.x; t < 2 * nk; t += blockDim.x) {
         const int kk = t >> 1, axis = t & 1, k = k0 + kk;
@@ -99,7 +102,7 @@ __device__ void build_tables(const Ctx<T>& c, int k0, int nk, bool scale_f) {
         const int n = axis ? P.C : P.R;
         const int stride = axis ? P.sy : P.sx;
         T* tab = (axis ? c.taby : c.tabx) + (size_t)kk * stride;
-        const double scale = axis ? P.norm : (scale_f ? c.q[3 * k] : 1.0);
+        const double scale = axis ? (fmode == 2 ? P.norm * c.q[3 * k] : P.norm) : (fmode == 1 ? c.q[3 * k] : 1.0);
         const double fl = floor(coord);
         int m = 0;
         if (fl > 0.0) m = (fl > (double)(n - 1)) ? n - 1 : (int)fl;
@@ -208,7 +211,8 @@ __device__ void render_chunk(const Ctx<T>& c, int nk, bool first, bool last, boo
 }
 
 // ---------------------------------------------------------------------------------------------- gradients
-template <typename T>
+// FY: the column table holds f ey (build_tables fmode 2)
+template <typename T, bool FY = false>
 __device__ void grad_chunk(const Ctx<T>& c, int k0, int nk) {
     const FieldParams& P = *c.P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -229,21 +233,22 @@ __device__ void grad_chunk(const Ctx<T>& c, int k0, int nk) {
             const T* Lp = c.sL + jj;
             T c0a = 0, c1a = 0, c0b = 0, c1b = 0;
             int i = i0;
+            T dxa = (T)(((double)i0 + 0.5) - x), dxb = (T)(((double)i0 + 1.5) - x);  // row offsets, advanced by 2 per pass
             for (; i + 1 <= i1; i += 2) {
                 const T ra = Lp[i * P.C], rb = Lp[(i + 1) * P.C];
                 const T ea = tx[i], eb = tx[i + 1];
-                const T da = ea * (T)(((double)i + 0.5) - x), db = eb * (T)(((double)i + 1.5) - x);
                 c0a = fma(ra, ea, c0a);
-                c1a = fma(ra, da, c1a);
+                c1a = fma(ra, ea * dxa, c1a);
                 c0b = fma(rb, eb, c0b);
-                c1b = fma(rb, db, c1b);
+                c1b = fma(rb, eb * dxb, c1b);
+                dxa += (T)2;
+                dxb += (T)2;
             }
             if (i <= i1) {
                 const T ra = Lp[i * P.C];
                 const T ea = tx[i];
-                const T da = ea * (T)(((double)i + 0.5) - x);
                 c0a = fma(ra, ea, c0a);
-                c1a = fma(ra, da, c1a);
+                c1a = fma(ra, ea * dxa, c1a);
             }
             const T c0 = c0a + c0b, c1 = c1a + c1b;
             gf = fma(ey, c0, gf);
@@ -253,9 +258,9 @@ __device__ void grad_chunk(const Ctx<T>& c, int k0, int nk) {
         // lanes -> one value; accumulate the final reduction in double for both builds
         double df = warp_sum((double)gf), dx = warp_sum((double)gx), dy = warp_sum((double)gy);
         if (lane == 0) {
-            c.g[3 * k] = -df;
-            c.g[3 * k + 1] = -dx * f * P.inv_s2;
-            c.g[3 * k + 2] = -dy * f * P.inv_s2;
+            c.g[3 * k] = FY ? -df / f : -df;
+            c.g[3 * k + 1] = FY ? -dx * P.inv_s2 : -dx * f * P.inv_s2;
+            c.g[3 * k + 2] = FY ? -dy * P.inv_s2 : -dy * f * P.inv_s2;
         }
     }
 }
@@ -266,20 +271,30 @@ __device__ double eval_pixels(const Ctx<T>& c, bool want_V) {
     const FieldParams& P = *c.P;
     const int nchunks = c.N > 0 ? (c.N + P.Kc - 1) / P.Kc : 1;
     double vacc = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
-        build_tables<T>(c, k0, nk, true);
+    if (nchunks == 1 && c.N > 0) {
+        // every star's tables fit at once: ONE build serves the render and the gradient pass (flux in the column table)
+        build_tables<T>(c, 0, c.N, 2);
         __syncthreads();
-        render_chunk<T, MR, MC>(c, nk, ch == 0, ch == nchunks - 1, want_V, vacc);
+        render_chunk<T, MR, MC>(c, c.N, true, true, want_V, vacc);
         __syncthreads();
-    }
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
-        if (nk <= 0) break;
-        build_tables<T>(c, k0, nk, false);
+        grad_chunk<T, true>(c, 0, c.N);
         __syncthreads();
-        grad_chunk<T>(c, k0, nk);
-        __syncthreads();
+    } else {
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
+            build_tables<T>(c, k0, nk, 1);
+            __syncthreads();
+            render_chunk<T, MR, MC>(c, nk, ch == 0, ch == nchunks - 1, want_V, vacc);
+            __syncthreads();
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int k0 = ch * P.Kc, nk = min(P.Kc, c.N - k0);
+            if (nk <= 0) break;
+            build_tables<T>(c, k0, nk, 0);
+            __syncthreads();
+            grad_chunk<T>(c, k0, nk);
+            __syncthreads();
+        }
     }
     if (want_V) {
         double v[1] = {vacc};

@@ -128,8 +128,11 @@ int configure(srhmc_ctx* c) {
     }
     c->threads = threads;
     c->kc = pick_kernel(R, C, threads / 32);
-    P.sx = ((R + 8 * c->kc.mr - 1) / (8 * c->kc.mr)) * 8 * c->kc.mr;
-    P.sy = ((C + 4 * c->kc.mc - 1) / (4 * c->kc.mc)) * 4 * c->kc.mc;
+    // table strides: rows / columns rounded up to the warp tile, plus 16 bytes so that the tables of consecutive stars
+    // start on different shared-memory banks (one thread builds one table: 64-double strides put 16 stars on one bank)
+    const int tab_pad = prec == 64 ? 2 : 4;
+    P.sx = ((R + 8 * c->kc.mr - 1) / (8 * c->kc.mr)) * 8 * c->kc.mr + tab_pad;
+    P.sy = ((C + 4 * c->kc.mc - 1) / (4 * c->kc.mc)) * 4 * c->kc.mc + tab_pad;
     const int nwant = std::max(1, N);
     auto fit = [&](size_t budget, bool dsm) -> int {
         FieldParams Q = P;
