@@ -157,13 +157,21 @@ int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
 // Iteration chunks per chain for a MODE_RUN launch of `groups` warp-sized work items on `warps` resident warps.
 // One chunk when everything is resident at once (or the chains are short); otherwise enough chunks that the
 // under-filled last round costs a few percent instead of up to half the launch.
+// The kernel cuts L iterations into n chunks of ceil(L/n) iterations; every chunk must be non-empty (an empty last chunk
+// would wait for a predecessor that, being the real last one, never publishes): largest n' <= n with (n'-1) ceil(L/n') < L.
+static int valid_chunks(int n, int L) {
+    n = std::max(1, std::min(n, L));
+    while (n > 1 && (long long)(n - 1) * (((long long)L + n - 1) / n) >= (long long)L) --n;
+    return n;
+}
+
 int pick_chunks(long long groups, long long warps, int L) {
     if (const char* env = std::getenv("SRHMC_CHAIN_CHUNKS")) {
         const int c = std::atoi(env);
-        if (c >= 1) return std::max(1, std::min(c, L));
+        if (c >= 1) return valid_chunks(c, L);
     }
     if (groups <= warps || L < 64) return 1;
-    return std::max(1, std::min(16, L / 32));
+    return valid_chunks(std::min(16, L / 32), L);
 }
 
 long long chain_kernel_resident_warps(const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, int n_fields) {

@@ -795,8 +795,16 @@ static int run_pipelined(srhmc_ctx* c, const srhmc_run_args* a, int n_parts) {
     const long long W = std::max<long long>(1, chain_kernel_resident_warps(A, c->chain_plan, c->sm_count, (int)F));
     int cpp = 1;
     double best = -1.0;
+    // the kernel cuts L iterations into n chunks of ceil(L/n): every chunk must be non-empty, or its successor-less
+    // predecessor never publishes and the empty chunk waits for it (e.g. L = 385, n = 24: 23 x 17 > 385)
+    auto chunks_ok = [&](int n) {
+        const long long Lc = ((long long)L + n - 1) / n;
+        return (long long)(n - 1) * Lc < (long long)L;
+    };
+    if (!chunks_ok(n_parts)) return fail(SRHMC_ERR_INVALID, "run of %d iterations cannot be cut into %d parts", L, n_parts);
     for (int k = 1; k <= 8; ++k) {
         if ((long long)L < 16LL * k * n_parts) break;
+        if (!chunks_ok(n_parts * k)) continue;
         const long long tasks = (long long)groups * k, rounds = (tasks + W - 1) / W;
         const double eff = (double)tasks / (double)(rounds * W);
         if (eff > best + 0.01) { best = eff; cpp = k; }
