@@ -191,6 +191,7 @@ SIGNATURES = {
     "srhmc_philox_draws": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, c_double_p, c_double_p]),
     "srhmc_philox_draws_ids": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, c_double_p,
                                          c_double_p]),
+    "srhmc_plan_chunks": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "srhmc_test_device_math": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32]),
     "srhmc_measure_fma_peak": (C.c_int, [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_float)]),
     "srhmc_big_last_error": (C.c_char_p, []),

@@ -36,6 +36,8 @@ int convert_image_launch(cudaStream_t stream, const double* src, float* dst, siz
 // warp-resident one-star kernel (chain_kernel.cuh), FP64
 int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan);
 int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, cudaStream_t stream);
+// iteration chunks of the MODE_RUN work scheduler for `groups` warp-sized work items on `warps` resident warps
+int pick_chunks(long long groups, long long warps, int L);
 // warps a MODE_RUN launch of n_fields chains keeps resident (the denominator of its work scheduler's rounds)
 long long chain_kernel_resident_warps(const LaunchArgs& A, const ChainLaunchPlan& plan, int sms, int n_fields);
 

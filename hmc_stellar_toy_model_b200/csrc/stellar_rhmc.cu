@@ -770,6 +770,28 @@ int srhmc_run_download(srhmc_ctx* c, const srhmc_run_args* a) {
 // workload, 14.7 ms at the 55 GB/s of the link when copied after a 91.5 ms launch.  (Cutting the batch along the
 // CHAIN axis instead was measured slower than no overlap at all -- 136.6 vs 106.0 ms: four concurrent part-filled
 // grids defeat the chain kernel's work scheduler.)
+// Iteration chunks per part of a pipelined run: the part's (group, chunk) work items should fill whole rounds of the
+// resident warps.  The kernel cuts L iterations into n = n_parts * k chunks of ceil(L/n): every chunk must be non-empty,
+// or its successor-less predecessor never publishes and the empty chunk waits for it (e.g. L = 385, n = 24: 23 x 17 > 385;
+// L = 1001, n = 40).  Returns 0 when even n = n_parts is impossible.
+static int pipelined_chunks_per_part(int L, int n_parts, long long groups, long long W) {
+    auto chunks_ok = [&](int n) {
+        const long long Lc = ((long long)L + n - 1) / n;
+        return (long long)(n - 1) * Lc < (long long)L;
+    };
+    if (n_parts < 1 || !chunks_ok(n_parts)) return 0;
+    int cpp = 1;
+    double best = -1.0;
+    for (int k = 1; k <= 8; ++k) {
+        if ((long long)L < 16LL * k * n_parts) break;
+        if (!chunks_ok(n_parts * k)) continue;
+        const long long tasks = groups * k, rounds = (tasks + W - 1) / W;
+        const double eff = (double)tasks / (double)(rounds * W);
+        if (eff > best + 0.01) { best = eff; cpp = k; }
+    }
+    return cpp;
+}
+
 static int run_pipelined(srhmc_ctx* c, const srhmc_run_args* a, int n_parts) {
     if (int rc = srhmc_run_upload(c, a)) return rc;
     LaunchArgs A;
@@ -793,22 +815,8 @@ static int run_pipelined(srhmc_ctx* c, const srhmc_run_args* a, int n_parts) {
     c->sched_used = true;
     // iteration chunks per part: the part's (group, chunk) work items should fill whole rounds of the resident warps
     const long long W = std::max<long long>(1, chain_kernel_resident_warps(A, c->chain_plan, c->sm_count, (int)F));
-    int cpp = 1;
-    double best = -1.0;
-    // the kernel cuts L iterations into n chunks of ceil(L/n): every chunk must be non-empty, or its successor-less
-    // predecessor never publishes and the empty chunk waits for it (e.g. L = 385, n = 24: 23 x 17 > 385)
-    auto chunks_ok = [&](int n) {
-        const long long Lc = ((long long)L + n - 1) / n;
-        return (long long)(n - 1) * Lc < (long long)L;
-    };
-    if (!chunks_ok(n_parts)) return fail(SRHMC_ERR_INVALID, "run of %d iterations cannot be cut into %d parts", L, n_parts);
-    for (int k = 1; k <= 8; ++k) {
-        if ((long long)L < 16LL * k * n_parts) break;
-        if (!chunks_ok(n_parts * k)) continue;
-        const long long tasks = (long long)groups * k, rounds = (tasks + W - 1) / W;
-        const double eff = (double)tasks / (double)(rounds * W);
-        if (eff > best + 0.01) { best = eff; cpp = k; }
-    }
+    const int cpp = pipelined_chunks_per_part(L, n_parts, (long long)groups, W);
+    if (cpp < 1) return fail(SRHMC_ERR_INVALID, "run of %d iterations cannot be cut into %d parts", L, n_parts);
     A.n_chunks = n_parts * cpp;
     const int Lc = (L + A.n_chunks - 1) / A.n_chunks;  // the kernel's chunk length
     if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
@@ -845,6 +853,12 @@ static int run_pipelined(srhmc_ctx* c, const srhmc_run_args* a, int n_parts) {
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (sched_err) return fail(SRHMC_ERR_CUDA, "chain kernel scheduler timed out waiting for a predecessor chunk");
     return 0;
+}
+
+int srhmc_plan_chunks(int64_t groups, int64_t resident_warps, int32_t n_iterations, int32_t n_parts) {
+    if (groups < 1 || resident_warps < 1 || n_iterations < 1 || n_parts < 0) return 0;
+    if (n_parts == 0) return pick_chunks(groups, resident_warps, n_iterations);
+    return n_parts * pipelined_chunks_per_part(n_iterations, n_parts, groups, resident_warps);
 }
 
 int srhmc_run(srhmc_ctx* c, const srhmc_run_args* a) {

@@ -276,6 +276,12 @@ int srhmc_philox_draws(srhmc_ctx* ctx, uint64_t seed, int32_t niter, double* nor
 int srhmc_philox_draws_ids(srhmc_ctx* ctx, uint64_t seed, int32_t niter, int32_t field_id_base, int32_t field_id_stride,
                            double* normals, double* lnu);
 
+/* Diagnostic (host only, no device needed): into how many iteration chunks the one-star kernel's work scheduler cuts a
+ * run of n_iterations (= niter + 1) Metropolis iterations for `groups` warp-sized groups of chains on `resident_warps`
+ * warps -- n_parts = 0: a single launch; n_parts > 0: the pipelined srhmc_run of that many launches (returns the total
+ * over the parts, 0 if impossible).  Every chunk of ceil(n_iterations / chunks) iterations is non-empty. */
+int srhmc_plan_chunks(int64_t groups, int64_t resident_warps, int32_t n_iterations, int32_t n_parts);
+
 /* Diagnostic: evaluate the kernels' own device math on n values (which = 0: exp_neg(x), x <= 0; 1: log_pos(x), x > 0;
  * 2: rcp_fast(x)) so the test-suite can bound its error against libm. */
 int srhmc_test_device_math(srhmc_ctx* ctx, int32_t which, const double* x, double* y, int32_t n);

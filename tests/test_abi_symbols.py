@@ -73,3 +73,31 @@ def test_no_cpu_fallback_without_a_device():
     tf = C.c_double()
     assert _capi.load_library().srhmc_measure_fma_peak(0, 64, C.byref(tf), None) == -3
     assert _capi.load_library().srhmc_device_count() == 0
+
+
+def test_scheduler_never_plans_an_empty_chunk(monkeypatch):
+    """Host logic of the one-star kernel's work scheduler (no device needed): the run is cut into n chunks of
+    ceil(L/n) iterations and every chunk must hold at least one iteration -- an empty last chunk would wait for a
+    predecessor that never publishes (L = 385 in 24 chunks and L = 1001 in 40 were such cases)."""
+    from hmc_stellar_toy_model_b200 import _capi
+
+    lib = _capi.load_library()
+
+    def ok(n, L):
+        return n >= 1 and (n - 1) * -(-L // n) < L
+
+    for L in list(range(1, 700)) + [1000, 1001, 1024, 4097, 10001]:
+        for parts in (0, 2, 4, 8):
+            n = lib.srhmc_plan_chunks(1375, 1184, L, parts)
+            if parts == 0:
+                assert ok(n, L), (L, parts, n)
+            elif n:
+                assert n % parts == 0 and ok(n, L), (L, parts, n)
+            else:
+                assert not ok(parts, L), (L, parts)
+    assert lib.srhmc_plan_chunks(1375, 1184, 1001, 8) == 48 and lib.srhmc_plan_chunks(1375, 1184, 1001, 0) == 16
+    assert lib.srhmc_plan_chunks(100, 1184, 1001, 0) == 1  # everything resident at once: no chunking
+    for c in (1, 5, 24, 40, 500, 5000):
+        monkeypatch.setenv("SRHMC_CHAIN_CHUNKS", str(c))
+        for L in (1, 7, 385, 1001):
+            assert ok(lib.srhmc_plan_chunks(1375, 1184, L, 0), L), (c, L)
