@@ -300,3 +300,28 @@ def test_find_peaks_descent_matches_oracle_per_seed():
     same = steps == steps0
     assert relerr(q[same & alive], want[same & alive]) < 1e-9
     assert relerr(q[alive], want[alive]) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_find_peaks_oracle_matches_live_reference():
+    """A second configuration (24x40 image, two stars, coarser grid, larger steps) straight against the reference."""
+    import ref_shim
+
+    utils, _, smp = ref_shim.load()
+    np.random.seed(123)
+    gym = smp.lightsource_gym()
+    gym.num_rows = gym.num_cols = 36
+    fl = lambda m: utils.mag2flux(m) * gym.flux_to_count  # noqa: E731
+    q_true = np.array([[fl(17.5), 12.2, 25.1], [fl(20.0), 27.7, 9.4]])
+    gym.gen_mock_data(q_true=q_true)
+    state = np.random.get_state()
+    n_side = int(0.2 * 36) - 1
+    jitter = np.random.randn(n_side * n_side, 2)
+    np.random.set_state(state)
+    with ref_shim.quiet():
+        gym.find_peaks(linear_pix_density=0.2, Nstep=150, dt_f_coeff=0.2, dt_xy_coeff=0.05, dr_tol=1.5, dmag_tol=0.7)
+    L = so.LightSetup(num_rows=36, num_cols=36)
+    L.D = gym.D
+    got = so.ls_find_peaks(L, jitter, linear_pix_density=0.2, Nstep=150, dt_f_coeff=0.2, dt_xy_coeff=0.05, dr_tol=1.5,
+                           dmag_tol=0.7)
+    assert got.shape == gym.q_seed.shape and relerr(got, gym.q_seed) < 1e-12
