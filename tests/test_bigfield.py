@@ -336,3 +336,54 @@ def test_bigfield_peer_exchange_equals_untiled(path, monkeypatch):
     assert relerr(eng.stars(n)[0], qa) < 1e-9
     for s in strips:
         s.close()
+
+
+class _FakeStrip:
+    """Stands in for BigFieldStrip in the host-side plumbing test of PeerComm (no device)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.imported = None
+
+    def comm_export(self):
+        return bytes([self.rank]) * 64, 0x1000 * (self.rank + 1)
+
+    def comm_import(self, handles=None, raw_ptrs=None):
+        self.imported = handles if handles is not None else list(raw_ptrs)
+
+
+def _peer_handles_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = _FakeStrip(rank, world)
+        comm = bf.PeerComm([s], dist)
+        q.put((rank, s.imported, comm.in_process))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_comm_distributes_handles_in_rank_order():
+    """One strip per process: every rank ends up with the world's 64-byte mailbox handles concatenated in rank order (the
+    layout srhmc_big_comm_import expects); strips of one process exchange raw pointers in rank order instead."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_handles_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = bytes([0]) * 64 + bytes([1]) * 64
+    for rank, imported, in_process in res:
+        assert imported == want and not in_process
+    strips = [_FakeStrip(r, 3) for r in (2, 0, 1)]
+    comm = bf.PeerComm(strips)
+    assert comm.in_process and all(s.imported == [0x1000, 0x2000, 0x3000] for s in strips)
