@@ -435,23 +435,35 @@ class BigFieldRHMC:
             raise ValueError("CUDA-graph replay is not available with torch.distributed collectives")
         if use_graph and has_sched:
             raise ValueError("a g_ff2 schedule changes a launch parameter every iteration: run with use_graph=False")
+        self.replayed_launches = 0
         if use_graph:
             import torch
 
             self._all("RESET_ITER", st0)
-            stg = self._step_struct(dt, delta, g_ff2, counter_max, f_pos, -1, seed)
-            run_stream = torch.cuda.current_stream()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                cap = torch.cuda.current_stream().cuda_stream
+            # one captured iteration serves every later run with the same launch parameters (the chain row and the RNG
+            # counter come from the device-side iteration counter; the buffers are owned by the strips and never move)
+            key = (int(nsteps), float(dt), float(delta), float(g_ff2), int(counter_max), bool(f_pos), int(seed), L,
+                   tuple(s.n for s in self.strips))
+            if normals is not None or lnu is not None:
+                key = None  # injected draws live in buffers that are re-allocated per run: always capture afresh
+            if key is None or getattr(self, "_graph_key", None) != key:
+                stg = self._step_struct(dt, delta, g_ff2, counter_max, f_pos, -1, seed)
+                run_stream = torch.cuda.current_stream()
+                graph = torch.cuda.CUDAGraph()
+                before = [s.launch_count for s in self.strips]
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    cap = torch.cuda.current_stream().cuda_stream
+                    for s in self.strips:
+                        s.adopt_stream(cap)
+                    self._iteration(stg, nsteps)
                 for s in self.strips:
-                    s.adopt_stream(cap)
-                self._iteration(stg, nsteps)
-            for s in self.strips:
-                s.adopt_stream(run_stream.cuda_stream)
+                    s.adopt_stream(run_stream.cuda_stream)
+                self._graph, self._graph_key = graph, key
+                self._graph_nodes = sum(s.launch_count - b for s, b in zip(self.strips, before))
+                self.replayed_launches = -self._graph_nodes  # the capture itself executed nothing
             for _ in range(L):
-                graph.replay()
-            self._graph = graph  # keep alive until the results are read
+                self._graph.replay()
+            self.replayed_launches += self._graph_nodes * L  # kernels executed by the replays (not seen by launch_count)
         else:
             for l in range(L):
                 g = g_ff2

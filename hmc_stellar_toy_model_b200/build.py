@@ -16,7 +16,10 @@ SOURCES = ["stellar_rhmc.cu", "field_kernels_f64.cu", "field_kernels_f32.cu", "c
            "misc_kernels.cu", "mock_kernels.cu", "stats_kernels.cu", "peaks_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c"]
-LINK_FLAGS = ARCH + ["-shared", "-Xcompiler", "-fPIC"]
+# -cudart shared: the library depends on libcudart.so.12 (found through the rpath below or the loader path) instead of
+# embedding a static copy of the whole runtime and its entry-point name table
+CUDA_LIB = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+LINK_FLAGS = ARCH + ["-shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xlinker", "-rpath=" + CUDA_LIB]
 OBJ_DIR = os.path.join(HERE, "build")
 
 

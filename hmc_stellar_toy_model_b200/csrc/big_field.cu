@@ -987,7 +987,20 @@ int srhmc_big_comm_import(srhmc_big* b, const void* ipc_handles, void* const* ra
         if (r == b->rank) {
             b->peers.box[r] = reinterpret_cast<unsigned char*>(b->peerbox.ptr);
         } else if (raw_ptrs) {
-            b->peers.box[r] = reinterpret_cast<unsigned char*>(raw_ptrs[r]);   // same process: plain device pointers
+            // same process: plain device pointers.  A strip hosted on another device of this process needs peer access
+            // enabled explicitly (the IPC path below gets it from cudaIpcMemLazyEnablePeerAccess).
+            cudaPointerAttributes at;
+            BCU(cudaPointerGetAttributes(&at, raw_ptrs[r]));
+            if (at.type != cudaMemoryTypeDevice) return bfail(SRHMC_ERR_INVALID, "mailbox %d is not device memory", r);
+            if (at.device != b->cfg.device) {
+                int can = 0;
+                BCU(cudaDeviceCanAccessPeer(&can, b->cfg.device, at.device));
+                if (!can) return bfail(SRHMC_ERR_CUDA, "device %d cannot access the mailbox of rank %d on device %d", b->cfg.device, r, at.device);
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (pe != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", at.device, cudaGetErrorString(pe));
+            }
+            b->peers.box[r] = reinterpret_cast<unsigned char*>(raw_ptrs[r]);
         } else {
             cudaIpcMemHandle_t h;
             std::memcpy(&h, reinterpret_cast<const unsigned char*>(ipc_handles) + 64 * (size_t)r, 64);

@@ -567,17 +567,24 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             } else {
                 // wait until the previous chunk of this group has published its state (bounded spin: a scheduler
                 // fault must not hang the device)
+                // (the host caps the grid at the resident warp count, so the producer of chunk-1 is always on the device
+                // when this context has the GPU to itself; on a shared GPU the spin is bounded instead)
+                int ready = 1;
                 if (lane == 0) {
                     const long long t0 = clock64();
                     while (*((volatile int*)A.sched_done + grp_id) < chunk) {
-                        if (clock64() - t0 > 120000000000LL) {  // ~60 s
+                        if (*((volatile int*)A.sched_err) != 0 || clock64() - t0 > 120000000000LL) {  // ~60 s
                             atomicExch(A.sched_err, 1);
+                            ready = 0;
                             break;
                         }
                         __nanosleep(200);
                     }
                 }
-                __syncwarp();
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                // a chunk whose predecessor never arrived is dropped (no stale state is advanced, no rows are written);
+                // the host reports the scheduler fault
+                if (!ready) continue;
                 __threadfence();
                 const double* st = A.sched_state + (size_t)field * 8;
                 s.f = __ldcg(st); s.x = __ldcg(st + 1); s.y = __ldcg(st + 2);

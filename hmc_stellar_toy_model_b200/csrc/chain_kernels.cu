@@ -10,7 +10,7 @@ namespace srhmc {
 
 namespace {
 
-constexpr int kLPC = kChainLPC;  // lanes per chain: 8 -> 4 chains per warp (measured faster than 16 lanes / 2 chains)
+constexpr int kLPC = kChainLPC;  // lanes per chain: 4 -> 8 chains per warp (measured: 16 lanes 734, 8 lanes 1104, 4 lanes 1210 M star-steps/s)
 constexpr int kWarpsPerBlock = 1;
 // Column slots per lane: the full 32-column image, or a 24-column window around the star when the PSF weight of
 // every dropped column is below 2^-46 of its peak (sigma <= 1.50 px: |dy| >= 12 px).  SRHMC_CHAIN_WINDOW=0 at run time
@@ -188,8 +188,9 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     const int n_range = (A.field_end > 0 ? A.field_end : A.n_fields) - A.field_begin;
     const long long blocks = ((long long)n_range + chains_per_block - 1) / chains_per_block;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
-    // 168 registers -> 12 resident warps per SM (3 per scheduler).  Register-capped builds were measured: 128 registers /
-    // 16 warps 1057 M star-steps/s, 112 / 18 warps 892, 104 / 19 warps 843 against 1104 at 168 / 12.
+    // 4 lanes per chain: 218 registers -> 8 resident single-warp blocks per SM (2 per scheduler); residency comes from the
+    // occupancy query in chain_kernel_configure.  Register-capped 8-lane builds were measured earlier and are slower
+    // (128 registers / 16 warps 1057 M star-steps/s, 112 / 18 warps 892 against 1104 at 168 / 12).
     const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
     int grid = balanced_grid(max_k, blocks, sms);
     if (!(A.mode == MODE_RUN && A.sched_done != nullptr && A.chunk_count > 0)) A.n_chunks = 1;

@@ -79,7 +79,7 @@ struct LaunchArgs {
     const void* D;          // [n_images, R*C] in the pixel type
     const void* D_int;      // same images as exact unsigned integer counts, or nullptr (chain kernel, lossless)
     int D_int_bytes;        // 4: uint32, 2: uint16 (every count < 65536)
-    const double2* log_table;   // fastmath.cuh reciprocal/log table [128]
+    const double2* log_table;   // fastmath.cuh reciprocal/log table [kLogTableSize = 64]
     const int* nstars;      // [F] or nullptr
     // state in / out
     const double* q_in;     // [F,S]
@@ -109,7 +109,7 @@ struct LaunchArgs {
     // EVAL outputs
     double* V_out; double* grad_out; double* H_out; double* Hgrad_out;
     int* fp_counts;         // [F,2]
-    // chain-kernel work scheduler (MODE_RUN): iteration chunks per chain, per-group completion counters [ceil(F/4)],
+    // chain-kernel work scheduler (MODE_RUN): iteration chunks per chain, per-group completion counters [ceil(F/kChainGroup)],
     // travelling chain state [F,8], error word
     int n_chunks;            // iteration chunks per chain over the whole run
     int chunk_begin, chunk_count;  // chunks [chunk_begin, chunk_begin + chunk_count) are done by THIS launch (0, 0 = all)

@@ -182,15 +182,15 @@ class base_class(object):
     def H(self, q, grad=False):
         q = np.asarray(q, dtype=float).ravel()
         H, Hg = self._device_ctx(self._nobjs(q), need_data=False).metric(q, self.g_ff2)
-        return Hg if grad else H
+        return (H, Hg) if grad else H  # (H_diag, H_grad_diag) as sampler_RHMC.py:248-258
 
     def H_xx(self, f, grad=False):
         H, Hg = self._device_ctx(1, need_data=False).metric(np.array([f, 0., 0.]), self.g_ff2)
-        return float(Hg[1] if grad else H[1])
+        return (float(H[1]), float(Hg[1])) if grad else float(H[1])  # (value, grad) as sampler_RHMC.py:280
 
     def H_ff(self, f, grad=False):
         H, Hg = self._device_ctx(1, need_data=False).metric(np.array([f, 0., 0.]), self.g_ff2)
-        return float(Hg[0] if grad else H[0])
+        return (float(H[0]), float(Hg[0])) if grad else float(H[0])  # (value, grad) as sampler_RHMC.py:292
 
     def V(self, q, f_pos=False):
         q = np.asarray(q, dtype=float).ravel()

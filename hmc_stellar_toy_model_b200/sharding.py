@@ -98,7 +98,22 @@ def run_chains_sharded(make_context, D, q0, niter, nsteps, dt, rank, world, seed
     q0 = np.asarray(q0)
     n_items = q0.shape[0]
 
+    S = q0.shape[1]
+    stride = int(run_kw.get("chain_stride", 1) or 1)
+    rows = (niter + stride) // stride  # ceil((niter + 1) / stride) chain rows kept per field
+
     def run_local(ids):
+        if len(ids) == 0:
+            # fewer blocks than ranks: this rank owns nothing.  It still takes part in the gather, so it returns
+            # zero-length arrays with the shapes and dtypes the other ranks produce (no context is created: the library
+            # rejects n_fields < 1)
+            out = {"q_final": np.zeros((0, S)), "accept_rate": np.zeros((0,))}
+            for key, name, tail, dt_ in (("q", "q_chain", (rows, S), np.float64), ("p", "p_chain", (rows, S), np.float64),
+                                         ("E", "E_chain", (rows,), np.float64), ("V", "V_chain", (rows,), np.float64),
+                                         ("T", "T_chain", (rows,), np.float64), ("A", "A_chain", (rows,), np.uint8)):
+                if key in want:
+                    out[name] = np.zeros((0,) + tail, dtype=dt_)
+            return out
         with make_context(len(ids)) as ctx:
             ctx.set_data(D[ids])
             r = ctx.run(q0[ids], niter, nsteps, dt, seed=seed, want=want, field_ids=ids, **run_kw)

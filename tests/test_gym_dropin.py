@@ -197,13 +197,19 @@ def test_gym_methods_match_reference(name):
     gym.Nobjs, gym.d = q.size // 3, q.size
     assert relerr(gym.V(q, f_pos=True), g["V"]) < RTOL
     assert np.allclose(gym.dVdq(q), g["dVdq"], rtol=1e-9, atol=1e-10 * np.max(np.abs(g["dVdq"])))
-    assert relerr(gym.H(q), g["H"]) < RTOL and relerr(gym.H(q, grad=True), g["dH"]) < RTOL
+    assert relerr(gym.H(q), g["H"]) < RTOL
+    H_val, H_grad = gym.H(q, grad=True)  # the reference returns the pair (sampler_RHMC.py:248-258)
+    assert relerr(H_val, g["H"]) < RTOL and relerr(H_grad, g["dH"]) < RTOL
     assert relerr(gym.T(p, gym.H(q)), g["T"]) < RTOL
     assert np.allclose(gym.dphidq(q), g["dphidq"], rtol=1e-9, atol=1e-10 * np.max(np.abs(g["dphidq"])))
     if "dtaudq" in g:
         assert np.allclose(gym.dtaudq(q, p), g["dtaudq"], rtol=RTOL, atol=0)
         assert np.allclose(gym.dtaudp(q, p), g["dtaudp"], rtol=RTOL, atol=0)
-    assert relerr(gym.H_ff(q[0]), g["H"][0]) < RTOL and relerr(gym.H_xx(q[0], grad=True), g["dH"][1]) < RTOL
+    assert relerr(gym.H_ff(q[0]), g["H"][0]) < RTOL
+    hxx, dhxx = gym.H_xx(q[0], grad=True)  # (value, grad), sampler_RHMC.py:280
+    hff, dhff = gym.H_ff(q[0], grad=True)  # (value, grad), sampler_RHMC.py:292
+    assert relerr(hxx, g["H"][1]) < RTOL and relerr(dhxx, g["dH"][1]) < RTOL
+    assert relerr(hff, g["H"][0]) < RTOL and relerr(dhff, g["dH"][0]) < RTOL
     q1, p1 = gym.RHMC_single_step(np.copy(q), np.copy(p), 1e-6, 1000)
     assert relerr(q1, g["q_traj"][1]) < RTOL and relerr(p1, g["p_traj"][1]) < 1e-9
     assert np.isinf(gym.V(np.concatenate([[1.0], q[1:]]), f_pos=True))  # flux below f_lim

@@ -82,6 +82,77 @@ def test_two_rank_gloo_gather_restores_global_order(n_items):
     assert np.array_equal(out["A_chain"], (gid[:, None] + np.arange(4)[None, :]) % 2 == 0)
 
 
+class _StubResult:
+    def __init__(self, ids, rows, S):
+        gid = np.asarray(ids, dtype=float)
+        self.q_final = np.repeat(gid[:, None], S, axis=1)
+        self.accept_rate = gid / 10.0
+        self.q_chain = np.repeat(self.q_final[:, None, :], rows, axis=1)
+        self.E_chain = np.repeat(gid[:, None], rows, axis=1)
+        self.A_chain = (np.repeat(gid[:, None], rows, axis=1) % 2).astype(np.uint8)
+
+
+class _StubContext:
+    """Stands in for RHMCContext in the CPU test of run_chains_sharded: like the library it refuses an empty batch."""
+
+    def __init__(self, n):
+        if n < 1:
+            raise ValueError("n_fields must be >= 1")
+        self.n = n
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def set_data(self, D):
+        assert len(D) == self.n
+
+    def run(self, q0, niter, nsteps, dt, seed=0, want=(), field_ids=None, **kw):
+        return _StubResult(field_ids, niter + 1, q0.shape[1])
+
+
+def _worker_empty_shard(rank, world, port, n_items, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D = np.zeros((n_items, 4, 4))
+        q0 = np.zeros((n_items, 3))
+        out = sharding.run_chains_sharded(_StubContext, D, q0, 6, 10, 0.2, rank, world, dist=dist)
+        if rank == 0:
+            q.put(out)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_with_an_empty_shard_still_joins_the_gather():
+    """5 chains on 2 ranks with blocks of 8: rank 1 owns nothing, must not create a context and must not leave rank 0
+    waiting in the collective."""
+    import torch.multiprocessing as mp
+
+    n_items = 5
+    assert sharding.BLOCK * 2 > n_items and len(sharding.shard_ids(n_items, 1, 2)) == 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_empty_shard, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gid = np.arange(n_items, dtype=float)
+    assert out["q_chain"].shape == (n_items, 7, 3) and np.array_equal(out["q_chain"][:, 0, 0], gid)
+    assert np.array_equal(out["accept_rate"], gid / 10.0)
+    assert out["A_chain"].dtype == np.uint8 and np.array_equal(out["A_chain"][:, 0], gid % 2)
+
+
 @pytest.mark.gpu
 def test_sharded_run_is_bit_identical_to_single_context():
     """Two shards run one after the other on cuda:0 with their global chain ids reproduce the unsharded batch."""
