@@ -38,15 +38,28 @@ __host__ __device__ inline SmemLayout make_layout(const FieldParams& P, bool d_i
     s.q = take(S);
     s.p = take(S);
     s.g = take(S);
-    s.a1 = take(S);
-    s.a2 = take(S);
+    if (!P.v3) {
+        s.a1 = take(S);
+        s.a2 = take(S);
+    }
     s.red = take(8 * 32 * sizeof(double));
     s.D = take(d_in_smem ? (size_t)P.R * P.C * sizeof(T) : 0);
     s.L = take((size_t)P.R * P.C * sizeof(T));
     s.L2 = take(P.hess ? (size_t)P.R * P.C * sizeof(T) : 0);  // 1/Lambda image of the Hessian path (samplers.py:828-927)
-    s.tabx = take((size_t)P.Kc * P.sx * sizeof(T));
-    s.taby = take((size_t)P.Kc * P.sy * sizeof(T));
-    s.span = take((size_t)P.Kc * 4 * sizeof(short));
+    if (P.v3) {
+        // compact tables of ALL stars: rs pairs {ex, ex dx} + cs entries f ey per star.  The fixed-point scratch a1 / a2
+        // is only live between two evaluations and the tables only inside one, so they share the space.
+        const size_t rows = (size_t)P.Nmax * P.rs * 2 * sizeof(T), cols = (size_t)P.Nmax * P.cs * sizeof(T);
+        s.tabx = take(rows > 2 * S ? rows : 2 * S);
+        s.taby = take(cols);
+        s.span = take((size_t)P.Nmax * 2 * sizeof(int));
+        s.a1 = s.tabx;
+        s.a2 = s.tabx + S;
+    } else {
+        s.tabx = take((size_t)P.Kc * P.sx * sizeof(T));
+        s.taby = take((size_t)P.Kc * P.sy * sizeof(T));
+        s.span = take((size_t)P.Kc * 4 * sizeof(short));
+    }
     s.total = o;
     return s;
 }
@@ -265,13 +278,250 @@ __device__ void grad_chunk(const Ctx<T>& c, int k0, int nk) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- compact-table path ("v3")
+// Patch-limited evaluation for crowded fields (BASELINE configs[2..3]): same sums as above (sampler_RHMC.py:365-425 with
+// the PSF cut to (2 rad + 1)^2 pixels), organised so that a 204-star 64x64 field needs ONE table build, three CTA barriers
+// and no bounds handling in the hot loops:
+//   tables  one thread per (star, axis).  Rows: TL = 2 rad + 1 pairs {ex, ex dx} for the image rows [w0, w0 + TL) with
+//           w0 = clamp(m - rad, 0, R - TL) (m = pixel holding the star), zero outside the patch, one zero guard pair on each
+//           side.  Columns: TL + 1 entries f ey / (2 pi s^2) for the columns [je, je + TL + 1), je even (16-byte aligned
+//           residual pairs), zero outside the patch, three zero guards on each side.  The windows always lie inside the image.
+//   render  a warp owns 8 rows x 32 columns of Lambda in registers (2 x 4 pixels per lane); stars whose window meets the
+//           block are found with one ballot per 32 stars; rho = D / Lambda - 1 goes to shared memory.
+//   gather  16 lanes per star (two stars per warp): a lane owns two adjacent columns and walks the TL rows with one
+//           16-byte load of the residual pair and one broadcast load of {ex, ex dx} per row (4 FMAs), then the three
+//           sums are folded across the 16 lanes with five shuffles.
+template <typename T> struct Pair;
+template <> struct Pair<double> { typedef double2 type; static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); } };
+template <> struct Pair<float> { typedef float2 type; static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); } };
+
+template <typename T>
+__device__ void build_tables_v3(const Ctx<T>& c) {
+    typedef typename Pair<T>::type P2;
+    const FieldParams& P = *c.P;
+    const int TL = P.tl, CW = P.tl + 1;
+    int2* span = reinterpret_cast<int2*>(c.span);
+    for (int t = threadIdx.x; t < 2 * c.N; t += blockDim.x) {
+        const int k = t >> 1, axis = t & 1;
+        const double coord = c.q[3 * k + 1 + axis];
+        const int n = axis ? P.C : P.R;
+        const double fl = floor(coord);
+        int m = 0;
+        if (fl > 0.0) m = (fl > (double)(n - 1)) ? n - 1 : (int)fl;
+        const int lo = max(0, m - P.rad), hi = min(n - 1, m + P.rad);
+        const double u = ((double)m + 0.5) - coord;
+        const double scale = axis ? P.norm * c.q[3 * k] : 1.0;
+        const double e0 = exp(-(u * u) * P.inv2s2) * scale;
+        double eu = e0, ed = e0, ru = exp(-(2.0 * u + 1.0) * P.inv2s2), rd = exp((2.0 * u - 1.0) * P.inv2s2);
+        if (axis == 0) {
+            const int w0 = min(lo, P.R - TL);
+            P2* rt = reinterpret_cast<P2*>(c.tabx) + (k * P.rs + 1 - w0);  // rt[i]: image row i
+            const P2 zero = Pair<T>::make((T)0, (T)0);
+            for (int i = w0 - 1; i < lo; ++i) rt[i] = zero;                 // leading guard (+ rows cut by the image edge)
+            for (int i = hi + 1; i < w0 - 1 + P.rs; ++i) rt[i] = zero;      // trailing guard(s)
+            rt[m] = Pair<T>::make((T)e0, (T)(e0 * u));
+            for (int s = 1; s <= P.rad; ++s) {
+                eu *= ru; ru *= P.c2;
+                ed *= rd; rd *= P.c2;
+                if (m + s <= hi) rt[m + s] = Pair<T>::make((T)eu, (T)(eu * (u + (double)s)));
+                if (m - s >= lo) rt[m - s] = Pair<T>::make((T)ed, (T)(ed * (u - (double)s)));
+            }
+            span[k].x = w0 - 1;   // image row of pair 0
+        } else {
+            const int je = min(lo & ~1, P.C - CW);
+            T* ct = c.taby + (k * P.cs + 3 - je);  // ct[j]: image column j
+            for (int j = je - 3; j < lo; ++j) ct[j] = (T)0;
+            for (int j = hi + 1; j < je - 3 + P.cs; ++j) ct[j] = (T)0;
+            ct[m] = (T)e0;
+            for (int s = 1; s <= P.rad; ++s) {
+                eu *= ru; ru *= P.c2;
+                ed *= rd; rd *= P.c2;
+                if (m + s <= hi) ct[m + s] = (T)eu;
+                if (m - s >= lo) ct[m - s] = (T)ed;
+            }
+            span[k].y = je - 3;   // image column of entry 0
+        }
+    }
+}
+
+template <typename T>
+__device__ void render_v3(const Ctx<T>& c, bool want_V, double& vacc) {
+    typedef typename Pair<T>::type P2;
+    const FieldParams& P = *c.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int TL = P.tl, CW = P.tl + 1;
+    const int ntr = (P.R + 7) >> 3, ntc = (P.C + 31) >> 5;
+    const P2* rowtab = reinterpret_cast<const P2*>(c.tabx);
+    const T* coltab = c.taby;
+    const int2* span = reinterpret_cast<const int2*>(c.span);   // (image row of pair 0, image column of entry 0)
+    const int rs = P.rs, cs = P.cs;
+    for (int wt = warp; wt < ntr * ntc; wt += nwarps) {
+        const int ti = (wt / ntc) * 8, tj = (wt % ntc) * 32;
+        const int ib = ti + (lane >> 3) * 2, jb = tj + (lane & 7) * 4;
+        T acc[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) acc[r][cc] = (T)P.B;
+        // one hit = one star whose window meets this block: 2 row pairs + 4 column entries -> 8 FMAs per lane
+        auto hit_load = [&](int k, bool on, P2& r0, P2& r1, T (&f)[4]) -> bool {
+            const int2 sp = span[k];
+            const int orow = ib - sp.x, ocol = jb - sp.y;   // pair / entry index of the lane's first row / column
+            const bool in = on && (unsigned)orow <= (unsigned)TL && (unsigned)ocol <= (unsigned)(CW + 2);
+            if (in) {
+                const P2* rp = rowtab + (k * rs + orow);
+                const T* cp = coltab + (k * cs + ocol);
+                r0 = rp[0]; r1 = rp[1];
+                f[0] = cp[0]; f[1] = cp[1]; f[2] = cp[2]; f[3] = cp[3];
+            }
+            return in;
+        };
+        auto hit_fma = [&](const P2& r0, const P2& r1, const T (&f)[4]) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                acc[0][cc] = fma(r0.x, f[cc], acc[0][cc]);
+                acc[1][cc] = fma(r1.x, f[cc], acc[1][cc]);
+            }
+        };
+        for (int kb = 0; kb < c.N; kb += 32) {
+            const int kk = kb + lane;
+            bool hit = false;
+            if (kk < c.N) {
+                const int2 sp = span[kk];
+                hit = (sp.x < ti + 7) && (sp.x + TL >= ti) && (sp.y + 3 <= tj + 31) && (sp.y + 3 + CW > tj);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            // two hits per trip: their loads are in flight together
+            while (mask) {
+                const int k0 = kb + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const bool two = mask != 0;
+                const int k1 = two ? kb + __ffs(mask) - 1 : k0;
+                mask &= mask - 1;
+                P2 a0, a1, b0, b1;
+                T fa[4], fb[4];
+                const bool ina = hit_load(k0, true, a0, a1, fa);
+                const bool inb = hit_load(k1, two, b0, b1, fb);
+                if (ina) hit_fma(a0, a1, fa);
+                if (inb) hit_fma(b0, b1, fb);
+            }
+        }
+        // residual (and the pixel potential on request)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = ib + r;
+            if (i >= P.R) continue;
+            if (jb + 3 < P.C) {
+                const int pix = i * P.C + jb;
+                T d[4];
+                if (c.sD) VecLoad<T, 4>::ld(c.sD + pix, d); else VecLoad<T, 4>::ld(c.gD + pix, d);
+                T rho[4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    rho[cc] = fma(d[cc], rcp_fast(acc[r][cc]), (T)-1);
+                    if (want_V) {
+                        const double ld = (double)acc[r][cc];
+                        vacc += ld - (double)d[cc] * log(ld);
+                    }
+                }
+                P2* o = reinterpret_cast<P2*>(c.sL + pix);
+                o[0] = Pair<T>::make(rho[0], rho[1]);
+                o[1] = Pair<T>::make(rho[2], rho[3]);
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int j = jb + cc;
+                    if (j >= P.C) continue;
+                    const int pix = i * P.C + j;
+                    const T lam = acc[r][cc];
+                    const T d = c.sD ? c.sD[pix] : c.gD[pix];
+                    c.sL[pix] = fma(d, rcp_fast(lam), (T)-1);
+                    if (want_V) {
+                        const double ld = (double)lam;
+                        vacc += ld - (double)d * log(ld);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Two stars per warp trip (one per half-warp): lane hl of a half owns the columns je + 2 hl, je + 2 hl + 1 of its star's
+// window and walks all TL rows.
+template <typename T>
+__device__ void gather_v3(const Ctx<T>& c) {
+    typedef typename Pair<T>::type P2;
+    const FieldParams& P = *c.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const int TL = P.tl, CW = P.tl + 1;
+    const P2* rowtab = reinterpret_cast<const P2*>(c.tabx);
+    const int2* span = reinterpret_cast<const int2*>(c.span);
+    const int rstride = P.C >> 1;
+    const int cofs = 3 + min(2 * hl, CW);           // lanes 13..15 read the zero guards
+    const bool dead = 2 * hl >= CW;
+    const int npairs = (c.N + 1) >> 1;
+    for (int pr = warp; pr < npairs; pr += nwarps) {
+        const int kraw = 2 * pr + half;
+        const bool live = kraw < c.N;
+        const int k = live ? kraw : c.N - 1;
+        const int2 sp = span[k];
+        const int w0 = sp.x + 1, je = sp.y + 3;
+        const T* cp = c.taby + (k * P.cs + cofs);
+        const T fy0 = cp[0], fy1 = cp[1];
+        const int col = min(je + 2 * hl, P.C - 2);  // always inside the image, 16-byte aligned
+        const P2* rho = reinterpret_cast<const P2*>(c.sL + (w0 * P.C + col));
+        const P2* rp = rowtab + (k * P.rs + 1);
+        T a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll 5
+        for (int r = 0; r < TL; ++r) {
+            const P2 e = rp[r];
+            const P2 v = rho[r * rstride];
+            a0 = fma(v.x, e.x, a0);
+            a1 = fma(v.x, e.y, a1);
+            b0 = fma(v.y, e.x, b0);
+            b1 = fma(v.y, e.y, b1);
+        }
+        const double f = c.q[3 * k], y = c.q[3 * k + 2];
+        const double dy0 = ((double)(je + 2 * hl) + 0.5) - y;
+        // per-lane contributions of its two columns (the column table carries f)
+        double sf = (double)fy0 * (double)a0 + (double)fy1 * (double)b0;
+        double sx = (double)fy0 * (double)a1 + (double)fy1 * (double)b1;
+        double sy = ((double)fy0 * dy0) * (double)a0 + ((double)fy1 * (dy0 + 1.0)) * (double)b0;
+        if (dead) sf = sx = sy = 0.0;
+        // fold the three sums over the 16 lanes of the star: 2 + 1 + 1 + 1 shuffles
+        const bool h8 = hl & 8;
+        const double k0 = h8 ? sy : sf, k1 = h8 ? 0.0 : sx, t0 = h8 ? sf : sy, t1 = h8 ? sx : 0.0;
+        const double x0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8), x1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
+        // lanes 0-7: x0 = sum_f (pairs), x1 = sum_x; lanes 8-15: x0 = sum_y, x1 = 0
+        const bool h4 = hl & 4;
+        double yv = (h4 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, h4 ? x0 : x1, 4);
+        // lanes 0-3: sum_f, lanes 4-7: sum_x, lanes 8-11: sum_y, lanes 12-15: 0
+        yv += __shfl_xor_sync(0xffffffffu, yv, 2);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+        // g_f = -sum_f / f (reciprocal to 2^-60), g_x = -sum_x / s^2, g_y = -sum_y / s^2
+        const double sc = (hl < 4) ? rcp_fast(f) : P.inv_s2;
+        if (live && (hl & 3) == 0 && hl < 12) c.g[3 * k + (hl >> 2)] = -(yv * sc);
+    }
+}
+
 // Pixel part of V and dV/dq at the current c.q.  Returns sum(Lambda - D ln Lambda) in every thread when want_V.
-template <typename T, int MR, int MC>
+// KV3: -1 = follow P.v3 at run time (generic kernels), 1 = the compact-table path only, 0 = the chunked tables only
+template <typename T, int MR, int MC, int KV3 = -1>
 __device__ double eval_pixels(const Ctx<T>& c, bool want_V) {
     const FieldParams& P = *c.P;
     const int nchunks = c.N > 0 ? (c.N + P.Kc - 1) / P.Kc : 1;
     double vacc = 0.0;
-    if (nchunks == 1 && c.N > 0) {
+    if (KV3 == 1 || (KV3 < 0 && P.v3)) {
+        build_tables_v3<T>(c);
+        __syncthreads();
+        render_v3<T>(c, want_V, vacc);
+        __syncthreads();
+        gather_v3<T>(c);
+        __syncthreads();
+    } else if (KV3 == 1) {
+        // unreachable: the specialised kernel is only launched for compact-table contexts
+    } else if (nchunks == 1 && c.N > 0) {
         // every star's tables fit at once: ONE build serves the render and the gradient pass (flux in the column table)
         build_tables<T>(c, 0, c.N, 2);
         __syncthreads();
@@ -350,6 +600,11 @@ struct Energies {
     double V, T;
 };
 
+// two CTA-wide maxima of the fixed-point iteration counts (rhmc_step): a corner of the reduction scratch that block_sum
+// (at most 7 values wide here) never touches
+template <typename T>
+__device__ __forceinline__ int* fp_count_slots(const Ctx<T>& c) { return reinterpret_cast<int*>(c.red + 7 * 32); }
+
 // V(q, f_pos) and T(p, H(q)) from the cached pixel potential (sampler_RHMC.py:294-363).
 template <typename T>
 __device__ Energies energies(const Ctx<T>& c, double Vpix, int f_pos, bool with_T) {
@@ -381,13 +636,13 @@ __device__ Energies energies(const Ctx<T>& c, double Vpix, int f_pos, bool with_
 // ---------------------------------------------------------------------------------------------- one leapfrog step
 // base_class.RHMC_single_step (sampler_RHMC.py:522-566).  Requires c.g == pixel gradient at c.q on entry and
 // leaves it so on exit.  All threads of the CTA must call it.
-template <typename T, int MR, int MC>
+template <typename T, int MR, int MC, int KV3 = -1>
 __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool want_V, double& Vpix, int* counts) {
     const FieldParams& P = *c.P;
     const double h = c.h;
     const int tid = threadIdx.x, nt = blockDim.x;
 
-    // (1) p <- p - h dphi/dq(q); set up the p fixed point: a1 = anchor rho_f, a2 = -H_ff'/H_ff^2
+    // (1) p <- p - h dphi/dq(q); set up the p fixed point: a1[3k] = anchor rho_f, a2[3k] = -H_ff'/H_ff^2
     for (int k = tid; k < c.N; k += nt) {
         const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
         double gf, gx, gy;
@@ -397,31 +652,52 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
         c.p[3 * k] = pf;
         c.p[3 * k + 1] -= h * gx;
         c.p[3 * k + 2] -= h * gy;
-        c.a1[k] = pf;
-        c.a2[k] = -m.dHff / (m.Hff * m.Hff);
+        c.a1[3 * k] = pf;   // own slots only: the q fixed point below reuses a1 / a2 per component without a barrier
+        c.a2[3 * k] = -m.dHff / (m.Hff * m.Hff);
     }
     // (2) p' = rho - h dtau/dq(q, p)  until max|p - p'| <= delta   (only flux slots move)
-    int cnt_p = 0;
+    // (3) q' = sigma + h (p/H(sigma) + p/H(q))  until max|q - q'| <= delta
+    // The reference stops each loop when the maximum over ALL stars meets the tolerance (sampler_RHMC.py:533,543).  The
+    // per-star maps are contractions, so that count is the maximum of the per-star counts: every star first iterates to its
+    // own convergence (phase A), the CTA takes the maximum (one barrier instead of one vote per iteration), and every star
+    // continues to it (phase B) -- the same iterates, bit for bit, as iterating all stars together.
+    int cnt_p = 0, cnt_q = 0;
+    int* cmax = fp_count_slots(c);  // zero on entry (kernel start / the previous step)
+    auto p_iter = [&](int k, double& pf) -> bool {
+        const double pn = c.a1[3 * k] - h * (((pf * pf) * c.a2[3 * k]) / 2.0);
+        const bool more = fabs(pf - pn) > delta;
+        pf = pn;
+        return more;
+    };
     if (P.fp_mode == 0) {
-        while (cnt_p < counter_max) {
-            int more = 0;
-            for (int k = tid; k < c.N; k += nt) {
-                const double pf = c.p[3 * k];
-                const double pn = c.a1[k] - h * (((pf * pf) * c.a2[k]) / 2.0);
-                more |= (fabs(pf - pn) > delta);
-                c.p[3 * k] = pn;
+        int own = 0;
+        for (int k = tid; k < c.N; k += nt) {
+            double pf = c.p[3 * k];
+            int n = 0;
+            while (n < counter_max) {
+                const bool more = p_iter(k, pf);
+                ++n;
+                if (!more) break;
             }
-            ++cnt_p;
-            if (!__syncthreads_or(more)) break;
+            c.p[3 * k] = pf;
+            c.g[3 * k] = (double)n;   // the pixel gradient is dead until the evaluation at the end of the step
+            own = max(own, n);
+        }
+        own = __reduce_max_sync(0xffffffffu, own);
+        if ((tid & 31) == 0 && own > 0) atomicMax(&cmax[0], own);
+        __syncthreads();
+        cnt_p = cmax[0];
+        for (int k = tid; k < c.N; k += nt) {
+            double pf = c.p[3 * k];
+            for (int n = (int)c.g[3 * k]; n < cnt_p; ++n) p_iter(k, pf);
+            c.p[3 * k] = pf;
         }
     } else {
         for (int k = tid; k < c.N; k += nt) {
             double pf = c.p[3 * k];
             int n = 0;
             while (n < counter_max) {
-                const double pn = c.a1[k] - h * (((pf * pf) * c.a2[k]) / 2.0);
-                const bool more = fabs(pf - pn) > delta;
-                pf = pn;
+                const bool more = p_iter(k, pf);
                 ++n;
                 if (!more) break;
             }
@@ -429,8 +705,7 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
             cnt_p = max(cnt_p, n);
         }
     }
-    // (3) q' = sigma + h (p/H(sigma) + p/H(q))  until max|q - q'| <= delta.  a1 = sigma, a2 = p/H(sigma)
-    __syncthreads();  // a1/a2 change meaning (per-star scalars -> per-component vectors)
+    // a1 = sigma, a2 = p/H(sigma): a thread only touches the slots of its own stars
     for (int k = tid; k < c.N; k += nt) {
         const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
         c.a1[3 * k] = c.q[3 * k];
@@ -440,7 +715,6 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
         c.a2[3 * k + 1] = c.p[3 * k + 1] / m.Hxx;
         c.a2[3 * k + 2] = c.p[3 * k + 2] / m.Hxx;
     }
-    int cnt_q = 0;
     auto q_iter = [&](int k, double& qf, double& qx, double& qy) -> bool {
         const Metric m = metric_of(P, qf, c.g_ff2);
         const double nf = c.a1[3 * k] + h * (c.a2[3 * k] + c.p[3 * k] / m.Hff);
@@ -452,20 +726,8 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
         qy = ny;
         return d > delta;
     };
-    if (P.fp_mode == 0) {
-        while (cnt_q < counter_max) {
-            int more = 0;
-            for (int k = tid; k < c.N; k += nt) {
-                double qf = c.q[3 * k], qx = c.q[3 * k + 1], qy = c.q[3 * k + 2];
-                more |= q_iter(k, qf, qx, qy);
-                c.q[3 * k] = qf;
-                c.q[3 * k + 1] = qx;
-                c.q[3 * k + 2] = qy;
-            }
-            ++cnt_q;
-            if (!__syncthreads_or(more)) break;
-        }
-    } else {
+    {
+        int own = 0;
         for (int k = tid; k < c.N; k += nt) {
             double qf = c.q[3 * k], qx = c.q[3 * k + 1], qy = c.q[3 * k + 2];
             int n = 0;
@@ -477,7 +739,24 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
             c.q[3 * k] = qf;
             c.q[3 * k + 1] = qx;
             c.q[3 * k + 2] = qy;
-            cnt_q = max(cnt_q, n);
+            c.g[3 * k] = (double)n;
+            own = max(own, n);
+        }
+        if (P.fp_mode == 0) {
+            own = __reduce_max_sync(0xffffffffu, own);
+            if ((tid & 31) == 0 && own > 0) atomicMax(&cmax[1], own);
+            __syncthreads();
+            cnt_q = cmax[1];
+            if (tid == 0) cmax[0] = 0;  // every thread read it before the barrier above
+            for (int k = tid; k < c.N; k += nt) {
+                double qf = c.q[3 * k], qx = c.q[3 * k + 1], qy = c.q[3 * k + 2];
+                for (int n = (int)c.g[3 * k]; n < cnt_q; ++n) q_iter(k, qf, qx, qy);
+                c.q[3 * k] = qf;
+                c.q[3 * k + 1] = qx;
+                c.q[3 * k + 2] = qy;
+            }
+        } else {
+            cnt_q = own;
         }
     }
     // (4) p <- p - h dtau/dq(q, p) at the new q
@@ -487,8 +766,9 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
         c.p[3 * k] = pf - h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
     }
     __syncthreads();
+    if (tid == 0) cmax[1] = 0;  // read by every thread before the barrier above; next used after several more
     // (5) gradient at the new q, then p <- p - h dphi/dq(q)
-    const double v = eval_pixels<T, MR, MC>(c, want_V);
+    const double v = eval_pixels<T, MR, MC, KV3>(c, want_V);
     if (want_V) Vpix = v;
     for (int k = tid; k < c.N; k += nt) {
         const double f = c.q[3 * k], x = c.q[3 * k + 1], y = c.q[3 * k + 2];
@@ -513,7 +793,10 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <typename T, int MR, int MC>
+// KMODE: -1 = every mode in one kernel (A.mode decides), otherwise the kernel is compiled for that mode alone; KV3 as in
+// eval_pixels.  The specialised <MODE_RUN, 1> build is the hot path of crowded-field chains: a third of the code of the
+// generic kernel, no spills.
+template <typename T, int MR, int MC, int KMODE = -1, int KV3 = -1>
 __global__ void __launch_bounds__(512, 1)
 field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A, double* scratch, int d_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -552,10 +835,12 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
             c.q[i] = q_in[i];
             c.p[i] = (A.p_in != nullptr) ? A.p_in[(size_t)field * S + i] : 0.0;
         }
+        if (tid == 0) fp_count_slots(c)[0] = fp_count_slots(c)[1] = 0;
         __syncthreads();
 
-        if (A.mode == MODE_EVAL) {
-            const double Vpix = eval_pixels<T, MR, MC>(c, true);
+        const int mode = KMODE >= 0 ? KMODE : A.mode;
+        if (mode == MODE_EVAL) {
+            const double Vpix = eval_pixels<T, MR, MC, KV3>(c, true);
             const Energies e = energies(c, Vpix, A.f_pos, false);
             for (int k = tid; k < c.N; k += nt) {
                 double gf, gx, gy;
@@ -567,11 +852,11 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
             if (tid == 0 && A.V_out) A.V_out[field] = e.V;
-        } else if (A.mode == MODE_STEP) {
-            eval_pixels<T, MR, MC>(c, false);
+        } else if (mode == MODE_STEP) {
+            eval_pixels<T, MR, MC, KV3>(c, false);
             double Vpix = 0.0;
             int counts[2] = {0, 0};
-            for (int s = 0; s < A.nsteps; ++s) rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, false, Vpix, counts);
+            for (int s = 0; s < A.nsteps; ++s) rhmc_step<T, MR, MC, KV3>(c, A.delta, A.counter_max, false, Vpix, counts);
             for (int i = tid; i < 3 * c.N; i += nt) {
                 A.q_out[(size_t)field * S + i] = c.q[i];
                 A.p_out[(size_t)field * S + i] = c.p[i];
@@ -600,10 +885,10 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                     A.fp_counts[2 * field + 1] = cq;
                 }
             }
-        } else if (A.mode == MODE_SINGLE) {
+        } else if (mode == MODE_SINGLE) {
             // single_gym.run_single_RHMC, solver="implicit" (sampler_RHMC.py:649-783)
             const size_t rows = (size_t)A.nsteps + 1;
-            double Vpix = eval_pixels<T, MR, MC>(c, true);
+            double Vpix = eval_pixels<T, MR, MC, KV3>(c, true);
             const Energies e0 = energies(c, Vpix, A.f_pos, true);
             for (int i = tid; i < 3 * c.N; i += nt) {
                 A.q_chain[((size_t)field * rows) * S + i] = c.q[i];
@@ -615,7 +900,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                 A.T_chain[field * rows] = 0.0;
             }
             for (int s = 1; s <= A.nsteps; ++s) {
-                rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, true, Vpix, nullptr);
+                rhmc_step<T, MR, MC, KV3>(c, A.delta, A.counter_max, true, Vpix, nullptr);
                 const Energies e = energies(c, Vpix, A.f_pos, true);
                 for (int i = tid; i < 3 * c.N; i += nt) {
                     A.q_chain[((size_t)field * rows + s) * S + i] = c.q[i];
@@ -633,7 +918,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
             double* gs = qs + S;
             const size_t rows = (size_t)A.n_rows;
             const int L = A.niter + 1;
-            double Vpix = eval_pixels<T, MR, MC>(c, true);
+            double Vpix = eval_pixels<T, MR, MC, KV3>(c, true);
             int n_acc = 0;
             for (int l = 0; l < L; ++l) {
                 if (A.gff2_sched && l < A.n_gff2) c.g_ff2 = A.gff2_sched[l];
@@ -672,7 +957,7 @@ field_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ Laun
                     }
                 }
                 for (int s = 0; s < A.nsteps; ++s)
-                    rhmc_step<T, MR, MC>(c, A.delta, A.counter_max, s == A.nsteps - 1, Vpix, nullptr);
+                    rhmc_step<T, MR, MC, KV3>(c, A.delta, A.counter_max, s == A.nsteps - 1, Vpix, nullptr);
                 const Energies e1 = energies(c, Vpix, A.f_pos, true);
                 const double dE = (e1.V + e1.T) - E0;
                 const double lnu = A.lnu ? A.lnu[(size_t)field * L + l] : philox_lnu(A.seed, A.philox_field(field), (uint32_t)l);

@@ -82,6 +82,9 @@ struct srhmc_ctx {
     int threads = 256;
     size_t smem = 0;
     int d_in_smem = 1;
+    FieldParams P_ls;   // parameters of the lightsource-family kernels (chunked tables, never the compact-table path)
+    size_t smem_ls = 0;
+    int dsm_ls = 1;
     bool chain_ok = false;          // warp-resident one-star kernel configured for this context
     ChainLaunchPlan chain_plan;
     size_t pix_bytes = 8;
@@ -163,6 +166,35 @@ int configure(srhmc_ctx* c) {
     P.Kc = kc;
     c->d_in_smem = dsm ? 1 : 0;
     c->smem = field_layout_total(prec, P, dsm);
+    // the lightsource family (ls_kernel.cuh) always runs with the chunked tables configured above
+    c->P_ls = P;
+    c->smem_ls = c->smem;
+    c->dsm_ls = c->d_in_smem;
+    // compact-table evaluation (field_kernel.cuh "v3") when the PSF is patch-limited and every star's tables fit at once
+    {
+        const int TL = 2 * g.patch_radius + 1;
+        bool want = g.patch_radius > 0 && g.patch_radius <= 12 && (C % 2 == 0) && R >= TL && C >= TL + 1 && !P.hess && N >= 1;
+        if (const char* env = std::getenv("SRHMC_FIELD_V3"))
+            if (env[0] == '0') want = false;
+        if (want) {
+            FieldParams Q = P;
+            Q.v3 = 1;
+            Q.tl = TL;
+            Q.rs = (TL + 2) | 1;
+            Q.cs = (TL + 7) | 1;
+            bool dsm3 = true;
+            size_t tot = field_layout_total(prec, Q, true);
+            if (tot > kSmemMax) {
+                dsm3 = false;
+                tot = field_layout_total(prec, Q, false);
+            }
+            if (tot <= kSmemMax) {
+                P = Q;
+                c->d_in_smem = dsm3 ? 1 : 0;
+                c->smem = std::max(tot, c->smem_ls);
+            }
+        }
+    }
     const int e = field_kernel_configure(prec, c->kc.mr, c->kc.mc, c->smem);
     if (e != 0) return fail(SRHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu B shared) failed: %s", c->smem, cudaGetErrorString((cudaError_t)e));
     if (prec == 64) {
@@ -950,8 +982,8 @@ static int ls_common(srhmc_ctx* c, LsArgs& A, const double* q0, const double* p0
 
 static int ls_launch(srhmc_ctx* c, const LsArgs& A) {
     if (c->timed) CU_TRY(cudaEventRecord(c->ev0, c->stream));
-    const int rc = ls_kernel_launch(c->kc.mr, c->kc.mc, std::max(1, A.n_fields), c->threads, c->smem, c->stream, c->P, A,
-                                    c->ls_scratch.as<double>(), c->d_in_smem);
+    const int rc = ls_kernel_launch(c->kc.mr, c->kc.mc, std::max(1, A.n_fields), c->threads, c->smem, c->stream, c->P_ls, A,
+                                    c->ls_scratch.as<double>(), c->dsm_ls);
     if (rc != 0) return fail(SRHMC_ERR_CUDA, "lightsource kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (c->timed) CU_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
