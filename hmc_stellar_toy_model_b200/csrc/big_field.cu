@@ -19,6 +19,7 @@
 // Tiling: a rank owns global rows [own_lo, own_hi) and holds data rows [row0, row0+nrows) (strip + halo).  Owned
 // stars may drift `halo - patch_radius` rows outside the strip; neighbours' stars that can touch the local rows
 // arrive as ghosts (f, x, y) in the gathered boundary buffers and are only rendered, never updated.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -717,6 +718,9 @@ struct srhmc_big {
     BBuf epart, tickets;  // per-block energy partials; last-block tickets [0] energy, [1] tile potential
     int nty = 0, ntx = 0;
     bool use_tiles = false;
+    bool tma = false;          // a tensor map over the data window exists: the tile kernels load their tile by TMA
+    bool tile2 = false;        // persistent variant (big_tile2_kernel, SRHMC_TILE_V2=1) instead of one CTA per tile
+    CUtensorMap tmapD{};
     int world = 1, rank = 0;
     bool have_data = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -786,6 +790,43 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
         if (!rc && (cudaFuncSetAttribute(big_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess ||
                     cudaFuncSetAttribute(big_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess))
             rc = 1;
+    }
+    if (!rc && b->use_tiles) {
+        // 2-D tensor map over the FP64 data window [nrows, C] with 64 x 64 boxes for the TMA tile loads
+        bool want = (cfg->cols % 2) == 0;   // global row stride must be a multiple of 16 bytes
+        if (const char* e = std::getenv("SRHMC_TILE_TMA"))
+            if (e[0] == '0') want = false;   // A/B: cp.async staging
+        // Measured on 8192^2 / 1e5 stars: one CTA per tile 323 M star-steps/s, persistent variant 308 -- the persistent
+        // kernel is kept selectable, the default is the faster one.
+        bool want2 = false;
+        if (const char* e = std::getenv("SRHMC_TILE_V2")) want2 = e[0] == '1';
+        if (want) {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+                qres == cudaDriverEntryPointSuccess) {
+                const cuuint64_t dims[2] = {(cuuint64_t)cfg->cols, (cuuint64_t)cfg->nrows};
+                const cuuint64_t strides[1] = {(cuuint64_t)cfg->cols * 8};
+                const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)kTile};
+                const cuuint32_t estr[2] = {1, 1};
+                const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&b->tmapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, b->D.ptr, dims, strides, box,
+                                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                b->tma = cr == CUDA_SUCCESS;
+            } else {
+                cudaGetLastError();
+            }
+            b->tile2 = b->tma && want2;
+            if (b->tile2 &&
+                (cudaFuncSetAttribute(big_tile2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)) != cudaSuccess ||
+                 cudaFuncSetAttribute(big_tile2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)) != cudaSuccess)) {
+                cudaGetLastError();
+                b->tile2 = false;
+            }
+        }
     }
     rc |= b->q.ensure(S * 8); rc |= b->p.ensure(S * 8); rc |= b->g.ensure(S * 8);
     rc |= b->a1.ensure(S * 8); rc |= b->a2.ensure(S * 8 + (size_t)cfg->max_stars * 4 + 8);
@@ -896,7 +937,8 @@ int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t 
             big_bin_kernel<<<std::max(1, std::min((n + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
                 b->P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
         big_tile_kernel<2><<<(int)ntiles, kTileThreads, sizeof(TileSmem), st>>>(b->P, S, b->ntx, nullptr, b->tcnt.as<int>(), b->tlist.as<int2>(),
-                                                                                nullptr, nullptr, nullptr, nullptr, nullptr, b->D.as<double>(), seed);
+                                                                                nullptr, nullptr, nullptr, nullptr, nullptr, b->D.as<double>(), seed,
+                                                                                b->tmapD, 0);
         b->launches += 2;
         e = cudaGetLastError();
     }
@@ -1146,14 +1188,28 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                     b->launches += 1;
                 }
                 b->own_binned = false;  // the tile kernel consumes the lists and re-zeroes the counters
-                if (want_V)
+                if (b->tile2) {
+                    int grid2 = std::min(ntiles, 4 * b->sm_count);   // persistent: 4 CTAs per SM walk the tiles
+                    if (const char* e = std::getenv("SRHMC_TILE_GRID")) {   // experiments: CTAs per SM, 0 = one CTA per tile
+                        const int k = std::atoi(e);
+                        grid2 = k <= 0 ? ntiles : std::min(ntiles, k * b->sm_count);
+                    }
+                    if (want_V)
+                        big_tile2_kernel<true><<<grid2, kTileThreads, sizeof(Tile2Smem), st>>>(P, S, b->tmapD, b->ntx, ntiles, b->tcnt.as<int>(),
+                            b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
+                            b->scalars.as<double>(), cnt);
+                    else
+                        big_tile2_kernel<false><<<grid2, kTileThreads, sizeof(Tile2Smem), st>>>(P, S, b->tmapD, b->ntx, ntiles, b->tcnt.as<int>(),
+                            b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
+                            b->scalars.as<double>(), cnt);
+                } else if (want_V)
                     big_tile_kernel<1><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
                         b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
-                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull);
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull, b->tmapD, b->tma ? 1 : 0);
                 else
                     big_tile_kernel<0><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
                         b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
-                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull);
+                        b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull, b->tmapD, b->tma ? 1 : 0);
                 b->launches += 1;
                 if (tail == 0) {
                     big_gsum_kernel<<<gs, tb, 0, st>>>(P, b->q.as<double>(), n, b->gpart.as<double>(), b->g.as<double>());
