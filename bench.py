@@ -770,7 +770,7 @@ def run_ours(args):
 
     def c5(weak):
         return bench_bigfield(env, rows=args.rows, cols=args.cols, nstars=args.stars, weak=weak, niter=args.c5_niter,
-                              steps=args.sub_steps if which == "all" else args.steps, warmup=3, e2e_steps=2,
+                              steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
                               comm_kind=args.comm, with_parity=not weak)
 
     if which == "c4":

@@ -213,6 +213,95 @@ __global__ void big_gather_kernel(const BigParams P, const double* q, int n_own,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ peer exchange
+// Collectives of the tiled field done by our own kernels over peer-mapped memory (NVLink P2P between the GPUs of a node;
+// CUDA IPC between their processes) instead of NCCL: every rank owns one PeerBox that all ranks can address.  A
+// contribution is `payload, then tag = epoch` (system-scope fence in between); the receiver spins on the tag.  Slots are
+// double-buffered by epoch parity: a rank can run at most one exchange ahead of a peer, because finishing exchange k+1
+// needs the peer's k+1 contribution, which the peer sends only after it has consumed exchange k.  Epochs live in device
+// memory and are advanced by the kernels themselves, so a captured CUDA graph of an iteration can be replayed.
+constexpr int kMaxWorld = 16;
+
+struct PeerSlot {                 // one small-vector contribution
+    unsigned long long tag;
+    double v[8];
+    double pad[7];                // 128 bytes
+};
+
+struct PeerHeader {
+    PeerSlot ar[2][kMaxWorld];    // [epoch parity][source rank]
+    unsigned long long gtag[2][2];  // ghost mailboxes [parity][side]: tag
+};
+// ghost mailbox payloads follow the header: [parity][side][list doubles]
+
+struct PeerPtrs {
+    unsigned char* box[kMaxWorld];
+};
+
+__device__ __forceinline__ void peer_publish_tag(unsigned long long* tag, unsigned long long e) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(tag) = e;
+}
+
+// spin until *tag >= e; false (and err flag 4) after ~5 s so that a lost peer cannot hang the GPU; once the flag is up
+// every later wait gives up at once
+__device__ __forceinline__ bool peer_wait_tag(const unsigned long long* tag, unsigned long long e, int* err) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned long long*>(tag) < e) {
+        if (*reinterpret_cast<volatile int*>(err) == 4) return false;
+        if (clock64() - t0 > 10000000000LL) {
+            atomicExch(err, 4);
+            return false;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
+
+// The field-wide maximum of a fixed-point count taken INSIDE the kernel that consumes it (no separate exchange kernel):
+// block 0 sends this rank's count to every rank's mailbox, every block waits for the world's contributions in its OWN
+// rank's mailbox (local memory) and takes the maximum; the last block to leave the kernel advances the epoch, so every
+// block of the launch sees the same one.
+struct PeerX {
+    PeerPtrs peers;
+    int rank, world, on;
+    unsigned long long* epoch;
+    unsigned int* ticket;
+    int* err;
+};
+
+__device__ __forceinline__ int peer_max_in_kernel(const PeerX& X, int local) {
+    __shared__ int s_max;
+    const unsigned long long e = X.epoch[0] + 1;
+    const int par = (int)(e & 1), t = threadIdx.x;
+    if (t == 0) s_max = local;
+    __syncthreads();
+    if (t < X.world) {
+        if (blockIdx.x == 0) {
+            PeerSlot* s = &reinterpret_cast<PeerHeader*>(X.peers.box[t])->ar[par][X.rank];
+            s->v[0] = (double)local;
+            peer_publish_tag(&s->tag, e);
+        }
+        const PeerSlot* mine = &reinterpret_cast<const PeerHeader*>(X.peers.box[X.rank])->ar[par][t];
+        if (peer_wait_tag(&mine->tag, e, X.err)) atomicMax(&s_max, (int)__ldcv(&mine->v[0]));
+    }
+    __syncthreads();
+    return s_max;
+}
+
+__device__ __forceinline__ void peer_epoch_advance(const PeerX& X) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(X.ticket, 1u) == gridDim.x - 1) {
+            X.epoch[0] += 1;
+            *X.ticket = 0u;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ scalar kernels
 struct BigStep {
     double h, delta, g_ff2;
@@ -255,8 +344,8 @@ __global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, cons
 
 // p fixed point phase B (continue to the global count), then (3) q fixed point phase A
 __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, double* a1, double* a2,
-                                     const int* cnt_p, int* cnt_q) {
-    const int target = *cnt_p;
+                                     const int* cnt_p, int* cnt_q, const PeerX X) {
+    const int target = X.on ? peer_max_in_kernel(X, *cnt_p) : *cnt_p;
     int local_max = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         double pf = p[3 * k];
@@ -290,13 +379,14 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
         reinterpret_cast<int*>(a2 + 3 * (size_t)n)[k] = c;
     }
     if (local_max) atomicMax(cnt_q, local_max);
+    if (X.on) peer_epoch_advance(X);
 }
 
 // q fixed point phase B, then (4) p -= h dtau/dq at the new q
 // and -- tile path -- the pair records of the star's final position for the coming evaluation (bin_star, big_tile.cuh)
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
-                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err) {
-    const int target = *cnt_q;
+                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err, const PeerX X) {
+    const int target = X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
         const double bf = a2[3 * k], bx = a2[3 * k + 1], by = a2[3 * k + 2];
@@ -313,6 +403,7 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
         p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
         if (tcnt) bin_star(P, ntx, k, qx, qy, true, tcnt, tlist, err);
     }
+    if (X.on) peer_epoch_advance(X);
 }
 
 // (5) p -= h dphi/dq at the new q; (6) reflections
@@ -559,52 +650,6 @@ __global__ void big_pack_kernel(int n, const double* q, double lo_edge, double h
     }
 }
 
-// ------------------------------------------------------------------------------------------------ peer exchange
-// Collectives of the tiled field done by our own kernels over peer-mapped memory (NVLink P2P between the GPUs of a node;
-// CUDA IPC between their processes) instead of NCCL: every rank owns one PeerBox that all ranks can address.  A
-// contribution is `payload, then tag = epoch` (system-scope fence in between); the receiver spins on the tag.  Slots are
-// double-buffered by epoch parity: a rank can run at most one exchange ahead of a peer, because finishing exchange k+1
-// needs the peer's k+1 contribution, which the peer sends only after it has consumed exchange k.  Epochs live in device
-// memory and are advanced by the kernels themselves, so a captured CUDA graph of an iteration can be replayed.
-constexpr int kMaxWorld = 16;
-
-struct PeerSlot {                 // one small-vector contribution
-    unsigned long long tag;
-    double v[8];
-    double pad[7];                // 128 bytes
-};
-
-struct PeerHeader {
-    PeerSlot ar[2][kMaxWorld];    // [epoch parity][source rank]
-    unsigned long long gtag[2][2];  // ghost mailboxes [parity][side]: tag
-};
-// ghost mailbox payloads follow the header: [parity][side][list doubles]
-
-struct PeerPtrs {
-    unsigned char* box[kMaxWorld];
-};
-
-__device__ __forceinline__ void peer_publish_tag(unsigned long long* tag, unsigned long long e) {
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(tag) = e;
-}
-
-// spin until *tag >= e; false (and err flag 4) after ~5 s so that a lost peer cannot hang the GPU; once the flag is up
-// every later wait gives up at once
-__device__ __forceinline__ bool peer_wait_tag(const unsigned long long* tag, unsigned long long e, int* err) {
-    const long long t0 = clock64();
-    while (*reinterpret_cast<const volatile unsigned long long*>(tag) < e) {
-        if (*reinterpret_cast<volatile int*>(err) == 4) return false;
-        if (clock64() - t0 > 10000000000LL) {
-            atomicExch(err, 4);
-            return false;
-        }
-        __nanosleep(100);
-    }
-    __threadfence_system();
-    return true;
-}
-
 // all-reduce of a small vector: op 0 = max of n ints (in place), op 1 = sum of n doubles (in -> out), rank order
 __global__ void big_xchg_small_kernel(const PeerPtrs peers, int rank, int world, int op, int n, int* ivals, const double* din,
                                       double* dout, unsigned long long* epoch, int* err) {
@@ -641,7 +686,8 @@ __global__ void big_xchg_small_kernel(const PeerPtrs peers, int rank, int world,
 // boundary-star lists straight into the neighbours' mailboxes, then the received lists into the local `recv` layout
 // ([source rank][list][1 + 3 cap]) the evaluation reads: list 1 of rank-1 and list 0 of rank+1
 __global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
-                                      unsigned long long* epoch, int* err) {
+                                      unsigned long long* epoch, int* err, const BigParams P, int ntx, int n_own, int cap, int* tcnt,
+                                      int2* tlist) {
     const unsigned long long e = epoch[1] + 1;
     const int par = (int)(e & 1);
     auto mailbox = [&](int r, int side) {
@@ -677,6 +723,17 @@ __global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world,
     }
     __syncthreads();
     if (threadIdx.x == 0) epoch[1] = e;
+    // the received ghosts go straight into the tile lists (what a separate binning kernel used to do before the evaluation)
+    if (tcnt) {
+        for (int side = 0; side < 2; ++side) {
+            const int nb = side == 0 ? rank - 1 : rank + 1;
+            if (nb < 0 || nb >= world) continue;
+            const double* g = recv + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * list;
+            const int ng = min((int)g[0], cap);
+            for (int k = threadIdx.x; k < ng; k += blockDim.x)
+                bin_star(P, ntx, n_own + side * cap + k, g[2 + 3 * k], g[3 + 3 * k], false, tcnt, tlist, err);
+        }
+    }
 }
 
 struct BBuf {
@@ -711,7 +768,8 @@ struct srhmc_big {
     BBuf tcnt, tlist, gpart;
     bool own_binned = false;
     // peer exchange (our own collectives over P2P / IPC mapped memory)
-    BBuf peerbox, xepoch, packcnt;
+    BBuf peerbox, xepoch, packcnt, xticket;
+    bool ghosts_binned = false;   // the ghost exchange kernel has already put the received ghosts into the tile lists
     PeerPtrs peers{};
     void* ipc_opened[kMaxWorld] = {};
     bool peer_enabled = false;  // the pair records of the owned stars' current positions are already in the tile lists
@@ -861,7 +919,7 @@ int srhmc_big_destroy(srhmc_big* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
                    &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A,
-                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets, &b->xepoch, &b->packcnt};
+                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets, &b->xepoch, &b->packcnt, &b->xticket};
     for (BBuf* x : all) x->release();
     for (int r = 0; r < kMaxWorld; ++r)
         if (b->ipc_opened[r]) cudaIpcCloseMemHandle(b->ipc_opened[r]);
@@ -966,9 +1024,10 @@ int srhmc_big_set_stars(srhmc_big* b, const double* q, const int64_t* global_ids
         BCU(cudaMemcpyAsync(b->gid.ptr, global_ids, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
     }
     BCU(cudaMemsetAsync(b->p.ptr, 0, 3 * (size_t)b->cfg.max_stars * 8, b->stream));
-    if (b->own_binned) {  // records of the previous positions
+    if (b->own_binned || b->ghosts_binned) {  // records of the previous positions
         BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, b->stream));
         b->own_binned = false;
+        b->ghosts_binned = false;
     }
     BCU(cudaStreamSynchronize(b->stream));
     b->n = n;
@@ -1008,8 +1067,10 @@ int srhmc_big_comm_export(srhmc_big* b, void* ipc_handle_64, void** raw_ptr) {
         // a dedicated allocation: cudaIpcGetMemHandle exports the whole cudaMalloc block
         if (int rc = b->peerbox.ensure(peer_box_bytes(b))) return rc;
         if (int rc = b->xepoch.ensure(16)) return rc;
+        if (int rc = b->xticket.ensure(16)) return rc;
         BCU(cudaMemset(b->peerbox.ptr, 0, peer_box_bytes(b)));
         BCU(cudaMemset(b->xepoch.ptr, 0, 16));
+        BCU(cudaMemset(b->xticket.ptr, 0, 16));
     }
     if (ipc_handle_64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1144,6 +1205,12 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
     const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
     int* cnt = b->counters.as<int>();
     cudaStream_t st = b->stream;
+    PeerX X;
+    std::memset(&X, 0, sizeof(X));
+    if (b->peer_enabled && b->world > 1) {
+        X.peers = b->peers; X.rank = b->rank; X.world = b->world; X.on = 1;
+        X.epoch = b->xepoch.as<unsigned long long>(); X.ticket = b->xticket.as<unsigned int>(); X.err = b->err.as<int>();
+    }
     switch (phase) {
         case SRHMC_BIG_PACK: {
             // boundary lists for the neighbours: everything that can touch their data rows
@@ -1156,8 +1223,12 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                                                  std::max(1, b->cfg.max_ghosts), b->err.as<int>());
             b->launches += 2;
             if (b->peer_enabled && b->world > 1) {  // the exchange itself: our own kernel over peer memory
+                // ... which also puts the received ghosts into the tile lists (no separate binning kernel before the evaluation)
                 big_xchg_ghost_kernel<<<1, 256, 0, st>>>(b->peers, b->rank, b->world, b->send.as<double>(), b->recv.as<double>(), list,
-                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>(), P, b->ntx, n,
+                                                         std::max(1, b->cfg.max_ghosts), b->use_tiles ? b->tcnt.as<int>() : nullptr,
+                                                         b->use_tiles ? b->tlist.as<int2>() : nullptr);
+                b->ghosts_binned = b->use_tiles;
                 b->launches += 1;
             }
             break;
@@ -1182,12 +1253,13 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                         P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
                     b->launches += 1;
                 }
-                if (ga || gb) {
+                if ((ga || gb) && !b->ghosts_binned) {
                     big_bin_kernel<<<std::max(1, std::min((2 * S.cap + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
                         P, S, b->ntx, n, n + 2 * S.cap, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
                     b->launches += 1;
                 }
                 b->own_binned = false;  // the tile kernel consumes the lists and re-zeroes the counters
+                b->ghosts_binned = false;
                 if (b->tile2) {
                     int grid2 = std::min(ntiles, 4 * b->sm_count);   // persistent: 4 CTAs per SM walk the tiles
                     if (const char* e = std::getenv("SRHMC_TILE_GRID")) {   // experiments: CTAs per SM, 0 = one CTA per tile
@@ -1248,26 +1320,19 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_PFIX_QFIX:
-            if (b->peer_enabled && b->world > 1) {  // field-wide maximum of the p fixed-point counts
-                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
-                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
-                b->launches += 1;
-            }
+            // tiled over peers: the field-wide maximum of the p fixed-point counts is taken inside the kernel (PeerX)
             big_pfix_qfix_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
-                                                    b->a2.as<double>(), cnt, cnt + 1);
+                                                    b->a2.as<double>(), cnt, cnt + 1, X);
             b->launches += 1;
             break;
         case SRHMC_BIG_QFIX_KICK:
-            if (b->peer_enabled && b->world > 1) {  // field-wide maximum of the q fixed-point counts
-                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
-                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
-                b->launches += 1;
-            }
-            if (b->use_tiles && b->own_binned)  // records nobody consumed (two position updates without an evaluation)
+            if (b->use_tiles && (b->own_binned || b->ghosts_binned)) {  // records nobody consumed (two position updates without an evaluation)
                 BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
+                b->ghosts_binned = false;
+            }
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt + 1, b->ntx, b->use_tiles ? b->tcnt.as<int>() : nullptr,
-                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>());
+                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>(), X);
             b->own_binned = b->use_tiles;
             b->launches += 1;
             break;

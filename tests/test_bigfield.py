@@ -3,6 +3,7 @@ boundary lists), and on the GPU the untiled engine against the CTA-resident kern
 one device through LocalComm against the untiled engine."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -387,3 +388,52 @@ def test_peer_comm_distributes_handles_in_rank_order():
     strips = [_FakeStrip(r, 3) for r in (2, 0, 1)]
     comm = bf.PeerComm(strips)
     assert comm.in_process and all(s.imported == [0x1000, 0x2000, 0x3000] for s in strips)
+
+
+@pytest.mark.gpu
+def test_bigfield_full_size_spot_check_against_patch_oracle():
+    """BASELINE configs[4] at full size (8192 x 8192, 1e5 stars, device mock data): the pixel gradients of 200 random stars
+    against the NumPy patch-limited restatement evaluated on an 81 x 81 crop around each star (every star whose patch can
+    overlap the star's patch has its centre inside the crop); stars next to the image edges are always among them."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_for_bigfield", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    rows = cols = 8192
+    n = 100000
+    t = bench.c5_truth(rows, cols, n, 77)
+    c = t["consts"]
+    S = so.Setup(num_rows=rows, num_cols=cols, g_xx=c["g_xx"], g_ff=c["g_ff"], g_ff2=4.0, use_prior=True, alpha=c["alpha"],
+                 V_prior_const=c["V_prior_const"])
+    strip = bf.BigFieldStrip(rows=rows, cols=cols, rank=0, world=1, device=0, max_stars=n, max_ghosts=1, patch_radius=12,
+                             halo=24, **c)
+    D = strip.gen_mock_data(t["q_true"], seed=77, return_data=True)
+    q0 = t["q0"]
+    strip.set_stars(q0)
+    eng = bf.BigFieldRHMC([strip])
+    eng.evaluate(want_V=True, g_ff2=4.0)
+    grad = eng.stars(n)[2]
+    rng = np.random.RandomState(1)
+    near_edge = np.nonzero((q0[:, 1] < 14) | (q0[:, 1] > rows - 14) | (q0[:, 2] < 14) | (q0[:, 2] > cols - 14))[0][:20]
+    picks = np.unique(np.concatenate([rng.choice(n, 180, replace=False), near_edge]))
+    worst = 0.0
+    scale = np.max(np.abs(grad), axis=0)
+    for k in picks:
+        x, y = q0[k, 1], q0[k, 2]
+        i0, i1 = max(0, int(np.floor(x)) - 40), min(rows, int(np.floor(x)) + 41)
+        j0, j1 = max(0, int(np.floor(y)) - 40), min(cols, int(np.floor(y)) + 41)
+        sel = np.nonzero((np.abs(q0[:, 1] - x) <= 26) & (np.abs(q0[:, 2] - y) <= 26))[0]
+        qs = q0[sel] - np.array([0.0, i0, j0])
+        Sc = S.clone(num_rows=i1 - i0, num_cols=j1 - j0)
+        _, go = so.patch_eval(Sc, D[i0:i1, j0:j1], qs, rad=12)
+        mine = go[np.nonzero(sel == k)[0][0]]
+        err = np.abs(grad[k] - mine) / np.maximum(np.abs(mine), 1e-6 * scale)
+        worst = max(worst, float(err.max()))
+    assert worst < 1e-9, worst
+    strip.close()
