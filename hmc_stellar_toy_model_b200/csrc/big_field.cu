@@ -770,6 +770,10 @@ struct srhmc_big {
     // peer exchange (our own collectives over P2P / IPC mapped memory)
     BBuf peerbox, xepoch, packcnt, xticket;
     bool ghosts_binned = false;   // the ghost exchange kernel has already put the received ghosts into the tile lists
+    // Measured on 2 x B200 (8192^2 split in two strips): taking the fixed-point maxima inside their consumer kernels is
+    // SLOWER than the separate one-block exchange kernels (451 against 496 M star-steps/s: every block of the consumer polls
+    // the mailbox line the peer is writing), binning the ghosts in the exchange kernel is neutral and saves a launch.
+    bool fuse_max = false, fuse_bin = true;   // SRHMC_PEER_FUSE_MAX=1 / SRHMC_PEER_FUSE_BIN=0 switch them
     PeerPtrs peers{};
     void* ipc_opened[kMaxWorld] = {};
     bool peer_enabled = false;  // the pair records of the owned stars' current positions are already in the tile lists
@@ -1114,6 +1118,8 @@ int srhmc_big_comm_import(srhmc_big* b, const void* ipc_handles, void* const* ra
         }
     }
     b->peer_enabled = true;
+    if (const char* e = std::getenv("SRHMC_PEER_FUSE_MAX")) b->fuse_max = e[0] == '1';
+    if (const char* e = std::getenv("SRHMC_PEER_FUSE_BIN")) b->fuse_bin = e[0] != '0';
     return 0;
 }
 
@@ -1207,7 +1213,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
     cudaStream_t st = b->stream;
     PeerX X;
     std::memset(&X, 0, sizeof(X));
-    if (b->peer_enabled && b->world > 1) {
+    if (b->peer_enabled && b->world > 1 && b->fuse_max) {
         X.peers = b->peers; X.rank = b->rank; X.world = b->world; X.on = 1;
         X.epoch = b->xepoch.as<unsigned long long>(); X.ticket = b->xticket.as<unsigned int>(); X.err = b->err.as<int>();
     }
@@ -1226,9 +1232,9 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 // ... which also puts the received ghosts into the tile lists (no separate binning kernel before the evaluation)
                 big_xchg_ghost_kernel<<<1, 256, 0, st>>>(b->peers, b->rank, b->world, b->send.as<double>(), b->recv.as<double>(), list,
                                                          b->xepoch.as<unsigned long long>(), b->err.as<int>(), P, b->ntx, n,
-                                                         std::max(1, b->cfg.max_ghosts), b->use_tiles ? b->tcnt.as<int>() : nullptr,
+                                                         std::max(1, b->cfg.max_ghosts), (b->use_tiles && b->fuse_bin) ? b->tcnt.as<int>() : nullptr,
                                                          b->use_tiles ? b->tlist.as<int2>() : nullptr);
-                b->ghosts_binned = b->use_tiles;
+                b->ghosts_binned = b->use_tiles && b->fuse_bin;
                 b->launches += 1;
             }
             break;
@@ -1320,12 +1326,22 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_PFIX_QFIX:
+            if (b->peer_enabled && b->world > 1 && !b->fuse_max) {
+                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
+                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             // tiled over peers: the field-wide maximum of the p fixed-point counts is taken inside the kernel (PeerX)
             big_pfix_qfix_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt, cnt + 1, X);
             b->launches += 1;
             break;
         case SRHMC_BIG_QFIX_KICK:
+            if (b->peer_enabled && b->world > 1 && !b->fuse_max) {
+                big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
+                                                        b->xepoch.as<unsigned long long>(), b->err.as<int>());
+                b->launches += 1;
+            }
             if (b->use_tiles && (b->own_binned || b->ghosts_binned)) {  // records nobody consumed (two position updates without an evaluation)
                 BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
                 b->ghosts_binned = false;

@@ -4,4 +4,4 @@
 TAG=$1; shift
 env "$@" python bench.py --workload c5 --steps 5 --no-cpu 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.readline()); print('$TAG', '$*', round(d['value']/1e6,1), 'M/s', round(d['ms_per_step'],2), 'ms', round(d['roofline']['frac'],3))"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$TAG', '$*', round(d['value']/1e6,1), 'M/s', round(d['ms_per_step'],2), 'ms', round(d['roofline']['frac'],3))"
