@@ -781,8 +781,17 @@ def run_ours(args):
         out = c2()
     if rank == 0 and out is not None:
         out["cpu_baseline"] = cpu.get("c2" if which == "all" else which)
+    def c2_fp32():
+        wl = workload_c2(args.chains_per_mag, 77 + rank)
+        wl["name"] = "c2_one_star_32x32_fp32"
+        return bench_chains(env, wl, niter=args.niter, steps=args.sub_steps, warmup=3, e2e_steps=2,
+                            want=("q", "p", "E", "V", "T", "A"), precision=32, scaling="weak", seed_base=0,
+                            parallelism="independent chains sharded across %d GPU(s), no communication; FP32 pixel "
+                            "arithmetic for the gradient-only evaluations, FP64 state and energies" % world)
+
     if which == "all":
         subs = {}
+        subs["c2_fp32"] = guarded(env, "c2_fp32", c2_fp32)
         subs["c4"] = guarded(env, "c4", c4)
         subs["c5"] = guarded(env, "c5", lambda: c5(False))
         if world > 1:

@@ -86,6 +86,19 @@ __device__ __forceinline__ double ld_pix(const double* p) { return *p; }
 // (a MOV plus a DADD on the FP64 pipe)
 __device__ __forceinline__ double ld_pix(const unsigned int* p) { return (double)*p; }
 __device__ __forceinline__ double ld_pix(const unsigned short* p) { return (double)(unsigned int)*p; }
+// FP32 build (north_star: "<= 1e-4 in the FP32 build"): pixel as float, reciprocal by MUFU.RCP alone
+__device__ __forceinline__ float ld_pixf(const double* p) { return (float)*p; }
+__device__ __forceinline__ float ld_pixf(const unsigned int* p) { return (float)*p; }
+// uint16 count -> float without the conversion unit (the FP32 loop is bound by the XU pipe: MUFU.RCP + I2F per pixel):
+// 2^23 + d is exact for d < 2^16, so OR-ing d into the mantissa of 2^23 and subtracting 2^23 converts on the ALU / FP32 pipes
+__device__ __forceinline__ float ld_pixf(const unsigned short* p) {
+    return __uint_as_float(0x4B000000u | (unsigned int)*p) - 8388608.0f;
+}
+__device__ __forceinline__ float rcp_pixf(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 // (Measured and not adopted: feeding the count as the double 2^52 + d with fma(X, r, -2^52 r) = round(d r) removes the
 // I2F from the pixel loop but costs three integer instructions per pixel: 1422 against 1472 M star-steps/s.)
 #ifdef SRHMC_EXP_NEWTON2
@@ -175,9 +188,15 @@ __device__ __forceinline__ void row_window(float xc, float peak, float thresh, f
 // warp sees there (see rows_all_slots).  Code size matters here: a build that unrolled per-slot tier loops grew the
 // kernel to 30k instructions and spent 31% of its issue slots waiting for instruction fetch, so the kernel is
 // specialised per mode (template MODE) and the tier loops are kept compact.  `vconst` is the bracketed constant of this chain's image.
-template <int LPC, int NCS, bool WANT_V, typename DT>
+// PT = float selects the FP32 pixel arithmetic for the gradient-only evaluations (9 of 10 in a chain): float row table,
+// float Lambda / rho / column sums, MUFU.RCP; the star state, the tables' recurrences, the final reductions and every
+// evaluation that also returns the potential (WANT_V) stay FP64 -- so the energies of the Metropolis test are exact for
+// the state reached, and approximate gradients only change the proposal, not the target distribution.
+template <int LPC, int NCS, bool WANT_V, typename DT, typename PT = double>
 __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __restrict__ sD, double2* __restrict__ rt,
                                            const double2* __restrict__ ltab, int sub, double vconst, ChainState& s) {
+    constexpr bool F32 = sizeof(PT) == 4 && !WANT_V;
+    float2* __restrict__ rtf = reinterpret_cast<float2*>(rt + P.R);   // FP32 copy of the row table (allocated by the FP32 build)
     constexpr int CPL = NCS;            // column slots per lane
     constexpr int WIN = NCS * LPC;      // columns the chain's lanes cover
     constexpr unsigned FULL = 0xffffffffu;
@@ -223,7 +242,8 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
         const double r_dn = ok_r ? rcp_fast(w_r) * cLh : 0.0;
         double e = es, r = r_up, u = us;
         for (int k = ks; k < K; ++k) {
-            rt[sub + LPC * k] = make_double2(e, e * u);
+            if (F32) rtf[sub + LPC * k] = make_float2((float)e, (float)(e * u));
+            else rt[sub + LPC * k] = make_double2(e, e * u);
             if (WANT_V) sa += e;
             e *= r;
             r *= cL;
@@ -233,7 +253,8 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
         r = r_dn * cL;
         u = us - (double)LPC;
         for (int k = ks - 1; k >= 0; --k) {
-            rt[sub + LPC * k] = make_double2(e, e * u);
+            if (F32) rtf[sub + LPC * k] = make_float2((float)e, (float)(e * u));
+            else rt[sub + LPC * k] = make_double2(e, e * u);
             if (WANT_V) sa += e;
             e *= r;
             r *= cL;
@@ -265,7 +286,31 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
     int bad = 0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c0[c] = c1[c] = 0.0;
-    if (!WANT_V) {
+    if (F32) {
+        float feyf[CPL], c0f[CPL], c1f[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            feyf[c] = (float)fey[c];
+            c0f[c] = c1f[c] = 0.0f;
+        }
+        const float Bf = (float)P.B;
+#pragma unroll 2
+        for (int i = i_lo; i < i_hi; ++i) {
+            const float2 re = rtf[i];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const float lam = fmaf(re.x, feyf[c], Bf);
+                const float rho = fmaf(ld_pixf(sD + i * kChainCS + jb + LPC * c), rcp_pixf(lam), -1.0f);
+                c0f[c] = fmaf(rho, re.x, c0f[c]);
+                c1f[c] = fmaf(rho, re.y, c1f[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            c0[c] = (double)c0f[c];
+            c1[c] = (double)c1f[c];
+        }
+    } else if (!WANT_V) {
 #ifndef SRHMC_MAIN_UNROLL
 #define SRHMC_MAIN_UNROLL 2
 #endif
@@ -366,7 +411,7 @@ __device__ __forceinline__ void chain_energies(const FieldParams& P, const Chain
 
 // base_class.RHMC_single_step for a one-star field, state in registers (sampler_RHMC.py:522-566).
 // Requires s.g*, s.u, s.kap, s.ihxx, s.tphi valid at s.f on entry; leaves them valid on exit.
-template <int LPC, int NCS, typename DT>
+template <int LPC, int NCS, typename DT, typename PT = double>
 __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainConst& K, const DT* sD, double2* rt,
                                            const double2* ltab, int sub, double vconst, ChainState& s, int counter_max,
                                            bool want_V, int& cnt_p, int& cnt_q) {
@@ -421,9 +466,9 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
     s.pf = fma(-(K.hh * s.kap), s.pf * s.pf, s.pf);
     // (5) gradient at the new q and last half kick
     if (want_V)
-        chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
+        chain_eval<LPC, NCS, true, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
     else
-        chain_eval<LPC, NCS, false>(P, sD, rt, ltab, sub, vconst, s);
+        chain_eval<LPC, NCS, false, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
     {
         double gf = s.gf + s.tphi;
         if (P.use_prior) gf = fma(P.alpha, rcp_fast(s.f), gf);
@@ -438,9 +483,10 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
 }
 
 #ifndef SRHMC_CHAIN_MAXREG
-#define SRHMC_CHAIN_MAXREG (LPC <= 4 ? 232 : 168)
+#define SRHMC_CHAIN_MAXREG (kChainLPC <= 4 ? 232 : 168)
 #endif
-template <int LPC, typename DT, int MODE, int NCS, int MAXREG = SRHMC_CHAIN_MAXREG>
+constexpr int kChainMaxReg = SRHMC_CHAIN_MAXREG;
+template <int LPC, typename DT, int MODE, int NCS, int MAXREG = kChainMaxReg, typename PT = double>
 __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldParams P, const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPC;  // chains per warp
@@ -449,11 +495,12 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
     const int R = P.R, C = P.C;
     // per-chain image stride padded by LPC elements: the GPW chains of a warp then sit on disjoint shared-memory banks
     const size_t img_elems = (size_t)R * kChainCS + chain_pad<DT>(LPC);
-    const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * sizeof(double2));
+    constexpr size_t kRowTab = sizeof(double2) + (sizeof(PT) == 4 ? sizeof(float2) : 0);   // per image row and chain
+    const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * kRowTab);
     double2* ltab = reinterpret_cast<double2*>(smem_raw);
     unsigned char* wbase = smem_raw + kLogTableSize * sizeof(double2) + (size_t)warp * warp_bytes;
     DT* sD = reinterpret_cast<DT*>(wbase) + (size_t)grp * img_elems;
-    double2* rt = reinterpret_cast<double2*>(wbase + (size_t)GPW * img_elems * sizeof(DT)) + (size_t)grp * R;
+    double2* rt = reinterpret_cast<double2*>(wbase + (size_t)GPW * img_elems * sizeof(DT) + (size_t)grp * R * kRowTab);
     const double h = A.dt / 2.0;
     for (int i = threadIdx.x; i < kLogTableSize; i += blockDim.x) ltab[i] = A.log_table[i];
     __syncthreads();
@@ -503,7 +550,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
         int cp = 0, cq = 0;
 
         if (MODE == MODE_EVAL) {
-            chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, true, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V, T;
             chain_energies(P, K, s, A.f_pos, ltab, V, T);
@@ -520,9 +567,9 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 if (A.Hgrad_out) { A.Hgrad_out[o] = m.dHff; A.Hgrad_out[o + 1] = m.dHxx; A.Hgrad_out[o + 2] = m.dHxx; }
             }
         } else if (MODE == MODE_STEP) {
-            chain_eval<LPC, NCS, false>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, false, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
-            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
+            for (int t = 0; t < A.nsteps; ++t) chain_step<LPC, NCS, DT, PT>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, false, cp, cq);
             if (writer) {
                 const size_t o = (size_t)field * 3;
                 A.q_out[o] = s.f; A.q_out[o + 1] = s.x; A.q_out[o + 2] = s.y;
@@ -531,7 +578,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             }
         } else if (MODE == MODE_SINGLE) {
             const size_t rows = (size_t)A.nsteps + 1;
-            chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
+            chain_eval<LPC, NCS, true, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
             refresh_metric(K, s);
             double V0, T0;
             chain_energies(P, K, s, A.f_pos, ltab, V0, T0);
@@ -542,7 +589,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                 A.E_chain[field * rows] = 0.0; A.V_chain[field * rows] = 0.0; A.T_chain[field * rows] = 0.0;
             }
             for (int t = 1; t <= A.nsteps; ++t) {
-                chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
+                chain_step<LPC, NCS, DT, PT>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, true, cp, cq);
                 double V, T;
                 chain_energies(P, K, s, A.f_pos, ltab, V, T);
                 if (writer) {
@@ -563,7 +610,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
             const int grp_id = base / GPW;
             int n_acc = 0;
             if (chunk == 0) {
-                chain_eval<LPC, NCS, true>(P, sD, rt, ltab, sub, vconst, s);
+                chain_eval<LPC, NCS, true, DT, PT>(P, sD, rt, ltab, sub, vconst, s);
             } else {
                 // wait until the previous chunk of this group has published its state (bounded spin: a scheduler
                 // fault must not hang the device)
@@ -625,7 +672,7 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
                     if (A.T_chain) A.T_chain[row] = T0;
                 }
                 for (int t = 0; t < A.nsteps; ++t)
-                    chain_step<LPC, NCS>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
+                    chain_step<LPC, NCS, DT, PT>(P, K, sD, rt, ltab, sub, vconst, s, A.counter_max, t == A.nsteps - 1, cp, cq);
                 double V1, T1;
                 chain_energies(P, K, s, A.f_pos, ltab, V1, T1);
                 const double dE = (V1 + T1) - E0;

@@ -30,59 +30,60 @@ bool use_column_window(const FieldParams& P) {
     return half * half * P.inv2s2 >= 46.0 * M_LN2;
 }
 
-size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem) {
+size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem, bool f32 = false) {
     const size_t gpw = 32 / lpc;
-    const size_t per_warp = gpw * (((size_t)P.R * kChainCS + lpc) * elem + (size_t)P.R * sizeof(double2));
+    const size_t rowtab = sizeof(double2) + (f32 ? sizeof(float2) : 0);
+    const size_t per_warp = gpw * (((size_t)P.R * kChainCS + lpc) * elem + (size_t)P.R * rowtab);
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
-template <typename DT, int MODE, int NCS>
+template <typename DT, int MODE, int NCS, typename PT = double>
 int configure_mode(size_t smem, int nw, int& blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE, NCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto fn = chain_kernel<kLPC, DT, MODE, NCS, kChainMaxReg, PT>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain_kernel<kLPC, DT, MODE, NCS>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<kLPC, DT, MODE, NCS>, 32 * nw, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 32 * nw, smem);
     if (e != cudaSuccess) return (int)e;
     if (nb < 1) return (int)cudaErrorInvalidConfiguration;
     blocks_per_sm = blocks_per_sm == 0 ? nb : std::min(blocks_per_sm, nb);
     return 0;
 }
 
-template <typename DT, int NCS>
+template <typename DT, int NCS, typename PT = double>
 int configure_slots(size_t smem, int nw, int& blocks_per_sm) {
-    if (int rc = configure_mode<DT, MODE_EVAL, NCS>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<DT, MODE_STEP, NCS>(smem, nw, blocks_per_sm)) return rc;
-    if (int rc = configure_mode<DT, MODE_RUN, NCS>(smem, nw, blocks_per_sm)) return rc;
-    return configure_mode<DT, MODE_SINGLE, NCS>(smem, nw, blocks_per_sm);
+    if (int rc = configure_mode<DT, MODE_EVAL, NCS, PT>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_STEP, NCS, PT>(smem, nw, blocks_per_sm)) return rc;
+    if (int rc = configure_mode<DT, MODE_RUN, NCS, PT>(smem, nw, blocks_per_sm)) return rc;
+    return configure_mode<DT, MODE_SINGLE, NCS, PT>(smem, nw, blocks_per_sm);
 }
 
-template <typename DT>
+template <typename DT, typename PT = double>
 int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
-    smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT));
+    smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT), sizeof(PT) == 4);
     blocks_per_sm = 0;
-    if (use_column_window(P)) return configure_slots<DT, kSlotsWin>(smem, nw, blocks_per_sm);
-    return configure_slots<DT, kSlotsFull>(smem, nw, blocks_per_sm);
+    if (use_column_window(P)) return configure_slots<DT, kSlotsWin, PT>(smem, nw, blocks_per_sm);
+    return configure_slots<DT, kSlotsFull, PT>(smem, nw, blocks_per_sm);
 }
 
-template <typename DT, int NCS>
+template <typename DT, int NCS, typename PT = double>
 void launch_slots(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
     switch (A.mode) {
-        case MODE_EVAL: chain_kernel<kLPC, DT, MODE_EVAL, NCS><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_STEP: chain_kernel<kLPC, DT, MODE_STEP, NCS><<<grid, threads, smem, stream>>>(P, A); break;
-        case MODE_SINGLE: chain_kernel<kLPC, DT, MODE_SINGLE, NCS><<<grid, threads, smem, stream>>>(P, A); break;
-        default: chain_kernel<kLPC, DT, MODE_RUN, NCS><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_EVAL: chain_kernel<kLPC, DT, MODE_EVAL, NCS, kChainMaxReg, PT><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_STEP: chain_kernel<kLPC, DT, MODE_STEP, NCS, kChainMaxReg, PT><<<grid, threads, smem, stream>>>(P, A); break;
+        case MODE_SINGLE: chain_kernel<kLPC, DT, MODE_SINGLE, NCS, kChainMaxReg, PT><<<grid, threads, smem, stream>>>(P, A); break;
+        default: chain_kernel<kLPC, DT, MODE_RUN, NCS, kChainMaxReg, PT><<<grid, threads, smem, stream>>>(P, A); break;
     }
 }
 
-template <typename DT>
+template <typename DT, typename PT = double>
 void launch_mode(int grid, int threads, size_t smem, cudaStream_t stream, const FieldParams& P, const LaunchArgs& A) {
     if (use_column_window(P))
-        launch_slots<DT, kSlotsWin>(grid, threads, smem, stream, P, A);
+        launch_slots<DT, kSlotsWin, PT>(grid, threads, smem, stream, P, A);
     else
-        launch_slots<DT, kSlotsFull>(grid, threads, smem, stream, P, A);
+        launch_slots<DT, kSlotsFull, PT>(grid, threads, smem, stream, P, A);
 }
 
 // Grid = (blocks per SM) x SMs with the per-SM count chosen so that every SM runs the same number of equally long
@@ -151,7 +152,9 @@ int chain_kernel_configure(const FieldParams& P, ChainLaunchPlan& plan) {
     plan.nw = kWarpsPerBlock;
     if (int rc = configure_one<double>(P, plan.nw, plan.smem_f64, plan.blocks_per_sm_f64)) return rc;
     if (int rc = configure_one<unsigned int>(P, plan.nw, plan.smem_u32, plan.blocks_per_sm_u32)) return rc;
-    return configure_one<unsigned short>(P, plan.nw, plan.smem_u16, plan.blocks_per_sm_u16);
+    if (int rc = configure_one<unsigned short>(P, plan.nw, plan.smem_u16, plan.blocks_per_sm_u16)) return rc;
+    // FP32 pixel arithmetic (precision-32 contexts) on the uint16 count images
+    return configure_one<unsigned short, float>(P, plan.nw, plan.smem_u16_f32, plan.blocks_per_sm_u16_f32);
 }
 
 // Iteration chunks per chain for a MODE_RUN launch of `groups` warp-sized work items on `warps` resident warps.
@@ -178,7 +181,8 @@ long long chain_kernel_resident_warps(const LaunchArgs& A, const ChainLaunchPlan
     const int chains_per_block = plan.nw * (32 / plan.lpc);
     const long long blocks = ((long long)n_fields + chains_per_block - 1) / chains_per_block;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
-    const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
+    const int max_k = (u16 && A.pix_f32) ? plan.blocks_per_sm_u16_f32
+                                         : (u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64));
     return std::min<long long>(blocks, (long long)max_k * sms) * plan.nw;
 }
 
@@ -191,7 +195,9 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     // 4 lanes per chain: 218 registers -> 8 resident single-warp blocks per SM (2 per scheduler); residency comes from the
     // occupancy query in chain_kernel_configure.  Register-capped 8-lane builds were measured earlier and are slower
     // (128 registers / 16 warps 1057 M star-steps/s, 112 / 18 warps 892 against 1104 at 168 / 12).
-    const int max_k = u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64);
+    const bool f32 = u16 && A.pix_f32;
+    const int max_k = f32 ? plan.blocks_per_sm_u16_f32
+                          : (u16 ? plan.blocks_per_sm_u16 : (A.D_int != nullptr ? plan.blocks_per_sm_u32 : plan.blocks_per_sm_f64));
     int grid = balanced_grid(max_k, blocks, sms);
     if (!(A.mode == MODE_RUN && A.sched_done != nullptr && A.chunk_count > 0)) A.n_chunks = 1;
     if (A.mode == MODE_RUN && A.sched_done != nullptr && A.chunk_count > 0) {
@@ -204,7 +210,9 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
         if (chunks > 1 && !std::getenv("SRHMC_CHAIN_BLOCKS_PER_SM")) grid = full;
         A.n_chunks = pick_chunks(blocks, (long long)grid * plan.nw, A.niter + 1);
     }
-    if (u16) {
+    if (f32) {
+        launch_mode<unsigned short, float>(grid, 32 * plan.nw, plan.smem_u16_f32, stream, P, A);
+    } else if (u16) {
         launch_mode<unsigned short>(grid, 32 * plan.nw, plan.smem_u16, stream, P, A);
     } else if (A.D_int != nullptr) {
         launch_mode<unsigned int>(grid, 32 * plan.nw, plan.smem_u32, stream, P, A);

@@ -85,6 +85,7 @@ struct LaunchArgs {
     const void* D;          // [n_images, R*C] in the pixel type
     const void* D_int;      // same images as exact unsigned integer counts, or nullptr (chain kernel, lossless)
     int D_int_bytes;        // 4: uint32, 2: uint16 (every count < 65536)
+    int pix_f32;            // chain kernel: FP32 pixel arithmetic for the gradient-only evaluations (precision-32 contexts)
     const double2* log_table;   // fastmath.cuh reciprocal/log table [kLogTableSize = 64]
     const int* nstars;      // [F] or nullptr
     // state in / out

@@ -11,8 +11,8 @@ namespace srhmc {
 struct ChainLaunchPlan {
     int lpc = 16;   // lanes per chain
     int nw = 4;     // warps per block
-    size_t smem_f64 = 0, smem_u32 = 0, smem_u16 = 0;
-    int blocks_per_sm_f64 = 0, blocks_per_sm_u32 = 0, blocks_per_sm_u16 = 0;
+    size_t smem_f64 = 0, smem_u32 = 0, smem_u16 = 0, smem_u16_f32 = 0;
+    int blocks_per_sm_f64 = 0, blocks_per_sm_u32 = 0, blocks_per_sm_u16 = 0, blocks_per_sm_u16_f32 = 0;
 };
 
 // CTA-per-field kernel (field_kernel.cuh); precision 64|32, (mr, mc) in {(2,4), (2,2), (1,2)}

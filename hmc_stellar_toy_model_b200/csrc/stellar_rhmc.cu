@@ -206,7 +206,9 @@ int configure(srhmc_ctx* c) {
 
 int launch_field(srhmc_ctx* c, const LaunchArgs& A_in, bool one_star_everywhere) {
     LaunchArgs A = A_in;
-    const bool chain = c->chain_ok && one_star_everywhere;
+    // the FP32 build of the one-star kernel reads the uint16 count images only
+    const bool chain = c->chain_ok && one_star_everywhere && (c->cfg.precision == 64 || c->d_int_bytes == 2);
+    A.pix_f32 = (chain && c->cfg.precision == 32) ? 1 : 0;
     if (chain && A.mode == MODE_RUN) {
         // scheduler state of the chunked chain kernel: completion counters start at 0 for every launch
         const size_t groups = ((size_t)A.n_fields + kChainGroup - 1) / kChainGroup;
@@ -249,8 +251,8 @@ int download(srhmc_ctx* c, void* dst, const DevBuf& b, size_t bytes) {
 bool chain_kernel_eligible(const srhmc_config& g) {
     const char* off = std::getenv("SRHMC_DISABLE_CHAIN_KERNEL");
     if (off && off[0] == '1') return false;
-    return g.precision == 64 && g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc &&
-           !g.shared_data && g.patch_radius == 0;
+    // precision 32: FP32 pixel arithmetic on the uint16 count images (data that are not counts < 65536 take the CTA kernel)
+    return g.max_stars == 1 && g.num_cols <= 32 && g.num_rows <= 64 && !g.use_Vc && !g.shared_data && g.patch_radius == 0;
 }
 
 bool all_one_star(const srhmc_ctx* c, const int32_t* nstars) {
@@ -443,13 +445,13 @@ static int finish_data(srhmc_ctx* c, size_t n) {
         c->launches += 1;
     }
     c->d_int_bytes = 0;
-    if (c->chain_ok && c->cfg.precision == 64) {
+    if (c->chain_ok) {
         // lossless compact copies for the warp-resident kernel when every pixel is an integer count (Poisson data)
         if (int rc = c->D32.ensure(n * 4)) return rc;
         if (int rc = c->D16.ensure(n * 2)) return rc;
         CU_TRY(cudaMemsetAsync(c->flag.ptr, 0, 4, c->stream));
-        const int e = to_counts_launch(c->stream, c->D.as<double>(), c->D32.as<unsigned int>(), c->D16.as<unsigned short>(), n,
-                                       c->flag.as<int>());
+        const double* d64 = c->cfg.precision == 64 ? c->D.as<double>() : c->Dstage.as<double>();
+        const int e = to_counts_launch(c->stream, d64, c->D32.as<unsigned int>(), c->D16.as<unsigned short>(), n, c->flag.as<int>());
         if (e != 0) return fail(SRHMC_ERR_CUDA, "count conversion failed: %s", cudaGetErrorString((cudaError_t)e));
         c->launches += 1;
         int flags = 3;
@@ -736,6 +738,7 @@ static int build_run_launch_args(srhmc_ctx* c, const srhmc_run_args* a, LaunchAr
     A.D = c->D.ptr;
     A.D_int = c->d_int_bytes == 2 ? c->D16.ptr : (c->d_int_bytes == 4 ? c->D32.ptr : nullptr);
     A.D_int_bytes = c->d_int_bytes;
+    A.pix_f32 = (c->cfg.precision == 32 && c->d_int_bytes == 2) ? 1 : 0;   // (launch_field recomputes it for the chain kernel)
     A.log_table = reinterpret_cast<const double2*>(c->logtab.ptr);
     A.nstars = c->run_has_nstars ? c->nstars.as<int>() : nullptr;
     A.q_in = c->q.as<double>();
@@ -894,8 +897,8 @@ int srhmc_plan_chunks(int64_t groups, int64_t resident_warps, int32_t n_iteratio
 }
 
 int srhmc_run(srhmc_ctx* c, const srhmc_run_args* a) {
-    if (c && a && c->chain_ok && c->cfg.n_fields >= 4096 && a->niter + 1 >= 256 && a->chain_stride == 1 &&
-        all_one_star(c, a->nstars)) {
+    if (c && a && c->chain_ok && (c->cfg.precision == 64 || c->d_int_bytes == 2) && c->cfg.n_fields >= 4096 &&
+        a->niter + 1 >= 256 && a->chain_stride == 1 && all_one_star(c, a->nstars)) {
         int parts = 8;  // measured on the headline batch: 1 part 106.0 ms, 2: 102.6, 4: 98.9, 8: 97.6 (kernel alone 91.7)
         if (const char* e = std::getenv("SRHMC_RUN_PARTS")) parts = std::max(1, std::min(kMaxParts, std::atoi(e)));
         if (parts > 1) return run_pipelined(c, a, parts);
