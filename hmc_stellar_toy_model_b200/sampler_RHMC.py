@@ -466,48 +466,59 @@ class multi_gym(base_class):
         print("Finished. Final report.")
         self.R_accept_report(idx_iter=-1, running=False)
 
-    def _one_star(self, q3, p3=None):
-        """H (and T when p3 is given) of a single star: the reference's `self.Nobjs = 1` blocks."""
-        H, _ = self._rj_ctx().metric(np.asarray(q3, dtype=float), self.g_ff2)
-        T = None if p3 is None else self.T(p3, H)
-        return H, T
+    # ------------------------------------------------------------------ trans-dimensional proposals
+    # Same proposal densities, acceptance terms and consumption order of the legacy np.random stream as the reference's
+    # birth_death_move / split_merge_move (sampler_RHMC.py:1200-1445), written as: draw -> star table edit -> log ratio.
+    # Star state is handled as an (N, 3) table of (flux, row, col); every metric the proposal needs comes from ONE
+    # srhmc_metric call and the kinetic terms from srhmc_kinetic_diag on the device.
+    def _stars_metric(self, *stars):
+        """Diagonal metric of a few individual stars in one device call -> one length-3 array per star."""
+        flat = np.concatenate([np.asarray(s, dtype=float).ravel() for s in stars])
+        H, _ = self._rj_ctx().metric(flat, self.g_ff2)
+        return [H[3 * i:3 * i + 3] for i in range(len(stars))]
+
+    def _kinetic_sum(self, moms, metrics):
+        """Sum of the kinetic terms T(p, H) of several stars in one device reduction (T is additive over stars)."""
+        return self.T(np.concatenate(moms), np.concatenate(metrics))
+
+    def _resize(self, table_q, table_p, log_ratio, d_stars):
+        self.Nobjs += d_stars
+        self.d += 3 * d_stars
+        return table_q.reshape(-1), table_p.reshape(-1), log_ratio
 
     def birth_death_move(self, q_tmp, p_tmp, birth_death=None):
         """Birth (True) or death (False) proposal; returns (q, p, factor) (sampler_RHMC.py:1200-1273)."""
         if (birth_death is None) or (self.alpha is None) or (self.fmin is None) or (self.fmax is None):
             assert False
         self._prior_const()
+        table_q = np.asarray(q_tmp, dtype=float).reshape(-1, 3)
+        table_p = np.asarray(p_tmp, dtype=float).reshape(-1, 3)
         if birth_death:
-            q = np.zeros(q_tmp.size + 3)
-            p = np.zeros(q_tmp.size + 3)
-            q[:q_tmp.size] = q_tmp
-            p[:p_tmp.size] = p_tmp
-            x = np.random.random() * (self.num_rows - 2.) + 1.
-            y = np.random.random() * (self.num_cols - 2.) + 1.
-            f = gen_pow_law_sample(self.alpha, self.fmin, self.fmax, 1)[0]
-            q_new = np.array([f, x, y])
-            q[-3:] = q_new
-            H_diag, _ = self._one_star(q_new)
-            p_new = self.u_sample(3) * np.sqrt(H_diag)
-            p[-3:] = p_new
-            factor = self.alpha * np.log(f) - 3 / 2. + self.T(p_new, H_diag) + self.V_prior_const
-            self.d += 3
-            self.Nobjs += 1
-        else:
-            q = np.zeros(q_tmp.size - 3)
-            p = np.zeros(q_tmp.size - 3)
-            i_kill = np.random.randint(0, self.Nobjs, size=1)[0]
-            q_killed = q_tmp[3 * i_kill:3 * i_kill + 3]
-            p_killed = p_tmp[3 * i_kill:3 * i_kill + 3]
-            q[:3 * i_kill] = q_tmp[:3 * i_kill]
-            q[3 * i_kill:] = q_tmp[3 * i_kill + 3:]
-            p[:3 * i_kill] = p_tmp[:3 * i_kill]
-            p[3 * i_kill:] = p_tmp[3 * i_kill + 3:]
-            H_diag, T_killed = self._one_star(q_killed, p_killed)
-            factor = -self.alpha * np.log(q_killed[0]) + 3 / 2. - T_killed - self.V_prior_const
-            self.d -= 3
-            self.Nobjs -= 1
-        return q, p, factor
+            # draws: row, column, flux from the prior, three normals for the newborn's momentum
+            row = np.random.random() * (self.num_rows - 2.) + 1.
+            col = np.random.random() * (self.num_cols - 2.) + 1.
+            flux = gen_pow_law_sample(self.alpha, self.fmin, self.fmax, 1)[0]
+            newborn = np.array([flux, row, col])
+            (metric_new,) = self._stars_metric(newborn)
+            mom_new = self.u_sample(3) * np.sqrt(metric_new)
+            log_ratio = self.alpha * np.log(flux) - 3 / 2. + self.T(mom_new, metric_new) + self.V_prior_const
+            return self._resize(np.vstack([table_q, newborn]), np.vstack([table_p, mom_new]), log_ratio, +1)
+        victim = np.random.randint(0, self.Nobjs, size=1)[0]
+        (metric_old,) = self._stars_metric(table_q[victim])
+        log_ratio = (-self.alpha * np.log(table_q[victim, 0]) + 3 / 2. - self.T(table_p[victim], metric_old)
+                     - self.V_prior_const)
+        return self._resize(np.delete(table_q, victim, axis=0), np.delete(table_p, victim, axis=0), log_ratio, -1)
+
+    def _merge_weights(self, table_q, pdf):
+        """Probability of choosing the ordered pair (i, j) for a merge: Beta density of the flux share f_j / (f_i + f_j)
+        (zero for equal fluxes, i.e. the diagonal) times the Gaussian split kernel at their separation."""
+        flux, rows, cols = table_q[:, 0], table_q[:, 1], table_q[:, 2]
+        share = flux / (flux.reshape((-1, 1)) + flux)
+        w = pdf(share, self.beta_a, self.beta_b)
+        w[np.abs(share - 0.5) < 1e-6] = 0.
+        sep_sq = (rows.reshape((-1, 1)) - rows) ** 2 + (cols.reshape((-1, 1)) - cols) ** 2
+        w = w * (np.exp(-sep_sq / (2. * self.K_split ** 2)) / (2. * np.pi * self.K_split ** 2))
+        return w / np.sum(w)
 
     def split_merge_move(self, q_tmp, p_tmp, split_merge=None):
         """Split (True) or merge (False) proposal; returns (q, p, factor) (sampler_RHMC.py:1276-1445)."""
@@ -515,77 +526,44 @@ class multi_gym(base_class):
 
         if split_merge is None:
             assert False
+        table_q = np.array(np.asarray(q_tmp, dtype=float).reshape(-1, 3), copy=True)
+        table_p = np.array(np.asarray(p_tmp, dtype=float).reshape(-1, 3), copy=True)
+        kernel_norm = np.log(2 * np.pi * self.K_split ** 2)
         if split_merge:
-            q = np.zeros(q_tmp.size + 3)
-            p = np.zeros(q_tmp.size + 3)
-            q[:q_tmp.size] = q_tmp
-            p[:p_tmp.size] = p_tmp
-            i_star = np.random.randint(0, self.Nobjs, size=1)[0]
-            f_star, x_star, y_star = q_tmp[3 * i_star:3 * i_star + 3]
-            p_star = np.copy(p_tmp[3 * i_star:3 * i_star + 3])
-            q_star = np.copy(q_tmp[3 * i_star:3 * i_star + 3])
-            dx, dy = np.random.randn(2) * self.K_split
-            dr_sq = dx ** 2 + dy ** 2
-            F = BETA.rvs(self.beta_a, self.beta_b, size=1)[0]
-            q_prime = np.array([F * f_star, x_star + (1 - F) * dx, y_star + (1 - F) * dy])
-            q_dprime = np.array([(1 - F) * f_star, x_star - F * dx, y_star - F * dy])
-            q[3 * i_star:3 * i_star + 3] = q_prime
-            q[-3:] = q_dprime
-            H_diag, _ = self._one_star(q_prime)
-            p_prime = self.u_sample(3) * np.sqrt(H_diag)
-            p[3 * i_star:3 * i_star + 3] = p_prime
-            T_prime = self.T(p_prime, H_diag)
-            H_diag, _ = self._one_star(q_dprime)
-            p_dprime = self.u_sample(3) * np.sqrt(H_diag)
-            p[-3:] = p_dprime
-            T_dprime = self.T(p_dprime, H_diag)
-            _, T_star = self._one_star(q_star, p_star)
-            factor = (-3 / 2.) + np.log(f_star) - BETA.logpdf(F, self.beta_a, self.beta_b) \
-                + np.log(2 * np.pi * self.K_split ** 2) + (dr_sq / (2 * self.K_split ** 2)) \
-                + T_prime + T_dprime - T_star
-            self.d += 3
-            self.Nobjs += 1
-        else:
-            f_vec = np.array(q_tmp[0::3], dtype=float)
-            x_vec = np.array(q_tmp[1::3], dtype=float)
-            y_vec = np.array(q_tmp[2::3], dtype=float)
-            F_matrix = f_vec / (f_vec.reshape((self.Nobjs, 1)) + f_vec)
-            ibool = np.abs(F_matrix - 0.5) < 1e-6
-            BETA_F = BETA.pdf(F_matrix, self.beta_a, self.beta_b)
-            BETA_F[ibool] = 0.
-            R_sq = (x_vec.reshape((self.Nobjs, 1)) - x_vec) ** 2 + (y_vec.reshape((self.Nobjs, 1)) - y_vec) ** 2
-            Q_dxdy = np.exp(-R_sq / (2. * self.K_split ** 2)) / (2. * np.pi * self.K_split ** 2)
-            P_choose = BETA_F * Q_dxdy
-            P_choose /= np.sum(P_choose)
-            pair_num = np.random.choice(range(self.Nobjs ** 2), p=P_choose.ravel())
-            idx_prime = pair_num // self.Nobjs
-            idx_dprime = pair_num % self.Nobjs
-            q_prime = np.copy(q_tmp[3 * idx_prime:3 * idx_prime + 3])
-            p_prime = np.copy(p_tmp[3 * idx_prime:3 * idx_prime + 3])
-            q_dprime = np.copy(q_tmp[3 * idx_dprime:3 * idx_dprime + 3])
-            p_dprime = np.copy(p_tmp[3 * idx_dprime:3 * idx_dprime + 3])
-            f_prime, x_prime, y_prime = q_prime
-            f_dprime, x_dprime, y_dprime = q_dprime
-            F = f_prime / (f_prime + f_dprime)
-            dx = x_prime - x_dprime
-            dy = y_prime - y_dprime
-            dr_sq = dx ** 2 + dy ** 2
-            f_star = f_prime + f_dprime
-            q_star = np.array([f_star, F * x_prime + (1 - F) * x_dprime, F * y_prime + (1 - F) * y_dprime])
-            _, T_prime = self._one_star(q_prime, p_prime)
-            _, T_dprime = self._one_star(q_dprime, p_dprime)
-            H_diag, _ = self._one_star(q_star)
-            p_star = self.u_sample(3) * np.sqrt(H_diag)
-            T_star = self.T(p_star, H_diag)
-            idx_a, idx_b = (idx_prime, idx_dprime) if idx_prime < idx_dprime else (idx_dprime, idx_prime)
-            q = np.concatenate([q_tmp[:3 * idx_a], q_tmp[3 * idx_a + 3:3 * idx_b], q_tmp[3 * idx_b + 3:], q_star])
-            p = np.concatenate([p_tmp[:3 * idx_a], p_tmp[3 * idx_a + 3:3 * idx_b], p_tmp[3 * idx_b + 3:], p_star])
-            factor = (3 / 2.) - np.log(f_star) + BETA.logpdf(F, self.beta_a, self.beta_b) \
-                - np.log(2 * np.pi * self.K_split ** 2) - (dr_sq / (2 * self.K_split ** 2)) \
-                - T_prime - T_dprime + T_star
-            self.d -= 3
-            self.Nobjs -= 1
-        return q, p, factor
+            # draws: parent, offset of the pair, flux share, three normals per child
+            parent = np.random.randint(0, self.Nobjs, size=1)[0]
+            flux_p, row_p, col_p = table_q[parent]
+            off_r, off_c = np.random.randn(2) * self.K_split
+            share = BETA.rvs(self.beta_a, self.beta_b, size=1)[0]
+            z_one, z_two = self.u_sample(3), self.u_sample(3)
+            child_one = np.array([share * flux_p, row_p + (1 - share) * off_r, col_p + (1 - share) * off_c])
+            child_two = np.array([(1 - share) * flux_p, row_p - share * off_r, col_p - share * off_c])
+            m_one, m_two, m_parent = self._stars_metric(child_one, child_two, table_q[parent])
+            mom_one, mom_two = z_one * np.sqrt(m_one), z_two * np.sqrt(m_two)
+            T_children = self._kinetic_sum([mom_one, mom_two], [m_one, m_two])
+            T_parent = self.T(table_p[parent], m_parent)
+            log_ratio = ((-3 / 2.) + np.log(flux_p) - BETA.logpdf(share, self.beta_a, self.beta_b) + kernel_norm
+                         + ((off_r ** 2 + off_c ** 2) / (2 * self.K_split ** 2)) + T_children - T_parent)
+            table_q[parent], table_p[parent] = child_one, mom_one
+            return self._resize(np.vstack([table_q, child_two]), np.vstack([table_p, mom_two]), log_ratio, +1)
+        # merge: one draw picks the ordered pair, three normals give the merged star's momentum
+        n = self.Nobjs
+        pick = np.random.choice(range(n ** 2), p=self._merge_weights(table_q, BETA.pdf).ravel())
+        one, two = pick // n, pick % n
+        share = table_q[one, 0] / (table_q[one, 0] + table_q[two, 0])
+        gap_sq = (table_q[one, 1] - table_q[two, 1]) ** 2 + (table_q[one, 2] - table_q[two, 2]) ** 2
+        flux_m = table_q[one, 0] + table_q[two, 0]
+        merged = np.array([flux_m, share * table_q[one, 1] + (1 - share) * table_q[two, 1],
+                           share * table_q[one, 2] + (1 - share) * table_q[two, 2]])
+        m_one, m_two, m_merged = self._stars_metric(table_q[one], table_q[two], merged)
+        T_pair = self._kinetic_sum([table_p[one], table_p[two]], [m_one, m_two])
+        mom_merged = self.u_sample(3) * np.sqrt(m_merged)
+        T_merged = self.T(mom_merged, m_merged)
+        log_ratio = ((3 / 2.) - np.log(flux_m) + BETA.logpdf(share, self.beta_a, self.beta_b) - kernel_norm
+                     - (gap_sq / (2 * self.K_split ** 2)) - T_pair + T_merged)
+        keep = np.ones(n, dtype=bool)
+        keep[[one, two]] = False
+        return self._resize(np.vstack([table_q[keep], merged]), np.vstack([table_p[keep], mom_merged]), log_ratio, -1)
 
     def R_accept_report(self, idx_iter, cumulative=True, running=True, run_window=10):
         """Acceptance rate so far broken down by move type (sampler_RHMC.py:1447-1473)."""
