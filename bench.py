@@ -608,7 +608,7 @@ def tiled_parity_check(env, stream):
     return msg
 
 
-def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity):
+def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity, precision=64):
     """C5: ONE large field, row strips over the ranks (strong), or one rows x cols strip per rank (weak)."""
     torch = env.torch
     from hmc_stellar_toy_model_b200 import _capi
@@ -627,6 +627,8 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
     run = t["run"]
     strip = _make_strip(env, bf, rows_g, cols, nst_g, t["consts"], halo, rad)
     strip.set_stream(stream.cuda_stream)
+    if precision == 32:
+        strip.set_precision(32)
     if world == 1:
         comm = bf.NoComm()
     elif comm_kind == "nccl":
@@ -680,14 +682,15 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
         ms_per_step = total_ms / steps
         value = units * steps / (total_ms * 1e-3)
         A = rows_g * cols / float(nst_g)
-        bytes_per_unit = 8.0 * A + 96.0   # the data strip read once per gradient + star state
+        # the data strip read once per gradient + star state (FP32 build: float pixels for 9 of 10 evaluations)
+        bytes_per_unit = (8.0 if precision == 64 else 4.0 + 4.0 / run["nsteps"]) * A + 96.0
         gbs = bytes_per_unit * units / world / (ms_per_step * 1e-3) / 1e9
-        name = "c5_tiled_field_%dx%d_%dstars" % (rows_g, cols, nst_g)
+        name = "c5_tiled_field_%dx%d_%dstars%s" % (rows_g, cols, nst_g, "" if precision == 64 else "_fp32")
         n_own = strip.n
         rec = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": name, "rows": rows_g, "cols": cols, "stars": nst_g, "niter": niter,
                        "nsteps": run["nsteps"], "dt": run["dt"], "patch_radius": rad, "halo_rows": halo,
                        "rng": "device Philox4x32-10", "data_source": "device-side mock data (srhmc_big_mock_data)",
@@ -768,10 +771,11 @@ def run_ours(args):
                             device_data_seed=4, parallelism="%d independent fields split over %d GPU(s) (contiguous "
                             "blocks), no communication" % (per * world, world))
 
-    def c5(weak):
+    def c5(weak, precision=None):
         return bench_bigfield(env, rows=args.rows, cols=args.cols, nstars=args.stars, weak=weak, niter=args.c5_niter,
                               steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
-                              comm_kind=args.comm, with_parity=not weak)
+                              comm_kind=args.comm, with_parity=not weak and precision is None,
+                              precision=args.precision if precision is None else precision)
 
     if which == "c4":
         out = c4()
@@ -796,6 +800,8 @@ def run_ours(args):
         subs["c5"] = guarded(env, "c5", lambda: c5(False))
         if world > 1:
             subs["c5_weak"] = guarded(env, "c5_weak", lambda: c5(True))
+        else:
+            subs["c5_fp32"] = guarded(env, "c5_fp32", lambda: c5(False, 32))
         if rank == 0:
             for k in ("c4", "c5"):
                 if subs.get(k) is not None and "error" not in subs[k]:

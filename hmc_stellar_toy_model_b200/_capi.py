@@ -202,6 +202,7 @@ SIGNATURES = {
     "srhmc_big_synchronize": (C.c_int, [C.c_void_p]),
     "srhmc_big_launch_count": (C.c_int64, [C.c_void_p]),
     "srhmc_big_set_data": (C.c_int, [C.c_void_p, c_double_p]),
+    "srhmc_big_set_precision": (C.c_int, [C.c_void_p, C.c_int32]),
     "srhmc_big_mock_data": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_uint64, c_double_p]),
     "srhmc_big_set_stars": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int32]),
     "srhmc_big_get_stars": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),

@@ -132,6 +132,10 @@ class BigFieldStrip:
     def set_data(self, D_global):
         self.set_data_window(np.asarray(D_global)[self.row0:self.row0 + self.nrows])
 
+    def set_precision(self, precision):
+        """32: gradient-only evaluations through the FP32 tile kernel (float copy of the data); 64: everything FP64."""
+        check(self._lib.srhmc_big_set_precision(self._h, int(precision)))
+
     def gen_mock_data(self, q_true, seed=0, return_data=False):
         """Device-side gen_mock_data (sampler_RHMC.py:77-99) for this strip's data window.  q_true [N,3] (f, x, y) is the
         truth list of the WHOLE field, the same on every rank; the Philox counter of a pixel is its global index, so the

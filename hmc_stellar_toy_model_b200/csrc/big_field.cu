@@ -780,6 +780,9 @@ struct srhmc_big {
     BBuf epart, tickets;  // per-block energy partials; last-block tickets [0] energy, [1] tile potential
     int nty = 0, ntx = 0;
     bool use_tiles = false;
+    int precision = 64;        // 32: gradient-only evaluations run the FP32 tile kernel on a float copy of the data
+    BBuf D32;
+    CUtensorMap tmapD32{};
     bool tma = false;          // a tensor map over the data window exists: the tile kernels load their tile by TMA
     bool tile2 = false;        // persistent variant (big_tile2_kernel, SRHMC_TILE_V2=1) instead of one CTA per tile
     CUtensorMap tmapD{};
@@ -787,6 +790,45 @@ struct srhmc_big {
     bool have_data = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+
+namespace {
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor map over a [nrows, cols] image of `elem_bytes`-wide pixels with kTile x kTile boxes (TMA tile loads)
+bool encode_tile_map(CUtensorMap* map, void* base, int nrows, int cols, int elem_bytes) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)nrows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = reinterpret_cast<TmapEncodeFn>(fn)(
+        map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cr == CUDA_SUCCESS;
+}
+
+// float copy of the data window for the FP32 tile kernel (after every change of the FP64 data)
+int refresh_float_data(srhmc_big* b) {
+    if (b->precision != 32) return 0;
+    const size_t npix = (size_t)b->cfg.nrows * b->cfg.cols;
+    big_to_float_kernel<<<(int)std::min<size_t>((npix + 255) / 256, 8192), 256, 0, b->stream>>>(b->D.as<double>(), b->D32.as<float>(), npix);
+    b->launches += 1;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "float conversion of the data failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -863,24 +905,7 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
         bool want2 = false;
         if (const char* e = std::getenv("SRHMC_TILE_V2")) want2 = e[0] == '1';
         if (want) {
-            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-                qres == cudaDriverEntryPointSuccess) {
-                const cuuint64_t dims[2] = {(cuuint64_t)cfg->cols, (cuuint64_t)cfg->nrows};
-                const cuuint64_t strides[1] = {(cuuint64_t)cfg->cols * 8};
-                const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)kTile};
-                const cuuint32_t estr[2] = {1, 1};
-                const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&b->tmapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, b->D.ptr, dims, strides, box,
-                                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                b->tma = cr == CUDA_SUCCESS;
-            } else {
-                cudaGetLastError();
-            }
+            b->tma = encode_tile_map(&b->tmapD, b->D.ptr, cfg->nrows, cfg->cols, 8);
             b->tile2 = b->tma && want2;
             if (b->tile2 &&
                 (cudaFuncSetAttribute(big_tile2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)) != cudaSuccess ||
@@ -923,7 +948,7 @@ int srhmc_big_destroy(srhmc_big* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     BBuf* all[] = {&b->D, &b->L, &b->q, &b->p, &b->g, &b->a1, &b->a2, &b->q0, &b->g0, &b->gid, &b->vpart, &b->scalars, &b->gscalars, &b->state,
                    &b->counters, &b->send, &b->recv, &b->err, &b->normals, &b->lnu, &b->E, &b->V, &b->T, &b->A,
-                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets, &b->xepoch, &b->packcnt, &b->xticket};
+                   &b->tcnt, &b->tlist, &b->gpart, &b->epart, &b->tickets, &b->xepoch, &b->packcnt, &b->xticket, &b->D32};
     for (BBuf* x : all) x->release();
     for (int r = 0; r < kMaxWorld; ++r)
         if (b->ipc_opened[r]) cudaIpcCloseMemHandle(b->ipc_opened[r]);
@@ -963,8 +988,29 @@ int srhmc_big_set_data(srhmc_big* b, const double* D_local) {
     if (!b || !D_local) return bfail(SRHMC_ERR_INVALID, "null argument");
     BCU(cudaSetDevice(b->cfg.device));
     BCU(cudaMemcpyAsync(b->D.ptr, D_local, (size_t)b->cfg.nrows * b->cfg.cols * 8, cudaMemcpyHostToDevice, b->stream));
+    if (int rc = refresh_float_data(b)) return rc;
     BCU(cudaStreamSynchronize(b->stream));
     b->have_data = true;
+    return 0;
+}
+
+int srhmc_big_set_precision(srhmc_big* b, int32_t precision) {
+    // 32: gradient-only evaluations through the FP32 tile kernel (float copy of the data, TMA); 64: everything FP64
+    if (!b || (precision != 32 && precision != 64)) return bfail(SRHMC_ERR_INVALID, "precision must be 64 or 32");
+    BCU(cudaSetDevice(b->cfg.device));
+    if (precision == 32) {
+        if (!b->use_tiles || !b->tma)
+            return bfail(SRHMC_ERR_STATE, "the FP32 build needs the tile path with TMA (field of >= 2 tiles per SM, even column count)");
+        const size_t npix = (size_t)b->cfg.nrows * b->cfg.cols;
+        if (int rc = b->D32.ensure(npix * 4)) return rc;
+        if (!encode_tile_map(&b->tmapD32, b->D32.ptr, b->cfg.nrows, b->cfg.cols, 4)) return bfail(SRHMC_ERR_CUDA, "cannot encode the FP32 tensor map");
+        if (cudaFuncSetAttribute(big_tile32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemF)) != cudaSuccess)
+            return bfail(SRHMC_ERR_CUDA, "cannot configure the FP32 tile kernel");
+    }
+    b->precision = precision;
+    if (b->have_data)
+        if (int rc = refresh_float_data(b)) return rc;
+    BCU(cudaStreamSynchronize(b->stream));
     return 0;
 }
 
@@ -1006,6 +1052,7 @@ int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t 
     }
     if (e == cudaSuccess && D_local_out)
         e = cudaMemcpyAsync(D_local_out, b->D.ptr, (size_t)b->cfg.nrows * b->cfg.cols * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && refresh_float_data(b) != 0) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     truth.release();
     if (e != cudaSuccess) return bfail(SRHMC_ERR_CUDA, "mock data generation failed: %s", cudaGetErrorString(e));
@@ -1266,7 +1313,10 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 }
                 b->own_binned = false;  // the tile kernel consumes the lists and re-zeroes the counters
                 b->ghosts_binned = false;
-                if (b->tile2) {
+                if (b->precision == 32 && !want_V) {
+                    big_tile32_kernel<<<ntiles, kTileThreads, sizeof(TileSmemF), st>>>(P, S, b->ntx, b->tcnt.as<int>(), b->tlist.as<int2>(),
+                                                                                       b->gpart.as<double>(), cnt, b->tmapD32);
+                } else if (b->tile2) {
                     int grid2 = std::min(ntiles, 4 * b->sm_count);   // persistent: 4 CTAs per SM walk the tiles
                     if (const char* e = std::getenv("SRHMC_TILE_GRID")) {   // experiments: CTAs per SM, 0 = one CTA per tile
                         const int k = std::atoi(e);

@@ -397,6 +397,165 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     }
 }
 
+// ------------------------------------------------------------------------------------------------ FP32 gradient tile kernel
+// The FP32 build of the tile evaluation (north_star: "<= 1e-4 in the FP32 build"): gradient-only evaluations (every
+// leapfrog step but the last of a trajectory) read a float copy of the data window -- half the HBM bytes -- and do the
+// render, the residual (MUFU.RCP) and the residual-weighted sums in float; star state, the tables' exponentials, the
+// footprint sums and every evaluation that also returns the potential stay FP64, so the energies of the Metropolis test
+// are exact for the state reached.  Same structure as big_tile_kernel<0> (one CTA per 64x64 tile, TMA tile load).
+struct PairTabF {
+    float rowf[kTabLen];
+    float colf[kTabLen];
+    float dx0, dy0;
+};
+
+struct TileSmemF {
+    float rho[kTile][kTile];           // 16 KB, TMA destination
+    PairTabF tab[kTileChunk];
+    int2 list[kTileMaxList];
+    int box[kTileChunk][4];
+    unsigned long long mbar;
+};
+
+__device__ __forceinline__ void build_pair_tab_f(const BigParams& P, const TileSrc& S, int2 rec, int r0, int c0, int lane,
+                                                 PairTabF& T, int* box) {
+    const double* src = tile_source(S, rec.x);
+    const double f = src[0], x = src[1], y = src[2];
+    const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
+    const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
+    T.rowf[kTabPad + lane] = (ia + lane <= ib) ? (float)exp_neg(-(dx * dx) * P.inv2s2) : 0.0f;
+    T.colf[kTabPad + lane] = (ja + lane <= jb) ? (float)(exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f)) : 0.0f;
+    if (lane == 0) {
+        T.dx0 = (float)dx;
+        T.dy0 = (float)dy;
+        if (box) {
+            box[0] = ia; box[1] = ib; box[2] = ja; box[3] = jb;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 5)
+big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__ cnt, const int2* __restrict__ list,
+                  double* __restrict__ gpart, int* fp_counters, const __grid_constant__ CUtensorMap tmapD32) {
+    extern __shared__ __align__(128) unsigned char tile32_smem_raw[];
+    TileSmemF& sm = *reinterpret_cast<TileSmemF*>(tile32_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kTileThreads / 32;
+    const int ti = blockIdx.x / ntx, tj = blockIdx.x % ntx;
+    const int r0 = P.row0 + ti * kTile, c0 = tj * kTile;
+    const int vr = min(kTile, P.row0 + P.nrows - r0), vc = min(kTile, P.C - c0);
+    const int ty = tid >> 4, tx = tid & 15;
+    const int pr = 4 * ty, pc = 4 * tx;
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        mbar_expect_tx(&sm.mbar, kTile * kTile * 4);
+        tma_load_2d(&sm.rho[0][0], &tmapD32, c0, r0 - P.row0, &sm.mbar);
+    }
+    list += (size_t)blockIdx.x * kTileMaxList;
+    const int nl = min(cnt[blockIdx.x], kTileMaxList);
+    if (fp_counters && blockIdx.x == 0 && tid < 2) fp_counters[tid] = 0;
+    for (int k = tid; k < kTileChunk * 4 * kTabPad; k += kTileThreads) {
+        const int pair = k / (4 * kTabPad), e = k % (4 * kTabPad), side = e / kTabPad, g = e % kTabPad;
+        float* t = (side & 1) ? sm.tab[pair].colf : sm.tab[pair].rowf;
+        t[(side & 2) ? kTabPad + 32 + g : g] = 0.0f;
+    }
+    if (nl == 1) {
+        if (tid == 0) sm.list[0] = __ldcg(&list[0]);
+    } else if (nl > 1) {
+        for (int k = tid; k < nl; k += kTileThreads) {
+            const int2 rec = __ldcg(&list[k]);
+            int r = 0;
+            for (int m = 0; m < nl; ++m) r += __ldcg(&list[m].x) < rec.x;
+            sm.list[r] = rec;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) cnt[blockIdx.x] = 0;
+
+    float lam[4][4];
+    const float Bf = (float)P.F.B;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) lam[a][b] = Bf;
+    for (int base = 0; base < nl; base += kTileChunk) {
+        const int nc = min(kTileChunk, nl - base);
+        for (int s = warp; s < nc; s += kWarps) build_pair_tab_f(P, S, sm.list[base + s], r0, c0, lane, sm.tab[s], sm.box[s]);
+        __syncthreads();
+        for (int s = 0; s < nc; ++s) {
+            const int ia = sm.box[s][0], ja = sm.box[s][2];
+            if (pr + 3 < ia || pr > sm.box[s][1] || pc + 3 < ja || pc > sm.box[s][3]) continue;
+            const float* te = &sm.tab[s].rowf[kTabPad + pr - ia];
+            const float* tf = &sm.tab[s].colf[kTabPad + pc - ja];
+            const float ex[4] = {te[0], te[1], te[2], te[3]}, fy[4] = {tf[0], tf[1], tf[2], tf[3]};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) lam[a][b] = fmaf(ex[a], fy[b], lam[a][b]);
+        }
+        if (base + kTileChunk < nl) __syncthreads();
+    }
+    mbar_wait(&sm.mbar, 0u);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int li = pr + a;
+        const float4 d4 = *reinterpret_cast<const float4*>(&sm.rho[li][pc]);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float rho[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float rc;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(lam[a][b]));
+            rho[b] = (li < vr && pc + b < vc) ? fmaf(d[b], rc, -1.0f) : 0.0f;
+        }
+        *reinterpret_cast<float4*>(&sm.rho[li][pc]) = make_float4(rho[0], rho[1], rho[2], rho[3]);
+    }
+    __syncthreads();
+    const bool keep = nl <= kTileChunk;
+    for (int s = warp; s < nl; s += kWarps) {
+        const int2 rec = sm.list[s];
+        if (rec.x >= S.n_own) continue;
+        PairTabF& T = sm.tab[keep ? s : warp];
+        if (!keep) {
+            __syncwarp();
+            build_pair_tab_f(P, S, rec, r0, c0, lane, T, nullptr);
+            __syncwarp();
+        }
+        const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = rec.y >> 12 & 63, jb = (rec.y >> 18) & 63;
+        const float fy = T.colf[kTabPad + lane];
+        const float dyl = T.dy0 + (float)lane;
+        const float* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
+        const float* rf = &T.rowf[kTabPad];
+        float a0 = 0.0f, a1 = 0.0f, dxk = T.dx0;
+        const int nr = ib - ia + 1;
+#pragma unroll 4
+        for (int k = 0; k < nr; ++k) {
+            const float e = rf[k];
+            const float rho = col[k * kTile];
+            a0 = fmaf(rho, e, a0);
+            a1 = fmaf(rho * e, dxk, a1);
+            dxk += 1.0f;
+        }
+        if (ja + lane > jb) a0 = a1 = 0.0f;
+        double sf = (double)fy * (double)a0, sx = (double)fy * (double)a1, sy = ((double)fy * (double)dyl) * (double)a0, sz = 0.0;
+        {
+            const bool hi = lane & 16;
+            const double k0 = hi ? sy : sf, k1 = hi ? sz : sx, t0 = hi ? sf : sy, t1 = hi ? sx : sz;
+            const double x0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16), x1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
+            const bool h8 = lane & 8;
+            double yv = (h8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, h8 ? x0 : x1, 8);
+            yv += __shfl_xor_sync(0xffffffffu, yv, 4);
+            yv += __shfl_xor_sync(0xffffffffu, yv, 2);
+            yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+            if ((lane & 7) == 0 && lane < 24) gpart[((size_t)rec.x * 4 + (rec.y >> 24)) * 3 + (lane >> 3)] = yv;
+        }
+    }
+}
+
+__global__ void big_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+
 // ------------------------------------------------------------------------------------------------ persistent TMA variant
 // Same sums per tile as big_tile_kernel<0|1> (fixed summation orders: results are bit-reproducible run to run),
 // reorganised for Blackwell:

@@ -367,6 +367,10 @@ int srhmc_big_adopt_stream(srhmc_big* b, void* cuda_stream);  /* no synchronisat
 int srhmc_big_synchronize(srhmc_big* b);
 int64_t srhmc_big_launch_count(srhmc_big* b);
 int srhmc_big_set_data(srhmc_big* b, const double* D_local /* [nrows, cols] */);
+/* 32: the FP32 build -- gradient-only evaluations (every leapfrog step but the last of a trajectory) read a float copy of the
+ * data window and render / reduce in float; star state and every evaluation that returns the potential stay FP64.  Needs the
+ * tile path (srhmc_big_create chooses it for fields of at least 2 tiles per SM).  64 (default): everything FP64. */
+int srhmc_big_set_precision(srhmc_big* b, int32_t precision);
 /* Device-side gen_mock_data for the local data window (see srhmc_gen_mock_data): q_true [n,3] (f in counts, x, y) is
  * the WHOLE field's truth list, identical on every rank; the Philox counter is the global pixel index, so halo rows agree
  * between ranks.  D_local_out [nrows, cols] may be NULL. */

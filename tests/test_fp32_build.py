@@ -61,3 +61,44 @@ def test_fp32_chains_agree_with_fp64_chains():
     assert np.all(np.abs(ma - mb) <= 3.0 * np.maximum(sa, sb) + 1e-9)
     assert np.median(np.abs(sa - sb) / np.maximum(sa, 1e-12)) < 1e-2
     assert np.all(np.isfinite(b.E_chain))
+
+
+def test_fp32_tile_kernel_within_1e4_of_the_fp64_build():
+    """Large-field engine, 1600 x 1600 / 2000 stars (tile path): gradients of the FP32 tile kernel against the FP64 one
+    (which is checked against the oracle in test_bigfield.py) to 1e-4 of the per-coordinate scale, three leapfrog steps
+    to 1e-5 in q, and a Philox chain with the same decisions and energies (the energies stay FP64)."""
+    import torch
+
+    from hmc_stellar_toy_model_b200 import bigfield as bf
+    from test_bigfield import _consts, _synthetic_field
+
+    S, D, q0 = _synthetic_field(1600, 1600, 2000, 9)
+    n = len(q0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    res = {}
+    for prec in (64, 32):
+        s = bf.BigFieldStrip(rows=1600, cols=1600, rank=0, world=1, device=0, max_stars=n, max_ghosts=1, patch_radius=12,
+                             halo=20, **_consts(S))
+        s.set_stream(stream.cuda_stream)
+        s.set_data(D)
+        s.set_precision(prec)
+        s.set_stars(q0)
+        eng = bf.BigFieldRHMC([s])
+        eng.evaluate(want_V=False, g_ff2=4.0)
+        g = eng.stars(n)[2].copy()
+        rng = np.random.RandomState(3)
+        s.set_momenta(rng.randn(n, 3) * np.sqrt(so.metric(S, q0.ravel()).reshape(n, 3)))
+        eng.steps(3, 5e-2, g_ff2=4.0)
+        q3 = eng.stars(n)[0].copy()
+        s.set_stars(q0)
+        chain = eng.run(6, 5, 5e-2, f_pos=True, g_ff2=4.0, seed=4)
+        res[prec] = (g, q3, chain)
+        s.close()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    g64, q64, c64 = res[64]
+    g32, q32, c32 = res[32]
+    assert np.max(np.abs(g32 - g64) / np.max(np.abs(g64), axis=0, keepdims=True)) < 1e-4
+    assert relerr(q32, q64) < 1e-5
+    assert np.array_equal(c32["A_chain"], c64["A_chain"])
+    assert relerr(c32["E_chain"], c64["E_chain"]) < 1e-6
