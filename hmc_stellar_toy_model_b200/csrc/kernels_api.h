@@ -53,8 +53,9 @@ int poisson_launch(cudaStream_t stream, const double* lam, double* D, size_t n, 
                    unsigned long long index_base);
 
 // on-device chain statistics (stats_kernels.cu)
+size_t conv_stats_scratch_doubles(long long rows, int d, int n_groups, int cpg, int thin, int warm);
 int conv_stats_launch(cudaStream_t stream, const double* X, long long rows, int d, int n_groups, int cpg, int thin, int warm,
-                      double* means, double* R, double* neff);
+                      double* scratch, double* R, double* neff);
 
 // gradient-descent leg of lightsource_gym.find_peaks (peaks_kernels.cu): one warp per seed, image 0 of the context
 int peaks_launch(cudaStream_t stream, const FieldParams& P, const double* D, int n, int nstep, double dt_f_coeff,

@@ -1135,7 +1135,7 @@ int srhmc_convergence_stats(int32_t device, const double* q_chain, int64_t n_cha
     const size_t nx = (size_t)n_chains * n_iter * d, nout = (size_t)n_groups * d;
     DevBuf X, means, out;
     int rc = X.ensure(nx * 8);
-    if (!rc) rc = means.ensure(nout * 2 * cpg * 8);
+    if (!rc) rc = means.ensure(conv_stats_scratch_doubles(n_iter, d, n_groups, cpg, thin_rate, warm_up_num) * 8);
     if (!rc) rc = out.ensure(2 * nout * 8);
     cudaError_t e = cudaSuccess;
     if (!rc) e = cudaMemcpy(X.ptr, q_chain, nx * 8, cudaMemcpyHostToDevice);
@@ -1159,7 +1159,7 @@ int srhmc_run_stats(srhmc_ctx* c, int32_t n_groups, int32_t thin_rate, int32_t w
     CU_TRY(cudaSetDevice(c->cfg.device));
     const int cpg = c->cfg.n_fields / n_groups;
     const size_t nout = (size_t)n_groups * d;
-    if (int rc = c->st_means.ensure(nout * 2 * cpg * 8)) return rc;
+    if (int rc = c->st_means.ensure(conv_stats_scratch_doubles(c->run_rows, d, n_groups, cpg, thin_rate, warm_up_num) * 8)) return rc;
     if (int rc = c->st_R.ensure(nout * 8)) return rc;
     if (int rc = c->st_neff.ensure(nout * 8)) return rc;
     const int e = conv_stats_launch(c->stream, c->qchain.as<double>(), c->run_rows, d, n_groups, cpg, thin_rate, warm_up_num,
