@@ -837,7 +837,10 @@ def run_reference(args):
            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": wl_name, "description": "%d mags x 1000 one-star 32x32 chains" % len(MAGS) if wl_key == "c2" else wl_name,
-                      "sample": sample, "stars_per_field": 1 if wl_key == "c2" else 204, "nsteps": 10},
+                      "stars_per_field": 1 if wl_key == "c2" else 204, "niter": niter, "nsteps": 10,
+                      "dt": 0.2 if wl_key == "c2" else 5e-2, "rng": "np.random.RandomState draws injected into the oracle",
+                      "sample": sample,
+                      "parallelism": "%d host processes, one independent chain each" % cores},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                             "port_vs_reference": PORT_VS_REFERENCE},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -98,7 +98,9 @@ class lightsource_gym(object):
         if self.D is None:
             raise ValueError("gym.D is not set: call gen_mock_data() or assign the data image first")
         D = np.ascontiguousarray(self.D, dtype=np.float64)
-        if self._ctx_data is None or not np.array_equal(D, self._ctx_data):
+        from .sampler_RHMC import base_class  # the gyms share the "is gym.D still the device image?" test
+
+        if self._ctx_data is None or not base_class._same_image(D, self._ctx_data):
             self._ctx.set_data(D)
             self._ctx_data = D.copy()
         return self._ctx

@@ -325,3 +325,27 @@ def test_find_peaks_oracle_matches_live_reference():
     got = so.ls_find_peaks(L, jitter, linear_pix_density=0.2, Nstep=150, dt_f_coeff=0.2, dt_xy_coeff=0.05, dr_tol=1.5,
                            dmag_tol=0.7)
     assert got.shape == gym.q_seed.shape and relerr(got, gym.q_seed) < 1e-12
+
+
+@pytest.mark.gpu
+def test_device_noise_profile_matches_the_host_profile():
+    """gen_noise_profile (sampler_RHMC.py:118-145) with device_seed: 300 Poisson realisations drawn in one launch; the
+    residual histogram agrees with the np.random one within sampling noise, is reproducible, and leaves the global
+    np.random stream untouched."""
+    from hmc_stellar_toy_model_b200.sampler_RHMC import multi_gym
+
+    gym = multi_gym(dt=0.2, Nsteps=10, g_xx=1.0, g_ff=1.0, g_ff2=1.0)
+    gym.num_rows = gym.num_cols = 32
+    q_true = np.array([[18.0, 16.0, 16.0], [20.5, 8.3, 22.1]])
+    np.random.seed(3)
+    gym.gen_noise_profile(np.copy(q_true), N_trial=300)
+    host = gym.hist_noise.copy()
+    state = np.random.get_state()[1].copy()
+    gym.gen_noise_profile(np.copy(q_true), N_trial=300, device_seed=11)
+    dev = gym.hist_noise.copy()
+    assert np.array_equal(np.random.get_state()[1], state)
+    gym.gen_noise_profile(np.copy(q_true), N_trial=300, device_seed=11)
+    assert np.array_equal(dev, gym.hist_noise)
+    assert abs(dev.sum() - host.sum()) < 1e-3 * host.sum()
+    width = gym.centers_noise[1] - gym.centers_noise[0]
+    assert np.sum(np.abs(dev - host)) * width < 0.02   # total-variation distance of two 3e5-sample histograms
