@@ -761,13 +761,16 @@ def run_ours(args):
                             want=("q", "p", "E", "V", "T", "A"), precision=args.precision, scaling="weak", seed_base=0,
                             parallelism="independent chains sharded across %d GPU(s), no communication" % world)
 
-    def c4():
+    def c4(precision=None):
         total = args.fields
         per = max(1, total // world)
         wl = workload_c4(per, 5000 + rank, host_data=False)
         wl["desc"] = "%d crowded 64x64 fields x 204 stars in total, %d per GPU" % (per * world, per)
+        if precision == 32:
+            wl["name"] += "_fp32"
         return bench_chains(env, wl, niter=args.c4_niter, steps=args.sub_steps, warmup=3, e2e_steps=2, want=("E", "A"),
-                            precision=args.precision, scaling="strong", seed_base=17, field_id_base=rank * per,
+                            precision=args.precision if precision is None else precision, scaling="strong", seed_base=17,
+                            field_id_base=rank * per,
                             device_data_seed=4, parallelism="%d independent fields split over %d GPU(s) (contiguous "
                             "blocks), no communication" % (per * world, world))
 
@@ -801,6 +804,7 @@ def run_ours(args):
         if world > 1:
             subs["c5_weak"] = guarded(env, "c5_weak", lambda: c5(True))
         else:
+            subs["c4_fp32"] = guarded(env, "c4_fp32", lambda: c4(32))
             subs["c5_fp32"] = guarded(env, "c5_fp32", lambda: c5(False, 32))
         if rank == 0:
             for k in ("c4", "c5"):
