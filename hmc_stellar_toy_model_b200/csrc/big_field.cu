@@ -225,8 +225,16 @@ constexpr int kMaxWorld = 16;
 struct PeerSlot {                 // one small-vector contribution
     unsigned long long tag;
     double v[8];
-    double pad[7];                // 128 bytes
+    unsigned long long mword;     // max exchange: (epoch << 32) | value in ONE 8-byte store -- value and flag arrive together,
+                                  // so the exchange needs no system-scope fence on either side
+    double pad[6];                // 128 bytes
 };
+static_assert(sizeof(PeerSlot) == 128, "PeerSlot layout");
+
+// fence-free exchange of one non-negative int tagged with the epoch
+__device__ __forceinline__ void peer_send_word(PeerSlot* s, unsigned long long e, int val) {
+    *reinterpret_cast<volatile unsigned long long*>(&s->mword) = (e << 32) | (unsigned long long)(unsigned int)val;
+}
 
 struct PeerHeader {
     PeerSlot ar[2][kMaxWorld];    // [epoch parity][source rank]
@@ -260,6 +268,22 @@ __device__ __forceinline__ bool peer_wait_tag(const unsigned long long* tag, uns
 }
 
 
+// spin until the packed word of slot `s` carries epoch >= e; its low half is the value.  Same time-out rule as peer_wait_tag.
+__device__ __forceinline__ bool peer_wait_word(const PeerSlot* s, unsigned long long e, int* err, int& val) {
+    const long long t0 = clock64();
+    unsigned long long w;
+    while (((w = *reinterpret_cast<const volatile unsigned long long*>(&s->mword)) >> 32) < e) {
+        if (*reinterpret_cast<volatile int*>(err) == 4) return false;
+        if (clock64() - t0 > 10000000000LL) {
+            atomicExch(err, 4);
+            return false;
+        }
+        __nanosleep(40);
+    }
+    val = (int)(unsigned int)(w & 0xffffffffull);
+    return true;
+}
+
 // The field-wide maximum of a fixed-point count taken INSIDE the kernel that consumes it (no separate exchange kernel):
 // block 0 sends this rank's count to every rank's mailbox, every block waits for the world's contributions in its OWN
 // rank's mailbox (local memory) and takes the maximum; the last block to leave the kernel advances the epoch, so every
@@ -267,6 +291,7 @@ __device__ __forceinline__ bool peer_wait_tag(const unsigned long long* tag, uns
 struct PeerX {
     PeerPtrs peers;
     int rank, world, on;
+    int prod;   // the kernel that PRODUCES a fixed-point count all-reduces it in its last block (peer_max_epilogue)
     unsigned long long* epoch;
     unsigned int* ticket;
     int* err;
@@ -279,16 +304,44 @@ __device__ __forceinline__ int peer_max_in_kernel(const PeerX& X, int local) {
     if (t == 0) s_max = local;
     __syncthreads();
     if (t < X.world) {
-        if (blockIdx.x == 0) {
-            PeerSlot* s = &reinterpret_cast<PeerHeader*>(X.peers.box[t])->ar[par][X.rank];
-            s->v[0] = (double)local;
-            peer_publish_tag(&s->tag, e);
-        }
+        if (blockIdx.x == 0) peer_send_word(&reinterpret_cast<PeerHeader*>(X.peers.box[t])->ar[par][X.rank], e, local);
         const PeerSlot* mine = &reinterpret_cast<const PeerHeader*>(X.peers.box[X.rank])->ar[par][t];
-        if (peer_wait_tag(&mine->tag, e, X.err)) atomicMax(&s_max, (int)__ldcv(&mine->v[0]));
+        int got = 0;
+        if (peer_wait_word(mine, e, X.err, got)) atomicMax(&s_max, got);
     }
     __syncthreads();
     return s_max;
+}
+
+// all-reduce(max) of *word over the ranks by the LAST block to leave the kernel that produced it: the word is complete (every
+// block's atomicMax precedes its ticket), one block polls the mailbox, and the consumer kernel just reads the word.
+__device__ __forceinline__ void peer_max_epilogue(const PeerX& X, int* word) {
+    __shared__ int s_last, s_max;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(X.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned long long e = X.epoch[0] + 1;
+    const int par = (int)(e & 1), t = threadIdx.x;
+    const int local = *reinterpret_cast<volatile int*>(word);
+    if (t == 0) s_max = local;
+    __syncthreads();
+    if (t < X.world) {
+        peer_send_word(&reinterpret_cast<PeerHeader*>(X.peers.box[t])->ar[par][X.rank], e, local);
+        const PeerSlot* mine = &reinterpret_cast<const PeerHeader*>(X.peers.box[X.rank])->ar[par][t];
+        int got = 0;
+        if (peer_wait_word(mine, e, X.err, got)) atomicMax(&s_max, got);
+    }
+    __syncthreads();
+    if (t == 0) {
+        *word = s_max;
+        X.epoch[0] = e;
+        *X.ticket = 0u;
+    }
 }
 
 __device__ __forceinline__ void peer_epoch_advance(const PeerX& X) {
@@ -316,7 +369,7 @@ __device__ __forceinline__ double dphi_f(const BigParams& P, const Metric& m, do
 
 // (1) p -= h dphi/dq; (2) p fixed point, phase A: iterate to this star's own convergence, record the count
 __global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, const double* g,
-                                 double* a1, double* a2, int* cnt) {
+                                 double* a1, double* a2, int* cnt, const PeerX X) {
     int local_max = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double f = q[3 * k];
@@ -340,6 +393,7 @@ __global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, cons
         local_max = max(local_max, c);
     }
     if (local_max) atomicMax(cnt, local_max);
+    if (X.prod) peer_max_epilogue(X, cnt);
 }
 
 // p fixed point phase B (continue to the global count), then (3) q fixed point phase A
@@ -380,12 +434,14 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
     }
     if (local_max) atomicMax(cnt_q, local_max);
     if (X.on) peer_epoch_advance(X);
+    if (X.prod) peer_max_epilogue(X, cnt_q);
 }
 
 // q fixed point phase B, then (4) p -= h dtau/dq at the new q
 // and -- tile path -- the pair records of the star's final position for the coming evaluation (bin_star, big_tile.cuh)
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
-                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err, const PeerX X) {
+                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err, const PeerX X,
+                                     int2* pack_counts, double lo_edge, double hi_edge) {
     const int target = X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
@@ -402,6 +458,11 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
         const Metric m = metric_of(P.F, qf, S.g_ff2);
         p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
         if (tcnt) bin_star(P, ntx, k, qx, qy, true, tcnt, tlist, err);
+        // boundary-star counts per 1024-star chunk for the ordered ghost packing that follows (integer atomics: exact)
+        if (pack_counts) {
+            if (qx < lo_edge) atomicAdd(&pack_counts[k >> 10].x, 1);
+            if (qx >= hi_edge) atomicAdd(&pack_counts[k >> 10].y, 1);
+        }
     }
     if (X.on) peer_epoch_advance(X);
 }
@@ -427,7 +488,7 @@ __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, cons
 // big_kick2_kernel and big_kick1_kernel run back to back.
 template <bool NEXT>
 __global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, double* g,
-                                const double* gpart, double* a1, double* a2, int* cnt) {
+                                const double* gpart, double* a1, double* a2, int* cnt, const PeerX X) {
     int local_max = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
@@ -467,6 +528,7 @@ __global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const
         p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
     }
     if (NEXT && local_max) atomicMax(cnt, local_max);
+    if (NEXT && X.prod) peer_max_epilogue(X, cnt);
 }
 
 // momentum refresh p = z sqrt(H) (sampler_RHMC.py:1021-1022) with device Philox keyed by the GLOBAL star id, or
@@ -578,6 +640,7 @@ __global__ void big_restore_v_kernel(double* local_scalars, const double* state,
 // [b kPackChunk, (b+1) kPackChunk); a first kernel counts its matches, the second one starts at the sum of the counts of
 // the blocks before it and compacts with warp ballots.
 constexpr int kPackChunk = 1024;
+static_assert(kPackChunk == 1 << 10, "big_qfix_kick_kernel counts boundary stars per chunk with k >> 10");
 
 __global__ void big_pack_count_kernel(int n, const double* q, double lo_edge, double hi_edge, int2* counts) {
     __shared__ int c[2];
@@ -685,7 +748,7 @@ __global__ void big_xchg_small_kernel(const PeerPtrs peers, int rank, int world,
 
 // boundary-star lists straight into the neighbours' mailboxes, then the received lists into the local `recv` layout
 // ([source rank][list][1 + 3 cap]) the evaluation reads: list 1 of rank-1 and list 0 of rank+1
-__global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
+__device__ void ghost_exchange_body(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
                                       unsigned long long* epoch, int* err, const BigParams P, int ntx, int n_own, int cap, int* tcnt,
                                       int2* tlist) {
     const unsigned long long e = epoch[1] + 1;
@@ -703,8 +766,7 @@ __global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world,
         const int cnt = 1 + 3 * (int)src[0];
         for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();   // the block's payload stores precede the publishing threads' system-scope fence (cumulativity)
     if (threadIdx.x == 0 && rank > 0) peer_publish_tag(tagof(rank - 1, 1), e);
     if (threadIdx.x == 1 && rank < world - 1) peer_publish_tag(tagof(rank + 1, 0), e);
     __shared__ int ok;
@@ -734,6 +796,92 @@ __global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world,
                 bin_star(P, ntx, n_own + side * cap + k, g[2 + 3 * k], g[3 + 3 * k], false, tcnt, tlist, err);
         }
     }
+}
+
+__global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
+                                      unsigned long long* epoch, int* err, const BigParams P, int ntx, int n_own, int cap, int* tcnt,
+                                      int2* tlist) {
+    ghost_exchange_body(peers, rank, world, send, recv, list, epoch, err, P, ntx, n_own, cap, tcnt, tlist);
+}
+
+// Ordered ghost packing, the exchange and the binning of the received ghosts in ONE kernel: every block compacts its chunk
+// (as big_pack_kernel), the last block to finish runs the exchange body.  The chunk counts come from the position-update
+// kernel (big_qfix_kick_kernel) and are zeroed here for the next step.
+struct GhostX {
+    PeerPtrs peers;
+    int rank, world;
+    double* recv;
+    size_t list;
+    unsigned long long* epoch;
+    unsigned int* ticket;
+    int ntx, n_own;
+    int* tcnt;
+    int2* tlist;
+};
+
+__global__ void big_pack_xchg_kernel(int n, const double* q, double lo_edge, double hi_edge, int2* counts, double* send, int cap,
+                                     int* err, const BigParams P, const GhostX G) {
+    __shared__ int base[2];
+    __shared__ int wcount[2][32];
+    __shared__ int s_last;
+    int plo = 0, phi = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) {
+        const int2 c = counts[b];
+        plo += c.x;
+        phi += c.y;
+    }
+    if (threadIdx.x == 0) base[0] = base[1] = 0;
+    __syncthreads();
+    if (plo) atomicAdd(&base[0], plo);
+    if (phi) atomicAdd(&base[1], phi);
+    __syncthreads();
+    const int k_begin = blockIdx.x * kPackChunk, k_end = min(n, k_begin + kPackChunk);
+    for (int k0 = k_begin; k0 < k_end; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        bool lo = false, hi = false;
+        double f = 0, x = 0, y = 0;
+        if (k < k_end) {
+            f = q[3 * k]; x = q[3 * k + 1]; y = q[3 * k + 2];
+            lo = x < lo_edge;
+            hi = x >= hi_edge;
+        }
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
+        if (lane == 0) { wcount[0][w] = __popc(blo); wcount[1][w] = __popc(bhi); }
+        __syncthreads();
+        int off_lo = base[0], off_hi = base[1];
+        for (int i = 0; i < w; ++i) { off_lo += wcount[0][i]; off_hi += wcount[1][i]; }
+        const unsigned lt = (1u << lane) - 1u;
+        if (lo) {
+            const int o = off_lo + __popc(blo & lt);
+            if (o < cap) { double* d = send + 1 + 3 * (size_t)o; d[0] = f; d[1] = x; d[2] = y; } else atomicExch(err, 2);
+        }
+        if (hi) {
+            const int o = off_hi + __popc(bhi & lt);
+            if (o < cap) { double* d = send + (1 + 3 * (size_t)cap) + 1 + 3 * (size_t)o; d[0] = f; d[1] = x; d[2] = y; } else atomicExch(err, 2);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < nw; ++i) { base[0] += wcount[0][i]; base[1] += wcount[1][i]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) {
+        send[0] = (double)min(base[0], cap);
+        send[1 + 3 * (size_t)cap] = (double)min(base[1], cap);
+    }
+    // last block out: every chunk (and the two list lengths) is in `send`
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(G.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) counts[b] = make_int2(0, 0);   // for the next step's counting
+    if (threadIdx.x == 0) *G.ticket = 0u;
+    ghost_exchange_body(G.peers, G.rank, G.world, send, G.recv, G.list, G.epoch, err, P, G.ntx, G.n_own, cap, G.tcnt, G.tlist);
 }
 
 struct BBuf {
@@ -774,6 +922,11 @@ struct srhmc_big {
     // SLOWER than the separate one-block exchange kernels (451 against 496 M star-steps/s: every block of the consumer polls
     // the mailbox line the peer is writing), binning the ghosts in the exchange kernel is neutral and saves a launch.
     bool fuse_max = false, fuse_bin = true;   // SRHMC_PEER_FUSE_MAX=1 / SRHMC_PEER_FUSE_BIN=0 switch them
+    // Producer-side fusion (SRHMC_PEER_FUSE_PROD=0 switches it off): the kernel that produces a fixed-point count all-reduces
+    // it in its last block, the position-update kernel counts the boundary stars, and packing + ghost exchange + ghost
+    // binning are one kernel: 5 kernels per leapfrog step on N ranks instead of 9.
+    bool fuse_prod = true;
+    bool pack_counted = false;   // big_qfix_kick_kernel has left this step's chunk counts in packcnt
     PeerPtrs peers{};
     void* ipc_opened[kMaxWorld] = {};
     bool peer_enabled = false;  // the pair records of the owned stars' current positions are already in the tile lists
@@ -1080,6 +1233,10 @@ int srhmc_big_set_stars(srhmc_big* b, const double* q, const int64_t* global_ids
         b->own_binned = false;
         b->ghosts_binned = false;
     }
+    if (b->pack_counted) {  // boundary counts of the previous positions
+        BCU(cudaMemsetAsync(b->packcnt.ptr, 0, b->packcnt.cap, b->stream));
+        b->pack_counted = false;
+    }
     BCU(cudaStreamSynchronize(b->stream));
     b->n = n;
     return 0;
@@ -1167,6 +1324,9 @@ int srhmc_big_comm_import(srhmc_big* b, const void* ipc_handles, void* const* ra
     b->peer_enabled = true;
     if (const char* e = std::getenv("SRHMC_PEER_FUSE_MAX")) b->fuse_max = e[0] == '1';
     if (const char* e = std::getenv("SRHMC_PEER_FUSE_BIN")) b->fuse_bin = e[0] != '0';
+    if (const char* e = std::getenv("SRHMC_PEER_FUSE_PROD")) b->fuse_prod = e[0] != '0';
+    if (b->fuse_max || !b->fuse_bin) b->fuse_prod = false;
+    BCU(cudaMemset(b->packcnt.ptr, 0, b->packcnt.cap));
     return 0;
 }
 
@@ -1260,8 +1420,11 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
     cudaStream_t st = b->stream;
     PeerX X;
     std::memset(&X, 0, sizeof(X));
-    if (b->peer_enabled && b->world > 1 && b->fuse_max) {
-        X.peers = b->peers; X.rank = b->rank; X.world = b->world; X.on = 1;
+    const bool peer_multi = b->peer_enabled && b->world > 1;
+    if (peer_multi && (b->fuse_max || b->fuse_prod)) {
+        X.peers = b->peers; X.rank = b->rank; X.world = b->world;
+        X.on = b->fuse_max ? 1 : 0;
+        X.prod = b->fuse_prod ? 1 : 0;
         X.epoch = b->xepoch.as<unsigned long long>(); X.ticket = b->xticket.as<unsigned int>(); X.err = b->err.as<int>();
     }
     switch (phase) {
@@ -1271,6 +1434,24 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             const double lo_edge = (b->rank > 0) ? (double)P.own_lo + reach : -1e300;
             const double hi_edge = (b->rank < b->world - 1) ? (double)P.own_hi - reach : 1e300;
             const int pb = std::max(1, (n + kPackChunk - 1) / kPackChunk);
+            if (peer_multi && b->fuse_prod) {
+                if (!b->pack_counted) {   // a PACK that does not follow a position update (first evaluation of a run)
+                    big_pack_count_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>());
+                    b->launches += 1;
+                }
+                GhostX G;
+                G.peers = b->peers; G.rank = b->rank; G.world = b->world; G.recv = b->recv.as<double>(); G.list = list;
+                G.epoch = b->xepoch.as<unsigned long long>(); G.ticket = b->xticket.as<unsigned int>() + 1;
+                G.ntx = b->ntx; G.n_own = n;
+                G.tcnt = b->use_tiles ? b->tcnt.as<int>() : nullptr;
+                G.tlist = b->use_tiles ? b->tlist.as<int2>() : nullptr;
+                big_pack_xchg_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>(), b->send.as<double>(),
+                                                         std::max(1, b->cfg.max_ghosts), b->err.as<int>(), P, G);
+                b->ghosts_binned = b->use_tiles;
+                b->pack_counted = false;
+                b->launches += 1;
+                break;
+            }
             big_pack_count_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>());
             big_pack_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>(), b->send.as<double>(),
                                                  std::max(1, b->cfg.max_ghosts), b->err.as<int>());
@@ -1359,10 +1540,10 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             }
             if (tail == 1)
                 big_tail_kernel<false><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart,
-                                                          b->a1.as<double>(), b->a2.as<double>(), cnt);
+                                                          b->a1.as<double>(), b->a2.as<double>(), cnt, X);
             else if (tail == 2)
                 big_tail_kernel<true><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart,
-                                                         b->a1.as<double>(), b->a2.as<double>(), cnt);
+                                                         b->a1.as<double>(), b->a2.as<double>(), cnt, X);
             if (tail) b->launches += 1;
             break;
         }
@@ -1372,22 +1553,23 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
         case SRHMC_BIG_KICK1:
             BCU(cudaMemsetAsync(cnt, 0, 8, st));
             big_kick1_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(),
-                                                b->a1.as<double>(), b->a2.as<double>(), cnt);
+                                                b->a1.as<double>(), b->a2.as<double>(), cnt, X);
             b->launches += 1;
             break;
         case SRHMC_BIG_PFIX_QFIX:
-            if (b->peer_enabled && b->world > 1 && !b->fuse_max) {
+            if (peer_multi && !b->fuse_max && !b->fuse_prod) {
                 big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
                 b->launches += 1;
             }
-            // tiled over peers: the field-wide maximum of the p fixed-point counts is taken inside the kernel (PeerX)
+            // tiled over peers: the field-wide maximum of the p fixed-point counts was all-reduced by the last block of the
+            // kernel that produced it (fuse_prod), or is taken inside this kernel (fuse_max), or by the exchange kernel above
             big_pfix_qfix_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt, cnt + 1, X);
             b->launches += 1;
             break;
-        case SRHMC_BIG_QFIX_KICK:
-            if (b->peer_enabled && b->world > 1 && !b->fuse_max) {
+        case SRHMC_BIG_QFIX_KICK: {
+            if (peer_multi && !b->fuse_max && !b->fuse_prod) {
                 big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
                 b->launches += 1;
@@ -1396,12 +1578,21 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
                 b->ghosts_binned = false;
             }
+            const bool count_here = peer_multi && b->fuse_prod;
+            if (count_here && b->pack_counted)   // counts nobody consumed (two position updates without a PACK)
+                BCU(cudaMemsetAsync(b->packcnt.ptr, 0, b->packcnt.cap, st));
+            const double reach_k = (double)(b->cfg.nrows_halo + P.rad + 1);
+            const double lo_edge_k = (b->rank > 0) ? (double)P.own_lo + reach_k : -1e300;
+            const double hi_edge_k = (b->rank < b->world - 1) ? (double)P.own_hi - reach_k : 1e300;
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt + 1, b->ntx, b->use_tiles ? b->tcnt.as<int>() : nullptr,
-                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>(), X);
+                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>(), X,
+                                                    count_here ? b->packcnt.as<int2>() : nullptr, lo_edge_k, hi_edge_k);
+            b->pack_counted = count_here;
             b->own_binned = b->use_tiles;
             b->launches += 1;
             break;
+        }
         case SRHMC_BIG_KICK2:
             big_kick2_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>());
             b->launches += 1;
