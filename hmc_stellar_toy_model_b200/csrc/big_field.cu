@@ -440,7 +440,7 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
 // q fixed point phase B, then (4) p -= h dtau/dq at the new q
 // and -- tile path -- the pair records of the star's final position for the coming evaluation (bin_star, big_tile.cuh)
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
-                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, int2* tlist, int* err, const PeerX X,
+                                     const double* a2, const int* cnt_q, int ntx, int* tcnt, PairRec* tlist, int* err, const PeerX X,
                                      int2* pack_counts, double lo_edge, double hi_edge) {
     const int target = X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -457,7 +457,7 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
         q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
         const Metric m = metric_of(P.F, qf, S.g_ff2);
         p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
-        if (tcnt) bin_star(P, ntx, k, qx, qy, true, tcnt, tlist, err);
+        if (tcnt) bin_star(P, ntx, k, qf, qx, qy, true, tcnt, tlist, err);
         // boundary-star counts per 1024-star chunk for the ordered ghost packing that follows (integer atomics: exact)
         if (pack_counts) {
             if (qx < lo_edge) atomicAdd(&pack_counts[k >> 10].x, 1);
@@ -750,7 +750,7 @@ __global__ void big_xchg_small_kernel(const PeerPtrs peers, int rank, int world,
 // ([source rank][list][1 + 3 cap]) the evaluation reads: list 1 of rank-1 and list 0 of rank+1
 __device__ void ghost_exchange_body(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
                                       unsigned long long* epoch, int* err, const BigParams P, int ntx, int n_own, int cap, int* tcnt,
-                                      int2* tlist) {
+                                      PairRec* tlist) {
     const unsigned long long e = epoch[1] + 1;
     const int par = (int)(e & 1);
     auto mailbox = [&](int r, int side) {
@@ -793,14 +793,14 @@ __device__ void ghost_exchange_body(const PeerPtrs peers, int rank, int world, c
             const double* g = recv + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * list;
             const int ng = min((int)g[0], cap);
             for (int k = threadIdx.x; k < ng; k += blockDim.x)
-                bin_star(P, ntx, n_own + side * cap + k, g[2 + 3 * k], g[3 + 3 * k], false, tcnt, tlist, err);
+                bin_star(P, ntx, n_own + side * cap + k, g[1 + 3 * k], g[2 + 3 * k], g[3 + 3 * k], false, tcnt, tlist, err);
         }
     }
 }
 
 __global__ void big_xchg_ghost_kernel(const PeerPtrs peers, int rank, int world, const double* send, double* recv, size_t list,
                                       unsigned long long* epoch, int* err, const BigParams P, int ntx, int n_own, int cap, int* tcnt,
-                                      int2* tlist) {
+                                      PairRec* tlist) {
     ghost_exchange_body(peers, rank, world, send, recv, list, epoch, err, P, ntx, n_own, cap, tcnt, tlist);
 }
 
@@ -816,7 +816,7 @@ struct GhostX {
     unsigned int* ticket;
     int ntx, n_own;
     int* tcnt;
-    int2* tlist;
+    PairRec* tlist;
 };
 
 __global__ void big_pack_xchg_kernel(int n, const double* q, double lo_edge, double hi_edge, int2* counts, double* send, int cap,
@@ -1039,10 +1039,10 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     rc |= b->D.ensure(npix * 8);
     if (!b->use_tiles) rc |= b->L.ensure(npix * 8);
     if (b->use_tiles) {
-        // fixed-capacity pair lists (kTileMaxList records per tile: 8 KB of address space each, only the live records
+        // fixed-capacity pair lists (kTileMaxList records per tile: 32 KB of address space each, only the live records
         // are ever touched)
         rc |= b->tcnt.ensure(ntiles * 4);
-        rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(int2)); rc |= b->gpart.ensure(12 * (size_t)cfg->max_stars * 8);
+        rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(PairRec)); rc |= b->gpart.ensure(12 * (size_t)cfg->max_stars * 8);
         if (!rc) cudaMemset(b->tcnt.ptr, 0, ntiles * 4);
         if (!rc && (cudaFuncSetAttribute(big_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess ||
                     cudaFuncSetAttribute(big_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess))
@@ -1180,7 +1180,7 @@ int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t 
     if (int rc = truth.ensure((1 + 3 * (size_t)std::max(1, n)) * 8)) return rc;
     int rc = 0;
     rc |= b->tcnt.ensure(ntiles * 4);
-    rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(int2));
+    rc |= b->tlist.ensure(ntiles * (size_t)kTileMaxList * sizeof(PairRec));
     if (rc) { truth.release(); return SRHMC_ERR_CUDA; }
     if (cudaFuncSetAttribute(big_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)) != cudaSuccess) {
         truth.release();
@@ -1196,8 +1196,8 @@ int srhmc_big_mock_data(srhmc_big* b, const double* q_true, int32_t n, uint64_t 
         S.q = nullptr; S.ga = truth.as<double>(); S.gb = nullptr; S.n_own = 0; S.cap = std::max(1, n);
         if (n)
             big_bin_kernel<<<std::max(1, std::min((n + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
-                b->P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
-        big_tile_kernel<2><<<(int)ntiles, kTileThreads, sizeof(TileSmem), st>>>(b->P, S, b->ntx, nullptr, b->tcnt.as<int>(), b->tlist.as<int2>(),
+                b->P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<PairRec>(), b->err.as<int>());
+        big_tile_kernel<2><<<(int)ntiles, kTileThreads, sizeof(TileSmem), st>>>(b->P, S, b->ntx, nullptr, b->tcnt.as<int>(), b->tlist.as<PairRec>(),
                                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, b->D.as<double>(), seed,
                                                                                 b->tmapD, 0);
         b->launches += 2;
@@ -1444,7 +1444,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 G.epoch = b->xepoch.as<unsigned long long>(); G.ticket = b->xticket.as<unsigned int>() + 1;
                 G.ntx = b->ntx; G.n_own = n;
                 G.tcnt = b->use_tiles ? b->tcnt.as<int>() : nullptr;
-                G.tlist = b->use_tiles ? b->tlist.as<int2>() : nullptr;
+                G.tlist = b->use_tiles ? b->tlist.as<PairRec>() : nullptr;
                 big_pack_xchg_kernel<<<pb, 256, 0, st>>>(n, b->q.as<double>(), lo_edge, hi_edge, b->packcnt.as<int2>(), b->send.as<double>(),
                                                          std::max(1, b->cfg.max_ghosts), b->err.as<int>(), P, G);
                 b->ghosts_binned = b->use_tiles;
@@ -1461,7 +1461,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 big_xchg_ghost_kernel<<<1, 256, 0, st>>>(b->peers, b->rank, b->world, b->send.as<double>(), b->recv.as<double>(), list,
                                                          b->xepoch.as<unsigned long long>(), b->err.as<int>(), P, b->ntx, n,
                                                          std::max(1, b->cfg.max_ghosts), (b->use_tiles && b->fuse_bin) ? b->tcnt.as<int>() : nullptr,
-                                                         b->use_tiles ? b->tlist.as<int2>() : nullptr);
+                                                         b->use_tiles ? b->tlist.as<PairRec>() : nullptr);
                 b->ghosts_binned = b->use_tiles && b->fuse_bin;
                 b->launches += 1;
             }
@@ -1484,18 +1484,18 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 const int ntiles = b->nty * b->ntx;
                 if (!b->own_binned && n > 0) {
                     big_bin_kernel<<<std::max(1, std::min((n + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
-                        P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                        P, S, b->ntx, 0, n, b->tcnt.as<int>(), b->tlist.as<PairRec>(), b->err.as<int>());
                     b->launches += 1;
                 }
                 if ((ga || gb) && !b->ghosts_binned) {
                     big_bin_kernel<<<std::max(1, std::min((2 * S.cap + 255) / 256, 8 * b->sm_count)), 256, 0, st>>>(
-                        P, S, b->ntx, n, n + 2 * S.cap, b->tcnt.as<int>(), b->tlist.as<int2>(), b->err.as<int>());
+                        P, S, b->ntx, n, n + 2 * S.cap, b->tcnt.as<int>(), b->tlist.as<PairRec>(), b->err.as<int>());
                     b->launches += 1;
                 }
                 b->own_binned = false;  // the tile kernel consumes the lists and re-zeroes the counters
                 b->ghosts_binned = false;
                 if (b->precision == 32 && !want_V) {
-                    big_tile32_kernel<<<ntiles, kTileThreads, sizeof(TileSmemF), st>>>(P, S, b->ntx, b->tcnt.as<int>(), b->tlist.as<int2>(),
+                    big_tile32_kernel<<<ntiles, kTileThreads, sizeof(TileSmemF), st>>>(P, S, b->ntx, b->tcnt.as<int>(), b->tlist.as<PairRec>(),
                                                                                        b->gpart.as<double>(), cnt, b->tmapD32);
                 } else if (b->tile2) {
                     int grid2 = std::min(ntiles, 4 * b->sm_count);   // persistent: 4 CTAs per SM walk the tiles
@@ -1505,19 +1505,19 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                     }
                     if (want_V)
                         big_tile2_kernel<true><<<grid2, kTileThreads, sizeof(Tile2Smem), st>>>(P, S, b->tmapD, b->ntx, ntiles, b->tcnt.as<int>(),
-                            b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
+                            b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
                             b->scalars.as<double>(), cnt);
                     else
                         big_tile2_kernel<false><<<grid2, kTileThreads, sizeof(Tile2Smem), st>>>(P, S, b->tmapD, b->ntx, ntiles, b->tcnt.as<int>(),
-                            b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
+                            b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
                             b->scalars.as<double>(), cnt);
                 } else if (want_V)
                     big_tile_kernel<1><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
-                        b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(),
                         b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull, b->tmapD, b->tma ? 1 : 0);
                 else
                     big_tile_kernel<0><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
-                        b->tlist.as<int2>(), b->gpart.as<double>(), b->vpart.as<double>(),
+                        b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(),
                         b->tickets.as<unsigned int>() + 1, b->scalars.as<double>(), cnt, nullptr, 0ull, b->tmapD, b->tma ? 1 : 0);
                 b->launches += 1;
                 if (tail == 0) {
@@ -1586,7 +1586,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             const double hi_edge_k = (b->rank < b->world - 1) ? (double)P.own_hi - reach_k : 1e300;
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt + 1, b->ntx, b->use_tiles ? b->tcnt.as<int>() : nullptr,
-                                                    b->use_tiles ? b->tlist.as<int2>() : nullptr, b->err.as<int>(), X,
+                                                    b->use_tiles ? b->tlist.as<PairRec>() : nullptr, b->err.as<int>(), X,
                                                     count_here ? b->packcnt.as<int2>() : nullptr, lo_edge_k, hi_edge_k);
             b->pack_counted = count_here;
             b->own_binned = b->use_tiles;

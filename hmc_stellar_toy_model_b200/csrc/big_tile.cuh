@@ -55,16 +55,33 @@ __device__ __forceinline__ TileSpan tile_span(const BigParams& P, int i0, int i1
     return t;
 }
 
-// (star, tile) pair record: star id and the box patch x tile in tile coordinates (6 bits each) + the index of the
-// tile in the star's 2x2 footprint
+// (star, tile) pair record: star id, the box patch x tile in tile coordinates (6 bits each) + the index of the tile in the
+// star's 2x2 footprint, and the star itself -- so the tile kernel needs ONE trip to global memory for its list instead of
+// three dependent ones (count -> records -> star data)
+struct __align__(16) PairRec {   // 32 bytes
+    int sid, box;
+    double f, x, y;
+};
+constexpr int kTileRecs = 64;    // records of a tile list kept whole in shared memory (later ones are re-read from L2)
+
+__device__ __forceinline__ PairRec ld_rec(const PairRec* p) {   // two 16-byte L2 loads
+    const int4 a = __ldcg(reinterpret_cast<const int4*>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    PairRec r;
+    r.sid = a.x; r.box = a.y;
+    r.f = __hiloint2double(a.w, a.z);
+    r.x = b.x; r.y = b.y;
+    return r;
+}
+
 __device__ __forceinline__ int pack_box(int ia, int ib, int ja, int jb, int slot) {
     return ia | (ib << 6) | (ja << 12) | (jb << 18) | (slot << 24);
 }
 
 // Append the pair records of one source star to the lists of the tiles its patch touches.  `owned`: the star belongs
 // to this rank, so leaving the local data window is an error (flag 1).  List overflow raises flag 3.
-__device__ __forceinline__ void bin_star(const BigParams& P, int ntx, int sid, double x, double y, bool owned, int* cnt,
-                                         int2* list, int* err) {
+__device__ __forceinline__ void bin_star(const BigParams& P, int ntx, int sid, double f, double x, double y, bool owned, int* cnt,
+                                         PairRec* list, int* err) {
     int i0, i1, j0, j1, mi, mj;
     bool clipped;
     if (!patch_of(P, x, y, i0, i1, j0, j1, mi, mj, clipped)) {
@@ -82,18 +99,21 @@ __device__ __forceinline__ void bin_star(const BigParams& P, int ntx, int sid, d
                 continue;
             }
             const int r0 = P.row0 + ti * kTile, c0 = tj * kTile;
-            list[(size_t)tile * kTileMaxList + pos] =
-                make_int2(sid, pack_box(max(i0, r0) - r0, min(i1, r0 + kTile - 1) - r0, max(j0, c0) - c0,
-                                        min(j1, c0 + kTile - 1) - c0, (ti - t.ti0) * 2 + (tj - t.tj0)));
+            PairRec rec;
+            rec.sid = sid;
+            rec.box = pack_box(max(i0, r0) - r0, min(i1, r0 + kTile - 1) - r0, max(j0, c0) - c0, min(j1, c0 + kTile - 1) - c0,
+                               (ti - t.ti0) * 2 + (tj - t.tj0));
+            rec.f = f; rec.x = x; rec.y = y;
+            list[(size_t)tile * kTileMaxList + pos] = rec;
         }
 }
 
 // sources [sid0, sid1): own stars are [0, n_own), the ghost lists follow (tile_source)
-__global__ void big_bin_kernel(const BigParams P, const TileSrc S, int ntx, int sid0, int sid1, int* cnt, int2* list, int* err) {
+__global__ void big_bin_kernel(const BigParams P, const TileSrc S, int ntx, int sid0, int sid1, int* cnt, PairRec* list, int* err) {
     for (int sid = sid0 + blockIdx.x * blockDim.x + threadIdx.x; sid < sid1; sid += gridDim.x * blockDim.x) {
         const double* src = tile_source(S, sid);
         if (!src) continue;
-        bin_star(P, ntx, sid, src[1], src[2], sid < S.n_own, cnt, list, err);
+        bin_star(P, ntx, sid, src[0], src[1], src[2], sid < S.n_own, cnt, list, err);
     }
 }
 
@@ -124,7 +144,9 @@ struct PairTab {
 struct TileSmem {
     double rho[kTile][kTile];          // 32 KB
     PairTab tab[kTileChunk];           // 656 B each
-    int2 list[kTileMaxList];           // sorted pair records
+    PairRec rec[kTileRecs];            // the first records of the list, in arrival order
+    int sid[kTileMaxList];             // star id of every record (ranking key)
+    unsigned short order[kTileMaxList];  // order[r] = arrival index of the record with the r-th smallest star id
     int box[kTileChunk][4];
     double red[32];
     double2 ltab[kLogTableSize];       // table of log_pos (fastmath.cuh), built per CTA when the potential is wanted
@@ -132,11 +154,10 @@ struct TileSmem {
     bool is_last;
 };
 
-__device__ __forceinline__ void build_pair_tab(const BigParams& P, const TileSrc& S, int2 rec, int r0, int c0, int lane,
+__device__ __forceinline__ void build_pair_tab(const BigParams& P, const PairRec& rec, int r0, int c0, int lane,
                                                PairTab& T, int* box) {
-    const double* src = tile_source(S, rec.x);
-    const double f = src[0], x = src[1], y = src[2];
-    const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
+    const double f = rec.f, x = rec.x, y = rec.y;
+    const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
     const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
     T.rowf[kTabPad + lane] = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
     T.colf[kTabPad + lane] = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
@@ -194,7 +215,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_kernel(const BigParams P, const TileSrc S, int ntx,
                                                                 const double* __restrict__ D,
                                                                 int* __restrict__ cnt,
-                                                                const int2* __restrict__ list, double* __restrict__ gpart,
+                                                                const PairRec* __restrict__ list, double* __restrict__ gpart,
                                                                 double* vpart, unsigned int* ticket, double* scalars,
                                                                 int* fp_counters, double* __restrict__ Dout,
                                                                 unsigned long long mock_seed,
@@ -243,9 +264,13 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         cp_async_commit();
     }
 
-    // ---- the tile's pair list, sorted by star id so that every sum below has a fixed order
+    // ---- the tile's pair list, ranked by star id so that every sum below has a fixed order.  The first kTileRecs records
+    //      are fetched speculatively together with the count (one trip to L2 instead of two dependent ones); they carry
+    //      the star's (f, x, y), so no third trip follows.
     list += (size_t)blockIdx.x * kTileMaxList;
-    constexpr int b0 = 0;
+    PairRec spec;
+    spec.sid = 0; spec.box = 0; spec.f = spec.x = spec.y = 0.0;
+    if (tid < kTileRecs) spec = ld_rec(&list[tid]);
     const int nl = min(cnt[blockIdx.x], kTileMaxList);  // an overflow was flagged when the list was filled
     // the fixed-point iteration counters of the leapfrog step are free between its last reader and the next step
     if (fp_counters && blockIdx.x == 0 && tid < 2) fp_counters[tid] = 0;
@@ -261,18 +286,25 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         const double rc = 1.0 / (1.0 + ((double)tid + 0.5) / (double)kLogTableSize);
         sm.ltab[tid] = make_double2(rc, -log(rc));
     }
-    if (nl == 1) {
-        if (tid == 0) sm.list[0] = __ldcg(&list[b0]);
-    } else if (nl > 1) {
-        for (int k = tid; k < nl; k += kTileThreads) {
-            const int2 rec = __ldcg(&list[b0 + k]);
-            int r = 0;
-            for (int m = 0; m < nl; ++m) r += __ldcg(&list[b0 + m].x) < rec.x;
-            sm.list[r] = rec;
-        }
+    if (tid < min(nl, kTileRecs)) {
+        sm.rec[tid] = spec;
+        sm.sid[tid] = spec.sid;
+    }
+    for (int k = kTileRecs + tid; k < nl; k += kTileThreads) sm.sid[k] = __ldcg(&list[k].sid);   // dense tiles only
+    __syncthreads();
+    for (int k = tid; k < nl; k += kTileThreads) {
+        const int mine = sm.sid[k];
+        int r = 0;
+        for (int m = 0; m < nl; ++m) r += sm.sid[m] < mine;
+        sm.order[r] = (unsigned short)k;
     }
     __syncthreads();
     if (tid == 0) cnt[blockIdx.x] = 0;  // every thread has read the count: ready for the next evaluation's binning
+    // record with the s-th smallest star id
+    auto rec_at = [&](int s) -> PairRec {
+        const int k = sm.order[s];
+        return k < kTileRecs ? sm.rec[k] : ld_rec(&list[k]);
+    };
 
     // ---- render Lambda = B + sum f PSF over the list, in list order
     double lam[4][4];
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         for (int b = 0; b < 4; ++b) lam[a][b] = P.F.B;
     for (int base = 0; base < nl; base += kTileChunk) {
         const int nc = min(kTileChunk, nl - base);
-        for (int s = warp; s < nc; s += kWarps) build_pair_tab(P, S, sm.list[base + s], r0, c0, lane, sm.tab[s], sm.box[s]);
+        for (int s = warp; s < nc; s += kWarps) build_pair_tab(P, rec_at(base + s), r0, c0, lane, sm.tab[s], sm.box[s]);
         __syncthreads();
         for (int s = 0; s < nc; ++s) {
             const int ia = sm.box[s][0], ja = sm.box[s][2];
@@ -344,15 +376,15 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     //      the warp rebuilds the pair's tables in its own slot.
     const bool keep = nl <= kTileChunk;
     for (int s = warp; s < nl; s += kWarps) {
-        const int2 rec = sm.list[s];
-        if (rec.x >= S.n_own) continue;  // ghosts are rendered only
+        const PairRec rec = rec_at(s);
+        if (rec.sid >= S.n_own) continue;  // ghosts are rendered only
         PairTab& T = sm.tab[keep ? s : warp];
         if (!keep) {
             __syncwarp();
-            build_pair_tab(P, S, rec, r0, c0, lane, T, nullptr);
+            build_pair_tab(P, rec, r0, c0, lane, T, nullptr);
             __syncwarp();
         }
-        const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
+        const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
         const double fy = T.colf[kTabPad + lane];                // f ey of this lane's column, 0 past the box
         const double dyl = T.dy0 + (double)lane;
         const double* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
@@ -380,7 +412,7 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
             yv += __shfl_xor_sync(0xffffffffu, yv, 2);
             yv += __shfl_xor_sync(0xffffffffu, yv, 1);
             // lane 0: sum sf, lane 8: sum sx, lane 16: sum sy
-            if ((lane & 7) == 0 && lane < 24) gpart[((size_t)rec.x * 4 + (rec.y >> 24)) * 3 + (lane >> 3)] = yv;
+            if ((lane & 7) == 0 && lane < 24) gpart[((size_t)rec.sid * 4 + (rec.box >> 24)) * 3 + (lane >> 3)] = yv;
         }
     }
     // ---- pixel potential: the last tile to finish sums the per-tile partials in tile order -> scalars[0]
@@ -412,16 +444,17 @@ struct PairTabF {
 struct TileSmemF {
     float rho[kTile][kTile];           // 16 KB, TMA destination
     PairTabF tab[kTileChunk];
-    int2 list[kTileMaxList];
+    PairRec rec[kTileRecs];
+    int sid[kTileMaxList];
+    unsigned short order[kTileMaxList];
     int box[kTileChunk][4];
     unsigned long long mbar;
 };
 
-__device__ __forceinline__ void build_pair_tab_f(const BigParams& P, const TileSrc& S, int2 rec, int r0, int c0, int lane,
+__device__ __forceinline__ void build_pair_tab_f(const BigParams& P, const PairRec& rec, int r0, int c0, int lane,
                                                  PairTabF& T, int* box) {
-    const double* src = tile_source(S, rec.x);
-    const double f = src[0], x = src[1], y = src[2];
-    const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = (rec.y >> 12) & 63, jb = (rec.y >> 18) & 63;
+    const double f = rec.f, x = rec.x, y = rec.y;
+    const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
     const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
     T.rowf[kTabPad + lane] = (ia + lane <= ib) ? (float)exp_neg(-(dx * dx) * P.inv2s2) : 0.0f;
     T.colf[kTabPad + lane] = (ja + lane <= jb) ? (float)(exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f)) : 0.0f;
@@ -435,7 +468,7 @@ __device__ __forceinline__ void build_pair_tab_f(const BigParams& P, const TileS
 }
 
 __global__ void __launch_bounds__(kTileThreads, 5)
-big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__ cnt, const int2* __restrict__ list,
+big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__ cnt, const PairRec* __restrict__ list,
                   double* __restrict__ gpart, int* fp_counters, const __grid_constant__ CUtensorMap tmapD32) {
     extern __shared__ __align__(128) unsigned char tile32_smem_raw[];
     TileSmemF& sm = *reinterpret_cast<TileSmemF*>(tile32_smem_raw);
@@ -452,6 +485,9 @@ big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__
         tma_load_2d(&sm.rho[0][0], &tmapD32, c0, r0 - P.row0, &sm.mbar);
     }
     list += (size_t)blockIdx.x * kTileMaxList;
+    PairRec spec;
+    spec.sid = 0; spec.box = 0; spec.f = spec.x = spec.y = 0.0;
+    if (tid < kTileRecs) spec = ld_rec(&list[tid]);   // speculative: in flight together with the count
     const int nl = min(cnt[blockIdx.x], kTileMaxList);
     if (fp_counters && blockIdx.x == 0 && tid < 2) fp_counters[tid] = 0;
     for (int k = tid; k < kTileChunk * 4 * kTabPad; k += kTileThreads) {
@@ -459,18 +495,24 @@ big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__
         float* t = (side & 1) ? sm.tab[pair].colf : sm.tab[pair].rowf;
         t[(side & 2) ? kTabPad + 32 + g : g] = 0.0f;
     }
-    if (nl == 1) {
-        if (tid == 0) sm.list[0] = __ldcg(&list[0]);
-    } else if (nl > 1) {
-        for (int k = tid; k < nl; k += kTileThreads) {
-            const int2 rec = __ldcg(&list[k]);
-            int r = 0;
-            for (int m = 0; m < nl; ++m) r += __ldcg(&list[m].x) < rec.x;
-            sm.list[r] = rec;
-        }
+    if (tid < min(nl, kTileRecs)) {
+        sm.rec[tid] = spec;
+        sm.sid[tid] = spec.sid;
+    }
+    for (int k = kTileRecs + tid; k < nl; k += kTileThreads) sm.sid[k] = __ldcg(&list[k].sid);
+    __syncthreads();
+    for (int k = tid; k < nl; k += kTileThreads) {
+        const int mine = sm.sid[k];
+        int r = 0;
+        for (int m = 0; m < nl; ++m) r += sm.sid[m] < mine;
+        sm.order[r] = (unsigned short)k;
     }
     __syncthreads();
     if (tid == 0) cnt[blockIdx.x] = 0;
+    auto rec_at = [&](int s) -> PairRec {
+        const int k = sm.order[s];
+        return k < kTileRecs ? sm.rec[k] : ld_rec(&list[k]);
+    };
 
     float lam[4][4];
     const float Bf = (float)P.F.B;
@@ -480,7 +522,7 @@ big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__
         for (int b = 0; b < 4; ++b) lam[a][b] = Bf;
     for (int base = 0; base < nl; base += kTileChunk) {
         const int nc = min(kTileChunk, nl - base);
-        for (int s = warp; s < nc; s += kWarps) build_pair_tab_f(P, S, sm.list[base + s], r0, c0, lane, sm.tab[s], sm.box[s]);
+        for (int s = warp; s < nc; s += kWarps) build_pair_tab_f(P, rec_at(base + s), r0, c0, lane, sm.tab[s], sm.box[s]);
         __syncthreads();
         for (int s = 0; s < nc; ++s) {
             const int ia = sm.box[s][0], ja = sm.box[s][2];
@@ -513,15 +555,15 @@ big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__
     __syncthreads();
     const bool keep = nl <= kTileChunk;
     for (int s = warp; s < nl; s += kWarps) {
-        const int2 rec = sm.list[s];
-        if (rec.x >= S.n_own) continue;
+        const PairRec rec = rec_at(s);
+        if (rec.sid >= S.n_own) continue;
         PairTabF& T = sm.tab[keep ? s : warp];
         if (!keep) {
             __syncwarp();
-            build_pair_tab_f(P, S, rec, r0, c0, lane, T, nullptr);
+            build_pair_tab_f(P, rec, r0, c0, lane, T, nullptr);
             __syncwarp();
         }
-        const int ia = rec.y & 63, ib = (rec.y >> 6) & 63, ja = rec.y >> 12 & 63, jb = (rec.y >> 18) & 63;
+        const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = rec.box >> 12 & 63, jb = (rec.box >> 18) & 63;
         const float fy = T.colf[kTabPad + lane];
         const float dyl = T.dy0 + (float)lane;
         const float* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
@@ -547,7 +589,7 @@ big_tile32_kernel(const BigParams P, const TileSrc S, int ntx, int* __restrict__
             yv += __shfl_xor_sync(0xffffffffu, yv, 4);
             yv += __shfl_xor_sync(0xffffffffu, yv, 2);
             yv += __shfl_xor_sync(0xffffffffu, yv, 1);
-            if ((lane & 7) == 0 && lane < 24) gpart[((size_t)rec.x * 4 + (rec.y >> 24)) * 3 + (lane >> 3)] = yv;
+            if ((lane & 7) == 0 && lane < 24) gpart[((size_t)rec.sid * 4 + (rec.box >> 24)) * 3 + (lane >> 3)] = yv;
         }
     }
 }
@@ -569,11 +611,6 @@ __global__ void big_to_float_kernel(const double* __restrict__ src, float* __res
 //     16-byte residual load + one {ex, ex dx} load per row for 4 FMAs, the reciprocal of Lambda is seeded in FP32.
 constexpr int kT2List = 96;     // sorted records held in shared memory per pass (denser tiles take several passes)
 constexpr int kT2Chunk = 16;    // table slots: render chunk = 16 pairs; the gather uses slots 2 warp, 2 warp + 1
-
-struct PairRec {                // 32 bytes
-    int sid, box;
-    double f, x, y;
-};
 
 struct PairTab2 {
     double2 rowp[kTabLen];      // {ex, ex dx} of row ia + k at [kTabPad + k]; zero outside the box
@@ -630,7 +667,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 template <bool WANT_V>
 __global__ void __launch_bounds__(kTileThreads, 4)
 big_tile2_kernel(const BigParams P, const TileSrc S, const __grid_constant__ CUtensorMap tmapD, int ntx, int ntiles,
-                 int* __restrict__ cnt, const int2* __restrict__ glist, double* __restrict__ gpart, double* vpart,
+                 int* __restrict__ cnt, const PairRec* __restrict__ glist, double* __restrict__ gpart, double* vpart,
                  unsigned int* ticket, double* scalars, int* fp_counters) {
     extern __shared__ __align__(128) unsigned char tile2_smem_raw[];
     Tile2Smem& sm = *reinterpret_cast<Tile2Smem*>(tile2_smem_raw);
@@ -652,24 +689,15 @@ big_tile2_kernel(const BigParams P, const TileSrc S, const __grid_constant__ CUt
     // The three dependent trips that fetch a tile's pair list, each asynchronous (global -> shared, no registers held):
     //   fetch_records: (star id, box) of record tid;  fetch_stars: (f, x, y) of that star, once the id has landed;
     //   rank_list: order[] by star id (fixed summation order).  Lists longer than kT2List go pass by pass (dense_pass).
-    auto fetch_records = [&](int buf, int nl, const int2* gl) {
-        if (nl <= kT2List && tid < nl) cp_async8(&sm.list[buf][tid].sid, &gl[tid]);
-        cp_async_commit();
-    };
-    auto fetch_stars = [&](int buf, int nl) {
-        cp_async_wait_all();   // own record
-        if (nl <= kT2List && tid < nl) {
-            PairRec& o = sm.list[buf][tid];
-            const double* src = tile_source(S, o.sid);
-            if (src) {
-                cp_async8(&o.f, src);
-                cp_async8(&o.x, src + 1);
-                cp_async8(&o.y, src + 2);
-            } else {
-                o.f = 0.0; o.x = 0.0; o.y = 0.0;
-            }
+    auto fetch_records = [&](int buf, int nl, const PairRec* gl) {
+        if (nl <= kT2List && tid < nl) {   // the whole 32-byte record (id, box, star) in two 16-byte asynchronous copies
+            cp_async16(&sm.list[buf][tid], &gl[tid]);
+            cp_async16(reinterpret_cast<char*>(&sm.list[buf][tid]) + 16, reinterpret_cast<const char*>(&gl[tid]) + 16);
         }
         cp_async_commit();
+    };
+    auto fetch_stars = [&](int buf, int nl) {   // nothing left to fetch: the records carry (f, x, y)
+        (void)buf; (void)nl;
     };
     auto rank_list = [&](int buf, int nl) {   // after a barrier that follows every thread's cp_async_wait_all
         if (nl <= kT2List && tid < nl) {
@@ -680,17 +708,14 @@ big_tile2_kernel(const BigParams P, const TileSrc S, const __grid_constant__ CUt
         }
         if (tid == 0) sm.nl[buf] = nl;
     };
-    auto dense_pass = [&](int buf, int nl_total, int base, const int2* gl) {
+    auto dense_pass = [&](int buf, int nl_total, int base, const PairRec* gl) {
         // dense tile: every record is ranked against the whole global list; this pass keeps ranks [base, base + kT2List)
         for (int k = tid; k < nl_total; k += kTileThreads) {
-            const int2 rc = __ldcg(&gl[k]);
+            const int mine = __ldcg(&gl[k].sid);
             int r = 0;
-            for (int m = 0; m < nl_total; ++m) r += __ldcg(&gl[m].x) < rc.x;
+            for (int m = 0; m < nl_total; ++m) r += __ldcg(&gl[m].sid) < mine;
             if (r >= base && r < base + kT2List) {
-                const double* src = tile_source(S, rc.x);
-                PairRec& o = sm.list[buf][r - base];
-                o.sid = rc.x; o.box = rc.y;
-                o.f = src ? src[0] : 0.0; o.x = src ? src[1] : 0.0; o.y = src ? src[2] : 0.0;
+                sm.list[buf][r - base] = ld_rec(&gl[k]);
                 sm.order[buf][r - base] = (unsigned char)(r - base);
             }
         }
@@ -702,7 +727,7 @@ big_tile2_kernel(const BigParams P, const TileSrc S, const __grid_constant__ CUt
     // prologue: the first tile's list (latency exposed once per CTA)
     if (tile < ntiles) {
         const int nl0 = min(__ldcg(&cnt[tile]), kTileMaxList);
-        const int2* gl = glist + (size_t)tile * kTileMaxList;
+        const PairRec* gl = glist + (size_t)tile * kTileMaxList;
         fetch_records(cur, nl0, gl);
         fetch_stars(cur, nl0);
         cp_async_wait_all();
