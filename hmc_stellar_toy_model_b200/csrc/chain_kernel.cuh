@@ -113,6 +113,52 @@ __device__ __forceinline__ double rcp_pix(double a) {
 __device__ __forceinline__ double rcp_pix(double a) { return rcp_fast(a); }
 #endif
 
+// Reciprocals of N pixels from ONE MUFU.RCP64H: 1/a_k = (product of the others) / (product of all).  The FP64 instruction
+// count is the same as N separate cubic Newton reciprocals (3 per pixel: products down, one Newton step, products up), but the
+// pixel loop was bound by the XU pipe (MUFU.RCP64H + I2F per pixel, 8 issue cycles each per scheduler against 14 cycles of
+// DFMA): this leaves one MUFU per 3 (4) pixels.  Each result carries <= 4 roundings (~2^-51 relative).  Lambda = 0 in a group
+// gives NaN for its neighbours as well (the reference gives inf at that pixel and a non-finite gradient either way).
+#ifndef SRHMC_RCP_TREE
+#define SRHMC_RCP_TREE 1
+#endif
+template <int N>
+__device__ __forceinline__ void rcp_group(const double (&a)[N], double (&r)[N]) {
+    if (SRHMC_RCP_TREE && N == 3) {
+        const double p01 = a[0] * a[1];
+        const double ip = rcp_pix(p01 * a[2]);
+        const double r01 = a[2] * ip;
+        r[2] = p01 * ip;
+        r[0] = a[1] * r01;
+        r[1] = a[0] * r01;
+    } else if (SRHMC_RCP_TREE && N == 4) {
+        const double p01 = a[0] * a[1], p23 = a[2] * a[3];
+        const double ip = rcp_pix(p01 * p23);
+        const double r01 = p23 * ip, r23 = p01 * ip;
+        r[0] = a[1] * r01;
+        r[1] = a[0] * r01;
+        r[2] = a[3] * r23;
+        r[3] = a[2] * r23;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) r[k] = rcp_pix(a[k]);
+    }
+}
+// reciprocals of the NCS pixels a lane owns in one image row: triples when NCS is a multiple of 3 (24-column window: 6 slots),
+// quadruples for the full-width variant (8 slots)
+template <int NCS>
+__device__ __forceinline__ void rcp_row(const double (&lam)[NCS], double (&r)[NCS]) {
+    constexpr int GS = (NCS % 3 == 0) ? 3 : (NCS % 4 == 0) ? 4 : 1;
+#pragma unroll
+    for (int g = 0; g < NCS / GS; ++g) {
+        double a[GS], o[GS];
+#pragma unroll
+        for (int k = 0; k < GS; ++k) a[k] = lam[g * GS + k];
+        rcp_group<GS>(a, o);
+#pragma unroll
+        for (int k = 0; k < GS; ++k) r[g * GS + k] = o[k];
+    }
+}
+
 // Elements of padding after each chain image so that the chains of one warp sit on disjoint shared-memory banks:
 // the LPC lanes of a chain read LPC consecutive pixels, so shifting chain g by g*LPC pixels tiles the banks.
 template <typename DT>
@@ -143,11 +189,14 @@ __device__ __forceinline__ void rows_all_slots(int r0, int r1, const DT* __restr
     constexpr int CPL = NCS;
     for (int i = r0; i < r1; ++i) {
         const double2 re = rt[i];
+        double lam[CPL], il[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) lam[c] = fma(re.x, fey[c], B);
+        rcp_row<CPL>(lam, il);
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-            const double lam = fma(re.x, fey[c], B);
             const double d = ld_pix(sDl + i * kChainCS + LPC * c);
-            const double rho = fma(d, rcp_pix(lam), -1.0);
+            const double rho = fma(d, il[c], -1.0);
             c0[c] = fma(rho, re.x, c0[c]);
             c1[c] = fma(rho, re.y, c1[c]);
             if (TIER == 0) {
@@ -318,10 +367,13 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
 #pragma unroll kMainUnroll
         for (int i = i_lo; i < i_hi; ++i) {
             const double2 re = rt[i];
+            double lam[CPL], il[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) lam[c] = fma(re.x, fey[c], P.B);
+            rcp_row<CPL>(lam, il);
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const double lam = fma(re.x, fey[c], P.B);
-                const double rho = fma(ld_pix(sD + i * kChainCS + jb + LPC * c), rcp_pix(lam), -1.0);
+                const double rho = fma(ld_pix(sD + i * kChainCS + jb + LPC * c), il[c], -1.0);
                 c0[c] = fma(rho, re.x, c0[c]);
                 c1[c] = fma(rho, re.y, c1[c]);
             }
