@@ -608,13 +608,18 @@ def tiled_parity_check(env, stream):
     return msg
 
 
-def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity, precision=64):
-    """C5: ONE large field, row strips over the ranks (strong), or one rows x cols strip per rank (weak)."""
+def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity, precision=64,
+                   replicas=False, label="c5_tiled_field", dt=None):
+    """C5: ONE large field, row strips over the ranks (strong), or one rows x cols strip per rank (weak).
+    replicas=True (C3): every rank runs its own copy of the whole field, no communication."""
     torch = env.torch
     from hmc_stellar_toy_model_b200 import _capi
     from hmc_stellar_toy_model_b200 import bigfield as bf
 
     rank, world = env.rank, env.world
+    n_ranks = world
+    if replicas:
+        rank, world, weak = 0, 1, False
     rows_g = rows * (world if weak else 1)
     nst_g = int(nstars * (world if weak else 1))
     rad, halo = 12, 24
@@ -624,8 +629,8 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
     if with_parity and world > 1 and comm_kind == "peer":
         parity = tiled_parity_check(env, stream)
     t = c5_truth(rows_g, cols, nst_g, 77)
-    run = t["run"]
-    strip = _make_strip(env, bf, rows_g, cols, nst_g, t["consts"], halo, rad)
+    run = dict(t["run"], dt=dt) if dt else t["run"]
+    strip = _make_strip(env, bf, rows_g, cols, nst_g, t["consts"], halo, rad, world=world, rank=rank)
     strip.set_stream(stream.cuda_stream)
     if precision == 32:
         strip.set_precision(32)
@@ -641,12 +646,12 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
     # neighbouring strips agree bit for bit), read back once into pinned memory for the e2e arm
     pin_D = _capi.PinnedBuffer((strip.nrows, cols))
     pin_D.array[...] = strip.gen_mock_data(t["q_true"], seed=77, return_data=True)
-    units = nst_g * (niter + 1) * run["nsteps"]
+    units = nst_g * (niter + 1) * run["nsteps"] * (n_ranks if replicas else 1)
     for w in range(warmup):
         strip.set_stars(t["q0"])
         eng.run(niter, seed=1000, **run)
     env.barrier()
-    sampler = ClockSampler(env.local).start() if rank == 0 else None
+    sampler = ClockSampler(env.local).start() if env.rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
     acc = 0.0
@@ -677,7 +682,8 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
         t_e2e += time.perf_counter() - t0
     total_ms, t_e2e = env.max_over_ranks([sum(times), t_e2e])
     rec = None
-    if rank == 0:
+    if env.rank == 0:
+        world = n_ranks
         peaks, peak_src = measured_peaks()
         ms_per_step = total_ms / steps
         value = units * steps / (total_ms * 1e-3)
@@ -685,18 +691,20 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
         # the data strip read once per gradient + star state (FP32 build: float pixels for 9 of 10 evaluations)
         bytes_per_unit = (8.0 if precision == 64 else 4.0 + 4.0 / run["nsteps"]) * A + 96.0
         gbs = bytes_per_unit * units / world / (ms_per_step * 1e-3) / 1e9
-        name = "c5_tiled_field_%dx%d_%dstars%s" % (rows_g, cols, nst_g, "" if precision == 64 else "_fp32")
+        name = "%s_%dx%d_%dstars%s" % (label, rows_g, cols, nst_g, "" if precision == 64 else "_fp32")
         n_own = strip.n
         rec = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (weak or replicas) else "strong",
             "vs_baseline": None, "dtype": "f64" if precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": name, "rows": rows_g, "cols": cols, "stars": nst_g, "niter": niter,
                        "nsteps": run["nsteps"], "dt": run["dt"], "patch_radius": rad, "halo_rows": halo,
                        "rng": "device Philox4x32-10", "data_source": "device-side mock data (srhmc_big_mock_data)",
                        "l2": "every gradient streams this rank's %.0f MB data window from HBM (larger than the 126 MB L2 "
                              "when above it; no flush between launches)" % (pin_D.nbytes / 1e6),
-                       "parallelism": "row strips over %d GPU(s); per step: 1 exchange of boundary stars with the two "
+                       "parallelism": ("replicas only: every one of the %d GPU(s) runs its own chain on the whole field "
+                                       "(one field of this size does not shard), no communication" % world) if replicas else
+                                      "row strips over %d GPU(s); per step: 1 exchange of boundary stars with the two "
                                       "neighbours, 2 max all-reduces; per iteration: 2 sum all-reduces of 8 doubles (%s)"
                                       % (world, "none: single GPU" if world == 1 else
                                          ("own kernels over NVLink peer memory, CUDA-graph replay" if comm_kind == "peer"
@@ -710,7 +718,11 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                          "peak_source": peak_src, "bytes_per_unit": bytes_per_unit,
                          "traffic": traffic_from_profile(name) if world == 1 else None,
-                         "note": "per GPU, over the WHOLE leapfrog step (tile kernel + the per-star kernels + exchanges); "
+                         "note": ("the %.1f MB data image stays in the 126 MB L2, so HBM is not what bounds this field: a leapfrog "
+                                  "step is a handful of dependent kernels over %d tiles (fewer CTAs than the GPU holds), i.e. "
+                                  "launch- and latency-bound; the HBM figure is reported for the common denominator only"
+                                  % (pin_D.nbytes / 1e6, ((rows_g + 63) // 64) * ((cols + 63) // 64))) if replicas else
+                                 "per GPU, over the WHOLE leapfrog step (tile kernel + the per-star kernels + exchanges); "
                                  "algorithmic bytes = the data strip read once per gradient + star state"},
             "accept_rate": acc,
         }
@@ -780,8 +792,18 @@ def run_ours(args):
                               comm_kind=args.comm, with_parity=not weak and precision is None,
                               precision=args.precision if precision is None else precision)
 
+    def c3():
+        # BASELINE configs[2]: "RHMC-big-sim2/3/4 crowded field: hundreds to thousands of stars in one large image with the
+        # full RHMC leapfrog loop" -- one 256 x 256 field at the sim4 / configs[3] density (0.05 stars per pixel: 3277 stars)
+        return bench_bigfield(env, rows=256, cols=256, nstars=3277, weak=False, niter=args.c5_niter,
+                              steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
+                              comm_kind=args.comm, with_parity=False, precision=args.precision, replicas=True,
+                              label="c3_crowded_field")
+
     if which == "c4":
         out = c4()
+    elif which == "c3":
+        out = c3()
     elif which == "c5":
         out = c5(args.weak)
     else:
@@ -799,6 +821,7 @@ def run_ours(args):
     if which == "all":
         subs = {}
         subs["c2_fp32"] = guarded(env, "c2_fp32", c2_fp32)
+        subs["c3"] = guarded(env, "c3", c3)
         subs["c4"] = guarded(env, "c4", c4)
         subs["c5"] = guarded(env, "c5", lambda: c5(False))
         if world > 1:
@@ -857,7 +880,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "c2", "c4", "c5"],
+    ap.add_argument("--workload", default="all", choices=["all", "c2", "c3", "c4", "c5"],
                     help="all: the c2 headline plus c4 / c5 records under 'workloads'; c2|c4|c5: that workload alone")
     ap.add_argument("--rows", type=int, default=8192, help="c5: image rows (per GPU with --weak); BASELINE configs[4] is 8192 x 8192")
     ap.add_argument("--cols", type=int, default=8192)
