@@ -145,7 +145,10 @@ struct TileSmem {
     double rho[kTile][kTile];          // 32 KB
     PairTab tab[kTileChunk];           // 656 B each
     PairRec rec[kTileRecs];            // the first records of the list, in arrival order
-    int sid[kTileMaxList];             // star id of every record (ranking key)
+    union {
+        int sid[kTileMaxList];         // star id of every record (ranking key): dead once the list is ranked ...
+        double rowd[kTileChunk][32];   // ... then ex_k dx_k of row ia + k per table slot (gather phase; no guards needed)
+    };
     unsigned short order[kTileMaxList];  // order[r] = arrival index of the record with the r-th smallest star id
     int box[kTileChunk][4];
     double red[32];
@@ -155,11 +158,13 @@ struct TileSmem {
 };
 
 __device__ __forceinline__ void build_pair_tab(const BigParams& P, const PairRec& rec, int r0, int c0, int lane,
-                                               PairTab& T, int* box) {
+                                               PairTab& T, int* box, double* rowd) {
     const double f = rec.f, x = rec.x, y = rec.y;
     const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
     const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
-    T.rowf[kTabPad + lane] = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
+    const double ex = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
+    T.rowf[kTabPad + lane] = ex;
+    rowd[lane] = ex * dx;
     T.colf[kTabPad + lane] = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
     if (lane == 0) {
         T.dx0 = dx;
@@ -168,6 +173,18 @@ __device__ __forceinline__ void build_pair_tab(const BigParams& P, const PairRec
             box[0] = ia; box[1] = ib; box[2] = ja; box[3] = jb;
         }
     }
+}
+
+// reciprocals of four pixels from one MUFU.RCP64H (product tree: the same number of FP64 instructions as four Newton
+// reciprocals, a quarter of the MUFU / move instructions; <= 4 roundings per result)
+__device__ __forceinline__ void rcp4(const double (&a)[4], double (&r)[4]) {
+    const double p01 = a[0] * a[1], p23 = a[2] * a[3];
+    const double ip = rcp_fast(p01 * p23);
+    const double r01 = p23 * ip, r23 = p01 * ip;
+    r[0] = a[1] * r01;
+    r[1] = a[0] * r01;
+    r[2] = a[3] * r23;
+    r[3] = a[2] * r23;
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS)
@@ -314,13 +331,19 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         for (int b = 0; b < 4; ++b) lam[a][b] = P.F.B;
     for (int base = 0; base < nl; base += kTileChunk) {
         const int nc = min(kTileChunk, nl - base);
-        for (int s = warp; s < nc; s += kWarps) build_pair_tab(P, rec_at(base + s), r0, c0, lane, sm.tab[s], sm.box[s]);
+        for (int s = warp; s < nc; s += kWarps)
+            build_pair_tab(P, rec_at(base + s), r0, c0, lane, sm.tab[s], sm.box[s], sm.rowd[s]);
         __syncthreads();
-        for (int s = 0; s < nc; ++s) {
-            const int ia = sm.box[s][0], ja = sm.box[s][2];
-            if (pr + 3 < ia || pr > sm.box[s][1] || pc + 3 < ja || pc > sm.box[s][3]) continue;
-            const double* te = &sm.tab[s].rowf[kTabPad + pr - ia];  // pr - ia in [-3, 31]: inside the padded table
-            const double* tf = &sm.tab[s].colf[kTabPad + pc - ja];
+        // pairs whose box meets the 8 image rows of this warp (lane s tests pair s), visited in list order
+        const int4 mybox = *reinterpret_cast<const int4*>(sm.box[lane & (kTileChunk - 1)]);
+        unsigned hits = __ballot_sync(0xffffffffu, lane < nc && 8 * warp <= mybox.y && 8 * warp + 7 >= mybox.x);
+        while (hits) {
+            const int s = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int4 bx = *reinterpret_cast<const int4*>(sm.box[s]);   // (ia, ib, ja, jb)
+            if (pr + 3 < bx.x || pr > bx.y || pc + 3 < bx.z || pc > bx.w) continue;
+            const double* te = &sm.tab[s].rowf[kTabPad + pr - bx.x];  // pr - ia in [-3, 31]: inside the padded table
+            const double* tf = &sm.tab[s].colf[kTabPad + pc - bx.z];
             const double ex[4] = {te[0], te[1], te[2], te[3]}, fy[4] = {tf[0], tf[1], tf[2], tf[3]};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -354,11 +377,12 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         const double2 d0 = *reinterpret_cast<const double2*>(&sm.rho[li][pc]);
         const double2 d1 = *reinterpret_cast<const double2*>(&sm.rho[li][pc + 2]);
         const double d[4] = {d0.x, d0.y, d1.x, d1.y};
-        double rho[4];
+        double rho[4], il[4];
+        rcp4(lam[a], il);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const bool in = li < vr && pc + b < vc;
-            rho[b] = in ? fma(d[b], rcp_fast(lam[a][b]), -1.0) : 0.0;
+            rho[b] = in ? fma(d[b], il[b], -1.0) : 0.0;
             if (WANT_V && own && pc + b < vc) v += lam[a][b] - d[b] * (lam[a][b] >= 2.3e-308 ? log_pos(lam[a][b], sm.ltab) : CUDART_NAN);  // ln of a non-positive model is NaN, as in NumPy
         }
         *reinterpret_cast<double2*>(&sm.rho[li][pc]) = make_double2(rho[0], rho[1]);
@@ -381,7 +405,7 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         PairTab& T = sm.tab[keep ? s : warp];
         if (!keep) {
             __syncwarp();
-            build_pair_tab(P, rec, r0, c0, lane, T, nullptr);
+            build_pair_tab(P, rec, r0, c0, lane, T, nullptr, sm.rowd[warp]);
             __syncwarp();
         }
         const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
@@ -389,15 +413,14 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
         const double dyl = T.dy0 + (double)lane;
         const double* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
         const double* rf = &T.rowf[kTabPad];
-        double a0 = 0.0, a1 = 0.0, dxk = T.dx0;
+        const double* rd = sm.rowd[keep ? s : warp];
+        double a0 = 0.0, a1 = 0.0;
         const int nr = ib - ia + 1;
-#pragma unroll 4
-        for (int k = 0; k < nr; ++k) {
-            const double e = rf[k];
+#pragma unroll 5
+        for (int k = 0; k < nr; ++k) {   // two broadcast loads, one residual load, two DFMAs per row
             const double rho = col[k * kTile];
-            a0 = fma(rho, e, a0);
-            a1 = fma(rho * e, dxk, a1);
-            dxk += 1.0;
+            a0 = fma(rho, rf[k], a0);
+            a1 = fma(rho, rd[k], a1);
         }
         // three warp sums with six shuffles: fold the values onto lane groups first
         if (ja + lane > jb) a0 = a1 = 0.0;  // lanes past the box read a clamped column

@@ -361,8 +361,10 @@ __device__ __forceinline__ void chain_eval(const FieldParams& P, const DT* __res
             c1[c] = (double)c1f[c];
         }
     } else if (!WANT_V) {
+        // rows per trip of the gradient-only loop.  With the product-tree reciprocal (one MUFU per three pixels) and a 255-register
+        // budget (still 8 single-warp blocks per SM) four rows measured best: x2 1533, x3 1543, x4 1556 M star-steps/s
 #ifndef SRHMC_MAIN_UNROLL
-#define SRHMC_MAIN_UNROLL 2
+#define SRHMC_MAIN_UNROLL (kChainLPC <= 4 ? 4 : 2)
 #endif
         constexpr int kMainUnroll = SRHMC_MAIN_UNROLL;
 #pragma unroll kMainUnroll
@@ -536,7 +538,7 @@ __device__ __forceinline__ void chain_step(const FieldParams& P, const ChainCons
 }
 
 #ifndef SRHMC_CHAIN_MAXREG
-#define SRHMC_CHAIN_MAXREG (kChainLPC <= 4 ? 232 : 168)
+#define SRHMC_CHAIN_MAXREG (kChainLPC <= 4 ? 255 : 168)
 #endif
 constexpr int kChainMaxReg = SRHMC_CHAIN_MAXREG;
 template <int LPC, typename DT, int MODE, int NCS, int MAXREG = kChainMaxReg, typename PT = double>

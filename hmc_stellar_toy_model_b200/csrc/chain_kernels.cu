@@ -11,7 +11,10 @@ namespace srhmc {
 namespace {
 
 constexpr int kLPC = kChainLPC;  // lanes per chain: 4 -> 8 chains per warp (measured: 16 lanes 734, 8 lanes 1104, 4 lanes 1210 M star-steps/s)
-constexpr int kWarpsPerBlock = 1;
+#ifndef SRHMC_CHAIN_WARPS_PER_BLOCK
+#define SRHMC_CHAIN_WARPS_PER_BLOCK 1
+#endif
+constexpr int kWarpsPerBlock = SRHMC_CHAIN_WARPS_PER_BLOCK;
 // Column slots per lane: the full 32-column image, or a 24-column window around the star when the PSF weight of
 // every dropped column is below 2^-46 of its peak (sigma <= 1.50 px: |dy| >= 12 px).  SRHMC_CHAIN_WINDOW=0 at run time
 // forces the full width (A/B measurements).
