@@ -67,8 +67,13 @@ template <typename DT, typename PT = double>
 int configure_one(const FieldParams& P, int nw, size_t& smem, int& blocks_per_sm) {
     smem = chain_smem_bytes(P, kLPC, nw, sizeof(DT), sizeof(PT) == 4);
     blocks_per_sm = 0;
-    if (use_column_window(P)) return configure_slots<DT, kSlotsWin, PT>(smem, nw, blocks_per_sm);
-    return configure_slots<DT, kSlotsFull, PT>(smem, nw, blocks_per_sm);
+    const int rc = use_column_window(P) ? configure_slots<DT, kSlotsWin, PT>(smem, nw, blocks_per_sm)
+                                        : configure_slots<DT, kSlotsFull, PT>(smem, nw, blocks_per_sm);
+    if (const char* env = std::getenv("SRHMC_CHAIN_MAX_RESIDENT")) {   // occupancy experiments: cap the resident blocks per SM
+        const int k = std::atoi(env);
+        if (rc == 0 && k >= 1) blocks_per_sm = std::min(blocks_per_sm, k);
+    }
+    return rc;
 }
 
 template <typename DT, int NCS, typename PT = double>
