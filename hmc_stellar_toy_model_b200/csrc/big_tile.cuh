@@ -131,9 +131,9 @@ constexpr int kTabLen = 32 + 2 * kTabPad;  // a thread reads 4 consecutive entri
 
 // Factor tables of one (star, tile) pair, built by one warp with two warp-wide exponentials (exp_neg: the kernels'
 // own branch-free FP64 exponential, fastmath.cuh) and used by BOTH the render and the gather phase:
-//   rowf[kTabPad + k] = ex_k      for row  ia + k of the box,  ex = exp(-(i+.5-x)^2/2s^2)
-//   colf[kTabPad + k] = f ey_k    for column ja + k,           ey = norm exp(-(j+.5-y)^2/2s^2)
-// zero past the box and in the guards; (dx0, dy0) = offsets of the box's first row / column from the star, from which
+//   rowf[kTabPad + k] = ex        of row (ia & ~1) + k,     ex = exp(-(i+.5-x)^2/2s^2)
+//   colf[kTabPad + k] = f ey      of column (ja & ~1) + k,  ey = norm exp(-(j+.5-y)^2/2s^2)
+// (even origins: see build_pair_tab) zero outside the box and in the guards; (dx0, dy0) = offsets of the box's first row / column from the star, from which
 // the gather phase forms ex dx and ey dy.
 struct PairTab {
     double rowf[kTabLen];
@@ -163,10 +163,15 @@ __device__ __forceinline__ void build_pair_tab(const BigParams& P, const PairRec
     const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
     const double dx = ((double)(r0 + ia + lane) + 0.5) - x, dy = ((double)(c0 + ja + lane) + 0.5) - y;
     const double ex = (ia + lane <= ib) ? exp_neg(-(dx * dx) * P.inv2s2) : 0.0;
-    T.rowf[kTabPad + lane] = ex;
+    // entry kTabPad + k belongs to row (ia & ~1) + k / column (ja & ~1) + k: a thread's four consecutive entries then start
+    // at an even index and load as two 16-byte words (half the shared-memory wavefronts of four 8-byte loads)
+    const int io = ia & 1, jo = ja & 1;
+    T.rowf[kTabPad + io + lane] = ex;
     rowd[lane] = ex * dx;
-    T.colf[kTabPad + lane] = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
+    T.colf[kTabPad + jo + lane] = (ja + lane <= jb) ? exp_neg(-(dy * dy) * P.inv2s2) * (P.norm * f) : 0.0;
     if (lane == 0) {
+        T.rowf[kTabPad + (io ? 0 : 32)] = 0.0;   // the 33rd body entry this pair's parity leaves unwritten
+        T.colf[kTabPad + (jo ? 0 : 32)] = 0.0;
         T.dx0 = dx;
         T.dy0 = dy;
         if (box) {
@@ -342,9 +347,11 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
             hits &= hits - 1;
             const int4 bx = *reinterpret_cast<const int4*>(sm.box[s]);   // (ia, ib, ja, jb)
             if (pr + 3 < bx.x || pr > bx.y || pc + 3 < bx.z || pc > bx.w) continue;
-            const double* te = &sm.tab[s].rowf[kTabPad + pr - bx.x];  // pr - ia in [-3, 31]: inside the padded table
-            const double* tf = &sm.tab[s].colf[kTabPad + pc - bx.z];
-            const double ex[4] = {te[0], te[1], te[2], te[3]}, fy[4] = {tf[0], tf[1], tf[2], tf[3]};
+            // pr - (ia & ~1) in [-2, 32], even: inside the padded table, 16-byte aligned
+            const double2* te = reinterpret_cast<const double2*>(&sm.tab[s].rowf[kTabPad + pr - (bx.x & ~1)]);
+            const double2* tf = reinterpret_cast<const double2*>(&sm.tab[s].colf[kTabPad + pc - (bx.z & ~1)]);
+            const double2 e01 = te[0], e23 = te[1], f01 = tf[0], f23 = tf[1];
+            const double ex[4] = {e01.x, e01.y, e23.x, e23.y}, fy[4] = {f01.x, f01.y, f23.x, f23.y};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -409,10 +416,10 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
             __syncwarp();
         }
         const int ia = rec.box & 63, ib = (rec.box >> 6) & 63, ja = (rec.box >> 12) & 63, jb = (rec.box >> 18) & 63;
-        const double fy = T.colf[kTabPad + lane];                // f ey of this lane's column, 0 past the box
+        const double fy = T.colf[kTabPad + (ja & 1) + lane];     // f ey of this lane's column, 0 past the box
         const double dyl = T.dy0 + (double)lane;
         const double* col = &sm.rho[ia][min(ja + lane, kTile - 1)];
-        const double* rf = &T.rowf[kTabPad];
+        const double* rf = &T.rowf[kTabPad + (ia & 1)];
         const double* rd = sm.rowd[keep ? s : warp];
         double a0 = 0.0, a1 = 0.0;
         const int nr = ib - ia + 1;

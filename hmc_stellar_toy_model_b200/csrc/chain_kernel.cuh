@@ -23,6 +23,7 @@
 namespace srhmc {
 
 constexpr int kChainCS = 32;  // column stride of a chain image in shared memory
+constexpr int kChainTabPad = 16;  // bytes of padding after each chain's row table (bank staggering, see chain_kernel)
 
 struct ChainState {
     double f, x, y, pf, px, py;  // q, p
@@ -551,11 +552,15 @@ __global__ void __maxnreg__(MAXREG) chain_kernel(const __grid_constant__ FieldPa
     // per-chain image stride padded by LPC elements: the GPW chains of a warp then sit on disjoint shared-memory banks
     const size_t img_elems = (size_t)R * kChainCS + chain_pad<DT>(LPC);
     constexpr size_t kRowTab = sizeof(double2) + (sizeof(PT) == 4 ? sizeof(float2) : 0);   // per image row and chain
-    const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + (size_t)R * kRowTab);
+    // row tables of the GPW chains of a warp: 16 bytes of padding per chain, so that entry i of chain g sits 4 (g + i) banks
+    // into shared memory and the warp's 8 distinct 16-byte entries of a row fill one 128-byte wavefront (unpadded, the
+    // 512-byte table stride put all eight on the same four banks: an 8-way conflict on every row-table load and store)
+    const size_t tab_bytes = (size_t)R * kRowTab + kChainTabPad;
+    const size_t warp_bytes = (size_t)GPW * (img_elems * sizeof(DT) + tab_bytes);
     double2* ltab = reinterpret_cast<double2*>(smem_raw);
     unsigned char* wbase = smem_raw + kLogTableSize * sizeof(double2) + (size_t)warp * warp_bytes;
     DT* sD = reinterpret_cast<DT*>(wbase) + (size_t)grp * img_elems;
-    double2* rt = reinterpret_cast<double2*>(wbase + (size_t)GPW * img_elems * sizeof(DT) + (size_t)grp * R * kRowTab);
+    double2* rt = reinterpret_cast<double2*>(wbase + (size_t)GPW * img_elems * sizeof(DT) + (size_t)grp * tab_bytes);
     const double h = A.dt / 2.0;
     for (int i = threadIdx.x; i < kLogTableSize; i += blockDim.x) ltab[i] = A.log_table[i];
     __syncthreads();

@@ -36,7 +36,7 @@ bool use_column_window(const FieldParams& P) {
 size_t chain_smem_bytes(const FieldParams& P, int lpc, int nw, size_t elem, bool f32 = false) {
     const size_t gpw = 32 / lpc;
     const size_t rowtab = sizeof(double2) + (f32 ? sizeof(float2) : 0);
-    const size_t per_warp = gpw * (((size_t)P.R * kChainCS + lpc) * elem + (size_t)P.R * rowtab);
+    const size_t per_warp = gpw * (((size_t)P.R * kChainCS + lpc) * elem + (size_t)P.R * rowtab + kChainTabPad);
     return kLogTableSize * sizeof(double2) + (size_t)nw * per_warp;
 }
 
