@@ -590,7 +590,9 @@ def tiled_parity_check(env, stream):
         eng = bf.BigFieldRHMC([strip], bf.PeerComm([strip], env.dist))
         b = eng.run(niter, seed=5, **run)
         qb = strip.get_stars()[0]
-        mine = qa[np.searchsorted(ids_all, strip.ids)]
+        back = np.empty(int(ids_all.max()) + 1 if len(ids_all) else 0, dtype=np.int64)
+        back[ids_all] = np.arange(len(ids_all))
+        mine = qa[back[strip.ids]]
         if not np.array_equal(a["A_chain"], b["A_chain"]):
             msg = "accept decisions differ: untiled %s tiled %s" % (a["A_chain"].tolist(), b["A_chain"].tolist())
         elif not a["A_chain"].any():

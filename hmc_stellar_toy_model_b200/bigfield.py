@@ -149,6 +149,13 @@ class BigFieldStrip:
         """Take the stars of the global list [N,3] (f, x, y) whose row coordinate falls in this strip."""
         q_global = np.asarray(q_global, dtype=np.float64).reshape(-1, 3)
         mine = np.nonzero(owner_of(q_global[:, 1], self.rows, self.world) == self.rank)[0].astype(np.int64)
+        # stars are stored in 64x64-tile order (row-major over the tiles, stable inside a tile): consecutive warps of the
+        # star-centric gradient kernel then read neighbouring patches (DRAM pages and L2 lines are shared instead of being
+        # opened once per 200-byte row segment).  `ids` carries the permutation: every per-star array of the API is in this order.
+        if len(mine) > 1:
+            ti = np.floor(q_global[mine, 1]).astype(np.int64) // 64
+            tj = np.floor(q_global[mine, 2]).astype(np.int64) // 64
+            mine = mine[np.argsort(ti * (self.cols // 64 + 1) + tj, kind="stable")]
         q = np.ascontiguousarray(q_global[mine])
         check(self._lib.srhmc_big_set_stars(self._h, _capi.dptr(q), mine.ctypes.data_as(C.POINTER(C.c_int64)), len(mine)))
         self.n, self.ids = len(mine), mine

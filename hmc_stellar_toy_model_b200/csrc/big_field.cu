@@ -108,6 +108,7 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* ticket, bool* fl
 }  // namespace
 
 #include "big_tile.cuh"
+#include "big_star.cuh"
 
 namespace {
 
@@ -938,6 +939,8 @@ struct srhmc_big {
     CUtensorMap tmapD32{};
     bool tma = false;          // a tensor map over the data window exists: the tile kernels load their tile by TMA
     bool tile2 = false;        // persistent variant (big_tile2_kernel, SRHMC_TILE_V2=1) instead of one CTA per tile
+    int star_mode = -1;        // gradient-only FP64 evaluations by big_star_kernel: -1 = when the tile lists are short (sparse
+                               // field), 0 = never, 1 = always (SRHMC_BIG_STAR)
     CUtensorMap tmapD{};
     int world = 1, rank = 0;
     bool have_data = false;
@@ -1031,6 +1034,7 @@ int srhmc_big_create(const srhmc_big_config* cfg, srhmc_big** out) {
     // Path of the EVAL phases: the fused tile kernel needs enough tiles to fill the GPU; small dense fields keep the
     // star-parallel scatter/gather kernels.  SRHMC_BIG_PATH=tile|scatter overrides (read when the context is created).
     b->use_tiles = ntiles >= 2 * (size_t)b->sm_count;
+    if (const char* e = std::getenv("SRHMC_BIG_STAR")) b->star_mode = std::atoi(e) > 0 ? 1 : 0;
     if (const char* e = std::getenv("SRHMC_BIG_PATH")) {
         if (!std::strcmp(e, "tile")) b->use_tiles = true;
         else if (!std::strcmp(e, "scatter")) b->use_tiles = false;
@@ -1511,6 +1515,19 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                         big_tile2_kernel<false><<<grid2, kTileThreads, sizeof(Tile2Smem), st>>>(P, S, b->tmapD, b->ntx, ntiles, b->tcnt.as<int>(),
                             b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(), b->tickets.as<unsigned int>() + 1,
                             b->scalars.as<double>(), cnt);
+                } else if (!want_V && n > 0 && P.rad <= 15 &&
+                           (b->star_mode == 1 || (b->star_mode < 0 && 2.0 * n <= 3.0 * ntiles))) {
+                    // very sparse field (mean tile list below ~1.5 records): one warp per owned star, neighbours from the tile lists
+                    // (big_star.cuh: only the patches are read, not every pixel); the lists are
+                    // consumed here, so their counters are re-zeroed by a memset node instead of by the tile CTAs
+                    const int sgrid = std::max(1, std::min((n + kStarWarps - 1) / kStarWarps, 64 * b->sm_count));
+                    if (P.rad <= 12)
+                        big_star_kernel<25><<<sgrid, 32 * kStarWarps, 0, st>>>(P, n, b->q.as<double>(), b->D.as<double>(), b->ntx,
+                                                                               b->tcnt.as<int>(), b->tlist.as<PairRec>(), b->gpart.as<double>(), cnt);
+                    else
+                        big_star_kernel<31><<<sgrid, 32 * kStarWarps, 0, st>>>(P, n, b->q.as<double>(), b->D.as<double>(), b->ntx,
+                                                                               b->tcnt.as<int>(), b->tlist.as<PairRec>(), b->gpart.as<double>(), cnt);
+                    BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)ntiles * 4, st));
                 } else if (want_V)
                     big_tile_kernel<1><<<ntiles, kTileThreads, sizeof(TileSmem), st>>>(P, S, b->ntx, b->D.as<double>(), b->tcnt.as<int>(),
                         b->tlist.as<PairRec>(), b->gpart.as<double>(), b->vpart.as<double>(),

@@ -165,7 +165,7 @@ def _grad_close(a, b, tol):
 def test_bigfield_eval_matches_reference_values(world, path, monkeypatch):
     """204 stars on 64x64 (golden from the reference): V and dV/dq through the scatter / pixel / gather kernels,
     untiled and tiled into 2 strips on one device."""
-    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
+    _set_path(monkeypatch, path)  # EVAL through the star-parallel kernels, the fused tile kernel or the star-centric kernel
     g = golden("field_eval_204")
     S = setup_from(g)
     eng = _engine(S, g["q"], world=world, halo=14)
@@ -181,11 +181,11 @@ def test_bigfield_eval_matches_reference_values(world, path, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("path", ["scatter", "tile"])
+@pytest.mark.parametrize("path", ["scatter", "tile", "star"])
 def test_bigfield_steps_match_cta_kernel(world, path, monkeypatch):
     """Three leapfrog steps of the 204-star field: same q, p as the CTA-resident kernel (which is parity-checked
     against the reference), including the field-wide stop rule of the fixed-point loops via the two-phase scheme."""
-    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
+    _set_path(monkeypatch, path)  # EVAL through the star-parallel kernels, the fused tile kernel or the star-centric kernel
     from test_gpu_parity import make_ctx
 
     g = golden("field_eval_204")
@@ -211,11 +211,11 @@ def test_bigfield_steps_match_cta_kernel(world, path, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1])
-@pytest.mark.parametrize("path", ["scatter", "tile"])
+@pytest.mark.parametrize("path", ["scatter", "tile", "star"])
 def test_bigfield_chain_matches_reference_chain(world, path, monkeypatch):
     """RHMC-big-sim3-like chain (100 stars, prior, g_ff2 schedule) recorded from the reference: accept decisions and
     energies from the large-field engine with the reference's draws injected."""
-    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
+    _set_path(monkeypatch, path)  # EVAL through the star-parallel kernels, the fused tile kernel or the star-centric kernel
     g = golden("chain_multi100")
     S = setup_from(g)
     q0 = so.format_q(S, g["q_model"])
@@ -229,11 +229,11 @@ def test_bigfield_chain_matches_reference_chain(world, path, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["scatter", "tile"])
+@pytest.mark.parametrize("path", ["scatter", "tile", "star"])
 def test_bigfield_philox_chain_tiled_equals_untiled(path, monkeypatch):
     """Device-RNG chain on a 256x96 field with 700 stars: a 4-strip tiling reproduces the untiled run (same accept
     decisions, energies to 1e-10) because the draws are keyed by global star id."""
-    monkeypatch.setenv("SRHMC_BIG_PATH", path)  # EVAL through the star-parallel kernels or the fused tile kernel
+    _set_path(monkeypatch, path)  # EVAL through the star-parallel kernels, the fused tile kernel or the star-centric kernel
     S = so.Setup(num_rows=256, num_cols=96, g_xx=0.05, g_ff=4.0, g_ff2=4.0, use_prior=True, alpha=2.0, V_prior_const=1.0)
     rng = np.random.RandomState(3)
     n = 700
@@ -291,6 +291,55 @@ def test_bigfield_tile_kernel_equals_star_parallel_kernels(rows, cols, world, mo
     assert _grad_close(res["tile"][1], res["scatter"][1], 1e-11)
     assert res["tile"][0] == res["tile2"][0] and np.array_equal(res["tile"][1], res["tile2"][1])
 
+
+
+def _set_path(monkeypatch, path):
+    """"scatter" | "tile" | "star": the star-centric gradient kernel rides on the tile path's lists (SRHMC_BIG_STAR forces it
+    on for fields the automatic rule would hand to the tile kernel, e.g. 204 stars in one tile -> the long-list code path)."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", "tile" if path == "star" else path)
+    monkeypatch.setenv("SRHMC_BIG_STAR", "1" if path == "star" else "0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,n,world", [(200, 330, 900, 1), (333, 321, 900, 1), (333, 321, 900, 3), (640, 700, 700, 1),
+                                               (640, 700, 700, 2)])
+def test_bigfield_star_kernel_equals_tile_kernel(rows, cols, n, world, monkeypatch):
+    """Gradient-only evaluation by the star-centric kernel (one warp per star, neighbours from the tile lists) against the
+    fused tile kernel: clipped patches at edges and corners, odd column counts, long lists (900 stars on 200x330: ~70 records
+    per tile -> the re-scanning path) and short ones (700 stars on 640x700: the register-cached path), untiled and tiled with
+    ghosts from the neighbouring strips.  dV/dq to 1e-12 of the per-coordinate scale, and bit-identical run to run."""
+    S, D, q0 = _synthetic_field(rows, cols, n, 5)
+    res = {}
+    for path in ("tile", "star", "star2"):
+        _set_path(monkeypatch, path[:4])
+        eng = _engine(S, q0.ravel(), world=world, D=D, halo=20)
+        eng.evaluate(want_V=False, g_ff2=4.0)
+        res[path] = eng.stars(n)[2]
+        if path == "star":
+            assert all(s.launch_count > 0 for s in eng.strips)
+    assert np.all(np.isfinite(res["star"]))
+    a, b = res["star"].reshape(-1, 3), res["tile"].reshape(-1, 3)
+    err = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b), axis=0, keepdims=True))))
+    assert err < 1e-11, err   # different summation order (whole patch at once vs per-tile partial sums): rounding only
+    assert np.array_equal(res["star"], res["star2"])
+
+
+@pytest.mark.gpu
+def test_bigfield_star_kernel_spot_check_against_patch_oracle(monkeypatch):
+    """The star-centric kernel chosen by the automatic rule (very sparse 1600x1600 field: 400 stars on 625 tiles) against the
+    NumPy patch oracle, and the same field with 3000 stars (tile kernel by the rule, star kernel forced)."""
+    monkeypatch.delenv("SRHMC_BIG_PATH", raising=False)
+    for n, force in ((400, None), (3000, "1")):
+        if force:
+            monkeypatch.setenv("SRHMC_BIG_STAR", force)
+        else:
+            monkeypatch.delenv("SRHMC_BIG_STAR", raising=False)
+        S, D, q0 = _synthetic_field(1600, 1600, n, 21)
+        eng = _engine(S, q0.ravel(), D=D, halo=20)
+        eng.evaluate(want_V=False, g_ff2=4.0)
+        grad = eng.stars(n)[2]
+        _, gref = so.patch_eval(S, D, q0, 12)
+        assert _grad_close(grad, gref, 1e-10)
 
 @pytest.mark.gpu
 def test_bigfield_tile_kernel_dense_list_chunks_and_auto_path(monkeypatch):
