@@ -377,23 +377,37 @@ __global__ void __launch_bounds__(kTileThreads, SRHMC_TILE_MIN_CTAS) big_tile_ke
     if (use_tma) mbar_wait(&sm.mbar, 0u);   // initialised by thread 0 before the barrier that follows the list sort
     else cp_async_wait_all();               // this thread's own copies (it reads nothing else here)
     double v = 0.0;
+    if (!WANT_V && vr == kTile && vc == kTile) {
+        // tile inside the image, gradient only: no per-pixel edge selects (a third of this phase's instructions)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int li = pr + a, gi = r0 + li;
-        const bool own = WANT_V && li < vr && gi >= P.own_lo && gi < P.own_hi;
-        const double2 d0 = *reinterpret_cast<const double2*>(&sm.rho[li][pc]);
-        const double2 d1 = *reinterpret_cast<const double2*>(&sm.rho[li][pc + 2]);
-        const double d[4] = {d0.x, d0.y, d1.x, d1.y};
-        double rho[4], il[4];
-        rcp4(lam[a], il);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const bool in = li < vr && pc + b < vc;
-            rho[b] = in ? fma(d[b], il[b], -1.0) : 0.0;
-            if (WANT_V && own && pc + b < vc) v += lam[a][b] - d[b] * (lam[a][b] >= 2.3e-308 ? log_pos(lam[a][b], sm.ltab) : CUDART_NAN);  // ln of a non-positive model is NaN, as in NumPy
+        for (int a = 0; a < 4; ++a) {
+            const int li = pr + a;
+            const double2 d0 = *reinterpret_cast<const double2*>(&sm.rho[li][pc]);
+            const double2 d1 = *reinterpret_cast<const double2*>(&sm.rho[li][pc + 2]);
+            double il[4];
+            rcp4(lam[a], il);
+            *reinterpret_cast<double2*>(&sm.rho[li][pc]) = make_double2(fma(d0.x, il[0], -1.0), fma(d0.y, il[1], -1.0));
+            *reinterpret_cast<double2*>(&sm.rho[li][pc + 2]) = make_double2(fma(d1.x, il[2], -1.0), fma(d1.y, il[3], -1.0));
         }
-        *reinterpret_cast<double2*>(&sm.rho[li][pc]) = make_double2(rho[0], rho[1]);
-        *reinterpret_cast<double2*>(&sm.rho[li][pc + 2]) = make_double2(rho[2], rho[3]);
+    } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int li = pr + a, gi = r0 + li;
+            const bool own = WANT_V && li < vr && gi >= P.own_lo && gi < P.own_hi;
+            const double2 d0 = *reinterpret_cast<const double2*>(&sm.rho[li][pc]);
+            const double2 d1 = *reinterpret_cast<const double2*>(&sm.rho[li][pc + 2]);
+            const double d[4] = {d0.x, d0.y, d1.x, d1.y};
+            double rho[4], il[4];
+            rcp4(lam[a], il);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const bool in = li < vr && pc + b < vc;
+                rho[b] = in ? fma(d[b], il[b], -1.0) : 0.0;
+                if (WANT_V && own && pc + b < vc) v += lam[a][b] - d[b] * (lam[a][b] >= 2.3e-308 ? log_pos(lam[a][b], sm.ltab) : CUDART_NAN);  // ln of a non-positive model is NaN, as in NumPy
+            }
+            *reinterpret_cast<double2*>(&sm.rho[li][pc]) = make_double2(rho[0], rho[1]);
+            *reinterpret_cast<double2*>(&sm.rho[li][pc + 2]) = make_double2(rho[2], rho[3]);
+        }
     }
     if (WANT_V) {
         double a1[1] = {v};
