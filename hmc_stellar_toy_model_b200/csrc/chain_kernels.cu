@@ -200,7 +200,8 @@ int chain_kernel_launch(const FieldParams& P, const LaunchArgs& A_in, const Chai
     const int n_range = (A.field_end > 0 ? A.field_end : A.n_fields) - A.field_begin;
     const long long blocks = ((long long)n_range + chains_per_block - 1) / chains_per_block;
     const bool u16 = A.D_int != nullptr && A.D_int_bytes == 2;
-    // 4 lanes per chain: 218 registers -> 8 resident single-warp blocks per SM (2 per scheduler); residency comes from the
+    // 4 lanes per chain: 240 of 255 registers -> 8 resident single-warp blocks per SM (2 per scheduler: the register file is
+    // partitioned per scheduler, a third warp would need <= 168 registers and measured slower); residency comes from the
     // occupancy query in chain_kernel_configure.  Register-capped 8-lane builds were measured earlier and are slower
     // (128 registers / 16 warps 1057 M star-steps/s, 112 / 18 warps 892 against 1104 at 168 / 12).
     const bool f32 = u16 && A.pix_f32;

@@ -1,5 +1,5 @@
 // FP64 exp / log tuned for the pixel loops: no special-case branches, coefficients read straight from the
-// constant bank (no per-use register moves), log through a 128-entry reciprocal table.
+// constant bank (no per-use register moves), log through a 64-entry reciprocal table.
 //
 // exp_neg(x), x <= 0:   n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), degree-12 Taylor polynomial on
 //                       |r| <= ln2/2 (truncation 1.7e-16), result scaled by 2^n through the exponent field.
