@@ -19,6 +19,8 @@ other BASELINE configs under "workloads":
                   kernels; strong scaling.  At N > 1 a small tiled chain is first checked against the untiled run through
                   the same IPC path ("parity_check").
   workloads.c5_weak   the same engine with an 8192 x 8192 strip PER GPU (N > 1 only).
+  workloads.c5_perstar  configs[4] with the per-star stop rule of the implicit loops (fixed_point_mode = 1: not the reference's
+                      field-wide rule; no iteration count crosses the GPUs, three kernels and one exchange per leapfrog step).
 
 Per record: `value` (inputs resident, device time from CUDA events on the launching stream), `e2e` (public API with
 pinned HOST buffers, copies inside the timed region), `roofline`, `clocks`, `gpu_launches`, and at N = 1 `cpu_baseline`
@@ -611,7 +613,7 @@ def tiled_parity_check(env, stream):
 
 
 def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity, precision=64,
-                   replicas=False, label="c5_tiled_field", dt=None):
+                   replicas=False, label="c5_tiled_field", dt=None, fixed_point_mode=0):
     """C5: ONE large field, row strips over the ranks (strong), or one rows x cols strip per rank (weak).
     replicas=True (C3): every rank runs its own copy of the whole field, no communication."""
     torch = env.torch
@@ -642,7 +644,7 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
         comm = bf.TorchDistComm(env.dist)   # NCCL collectives issued by the caller between the phases (eager launches)
     else:
         comm = bf.PeerComm([strip], env.dist)  # the library's own exchange kernels over NVLink peer memory; graph replay
-    eng = bf.BigFieldRHMC([strip], comm)
+    eng = bf.BigFieldRHMC([strip], comm, fixed_point_mode=fixed_point_mode)
 
     # data: generated on the device (srhmc_big_mock_data: tile-kernel render + counter-based Philox Poisson; halo rows of
     # neighbouring strips agree bit for bit), read back once into pinned memory for the e2e arm
@@ -693,7 +695,8 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
         # the data strip read once per gradient + star state (FP32 build: float pixels for 9 of 10 evaluations)
         bytes_per_unit = (8.0 if precision == 64 else 4.0 + 4.0 / run["nsteps"]) * A + 96.0
         gbs = bytes_per_unit * units / world / (ms_per_step * 1e-3) / 1e9
-        name = "%s_%dx%d_%dstars%s" % (label, rows_g, cols, nst_g, "" if precision == 64 else "_fp32")
+        name = "%s_%dx%d_%dstars%s%s" % (label, rows_g, cols, nst_g, "" if precision == 64 else "_fp32",
+                                         "_perstar" if fixed_point_mode else "")
         n_own = strip.n
         rec = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -702,6 +705,10 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
             "config": {"workload": name, "rows": rows_g, "cols": cols, "stars": nst_g, "niter": niter,
                        "nsteps": run["nsteps"], "dt": run["dt"], "patch_radius": rad, "halo_rows": halo,
                        "rng": "device Philox4x32-10", "data_source": "device-side mock data (srhmc_big_mock_data)",
+                       "fixed_point_mode": ("1: every star's implicit loops stop at the star's own convergence (NOT the reference's "
+                                            "field-wide stop rule: per-step results within delta of it); three kernels and one "
+                                            "exchange per leapfrog step" if fixed_point_mode else
+                                            "0: the reference's field-wide stop rule, bit for bit"),
                        "l2": "every gradient streams this rank's %.0f MB data window from HBM (larger than the 126 MB L2 "
                              "when above it; no flush between launches)" % (pin_D.nbytes / 1e6),
                        "parallelism": ("replicas only: every one of the %d GPU(s) runs its own chain on the whole field "
@@ -788,11 +795,12 @@ def run_ours(args):
                             device_data_seed=4, parallelism="%d independent fields split over %d GPU(s) (contiguous "
                             "blocks), no communication" % (per * world, world))
 
-    def c5(weak, precision=None):
+    def c5(weak, precision=None, fixed_point_mode=0):
         return bench_bigfield(env, rows=args.rows, cols=args.cols, nstars=args.stars, weak=weak, niter=args.c5_niter,
                               steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
-                              comm_kind=args.comm, with_parity=not weak and precision is None,
-                              precision=args.precision if precision is None else precision)
+                              comm_kind=args.comm, with_parity=not weak and precision is None and not fixed_point_mode,
+                              precision=args.precision if precision is None else precision,
+                              fixed_point_mode=fixed_point_mode or args.fixed_point_mode)
 
     def c3():
         # BASELINE configs[2]: "RHMC-big-sim2/3/4 crowded field: hundreds to thousands of stars in one large image with the
@@ -826,6 +834,7 @@ def run_ours(args):
         subs["c3"] = guarded(env, "c3", c3)
         subs["c4"] = guarded(env, "c4", c4)
         subs["c5"] = guarded(env, "c5", lambda: c5(False))
+        subs["c5_perstar"] = guarded(env, "c5_perstar", lambda: c5(False, fixed_point_mode=1))
         if world > 1:
             subs["c5_weak"] = guarded(env, "c5_weak", lambda: c5(True))
         else:
@@ -888,6 +897,8 @@ def main():
     ap.add_argument("--cols", type=int, default=8192)
     ap.add_argument("--stars", type=float, default=100000, help="c5: stars (per GPU with --weak); 1.49e-3 per pixel")
     ap.add_argument("--weak", action="store_true", help="c5 alone: grow the field with the GPU count")
+    ap.add_argument("--fixed-point-mode", type=int, default=0, choices=[0, 1],
+                    help="c5: 0 = the reference's field-wide stop rule (default), 1 = per-star stop rule")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="c5 on several GPUs: the library's own peer-memory exchange kernels, or NCCL through torch.distributed")
     ap.add_argument("--chains-per-mag", type=int, default=1000)

@@ -136,7 +136,7 @@ class BigStep(C.Structure):
     """struct srhmc_big_step"""
 
     _fields_ = [("dt", C.c_double), ("delta", C.c_double), ("g_ff2", C.c_double), ("counter_max", C.c_int32),
-                ("f_pos", C.c_int32), ("iteration", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
+                ("f_pos", C.c_int32), ("iteration", C.c_int32), ("fixed_point_mode", C.c_int32), ("seed", C.c_uint64)]
 
 
 class BigBuffers(C.Structure):

@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import check_big as check
 
 PHASE = dict(PACK=0, EVAL=1, EVAL_V=2, KICK1=3, PFIX_QFIX=4, QFIX_KICK=5, KICK2=6, MOMENTUM=7, ENERGY=8, RECORD_E0=9,
-             ACCEPT=10, RESET_ITER=11, EVAL_KICK2=12, EVAL_V_KICK2=13, EVAL_KICK2_KICK1=14)
+             ACCEPT=10, RESET_ITER=11, EVAL_KICK2=12, EVAL_V_KICK2=13, EVAL_KICK2_KICK1=14, PS_ADVANCE=15, EVAL_PS_ADVANCE=16)
 
 
 # ----------------------------------------------------------------------------------------------- host-side geometry
@@ -337,14 +337,21 @@ class BigFieldRHMC:
     """RHMC on one large field.  `strips` is the list of strips hosted by THIS process: one for a normal run (with
     NoComm or TorchDistComm), all of them for the single-GPU emulation of a tiling (LocalComm)."""
 
-    def __init__(self, strips, comm=None):
+    def __init__(self, strips, comm=None, fixed_point_mode=0):
+        """fixed_point_mode: 0 = the reference's stop rule for the two implicit loops of RHMC_single_step (iterate until the
+        slowest star of the whole field has converged, sampler_RHMC.py:531-545: parity with the reference, two max
+        all-reduces per leapfrog step when tiled); 1 = every star stops at its own convergence (what
+        srhmc_config.fixed_point_mode = 1 is for the CTA kernels): per-step results within `delta` of mode 0, three kernels
+        and one exchange per leapfrog step."""
         self.strips = list(strips)
         self.comm = comm if comm is not None else NoComm()
         self.multi = self.strips[0].world > 1
+        self.fixed_point_mode = int(fixed_point_mode)
 
     def _step_struct(self, dt, delta, g_ff2, counter_max, f_pos, iteration, seed):
         return _capi.BigStep(dt=float(dt), delta=float(delta), g_ff2=float(g_ff2), counter_max=int(counter_max),
-                             f_pos=int(bool(f_pos)), iteration=int(iteration), reserved=0, seed=int(seed))
+                             f_pos=int(bool(f_pos)), iteration=int(iteration),
+                             fixed_point_mode=int(getattr(self, "fixed_point_mode", 0)), seed=int(seed))
 
     def _all(self, name, st):
         for s in self.strips:
@@ -374,10 +381,19 @@ class BigFieldRHMC:
             self._all("PACK", st)
             self.comm.gather_ghosts(self.strips)
 
+    def _ghosts(self, st):
+        if self.multi:
+            self._all("PACK", st)
+            self.comm.gather_ghosts(self.strips)
+
     def leapfrog(self, st, want_V):
         """One RHMC_single_step (sampler_RHMC.py:522-566); needs the gradient at the current q."""
-        self._all("KICK1", st)
-        self._advance(st)
+        if st.fixed_point_mode:
+            self._all("PS_ADVANCE", st)
+            self._ghosts(st)
+        else:
+            self._all("KICK1", st)
+            self._advance(st)
         self._all("EVAL_V_KICK2" if want_V else "EVAL_KICK2", st)
 
     def trajectory(self, st, nsteps, want_V_last):
@@ -385,6 +401,18 @@ class BigFieldRHMC:
         gradient, so inside the trajectory they ride in one fused phase behind the evaluation (EVAL_KICK2_KICK1):
         four kernels per step on one GPU."""
         if nsteps <= 0:
+            return
+        if st.fixed_point_mode:
+            # per-star stop rule (fixed_point_mode = 1): no iteration count couples the stars, so everything between two
+            # evaluations is one kernel -- three kernels and ONE exchange (the ghost lists) per leapfrog step on N ranks
+            self._all("PS_ADVANCE", st)
+            self._ghosts(st)
+            for t in range(nsteps):
+                if t < nsteps - 1:
+                    self._all("EVAL_PS_ADVANCE", st)
+                    self._ghosts(st)
+                else:
+                    self._all("EVAL_V_KICK2" if want_V_last else "EVAL_KICK2", st)
             return
         self._all("KICK1", st)
         for t in range(nsteps):
@@ -454,7 +482,7 @@ class BigFieldRHMC:
             # one captured iteration serves every later run with the same launch parameters (the chain row and the RNG
             # counter come from the device-side iteration counter; the buffers are owned by the strips and never move)
             key = (int(nsteps), float(dt), float(delta), float(g_ff2), int(counter_max), bool(f_pos), int(seed), L,
-                   tuple(s.n for s in self.strips))
+                   tuple(s.n for s in self.strips), int(getattr(self, "fixed_point_mode", 0)))
             if normals is not None or lnu is not None:
                 key = None  # injected draws live in buffers that are re-allocated per run: always capture afresh
             if key is None or getattr(self, "_graph_key", None) != key:

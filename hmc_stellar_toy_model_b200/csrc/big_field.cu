@@ -360,6 +360,7 @@ __device__ __forceinline__ void peer_epoch_advance(const PeerX& X) {
 struct BigStep {
     double h, delta, g_ff2;
     int counter_max;
+    int per_star;   // srhmc_big_step.fixed_point_mode = 1: every star's fixed points stop at the star's own convergence
 };
 
 __device__ __forceinline__ double dphi_f(const BigParams& P, const Metric& m, double gpix_f, double f) {
@@ -394,13 +395,13 @@ __global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, cons
         local_max = max(local_max, c);
     }
     if (local_max) atomicMax(cnt, local_max);
-    if (X.prod) peer_max_epilogue(X, cnt);
+    if (X.prod && !S.per_star) peer_max_epilogue(X, cnt);
 }
 
 // p fixed point phase B (continue to the global count), then (3) q fixed point phase A
 __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, double* a1, double* a2,
                                      const int* cnt_p, int* cnt_q, const PeerX X) {
-    const int target = X.on ? peer_max_in_kernel(X, *cnt_p) : *cnt_p;
+    const int target = S.per_star ? 0 : (X.on ? peer_max_in_kernel(X, *cnt_p) : *cnt_p);
     int local_max = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         double pf = p[3 * k];
@@ -434,8 +435,8 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
         reinterpret_cast<int*>(a2 + 3 * (size_t)n)[k] = c;
     }
     if (local_max) atomicMax(cnt_q, local_max);
-    if (X.on) peer_epoch_advance(X);
-    if (X.prod) peer_max_epilogue(X, cnt_q);
+    if (X.on && !S.per_star) peer_epoch_advance(X);
+    if (X.prod && !S.per_star) peer_max_epilogue(X, cnt_q);
 }
 
 // q fixed point phase B, then (4) p -= h dtau/dq at the new q
@@ -443,7 +444,7 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
                                      const double* a2, const int* cnt_q, int ntx, int* tcnt, PairRec* tlist, int* err, const PeerX X,
                                      int2* pack_counts, double lo_edge, double hi_edge) {
-    const int target = X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q;
+    const int target = S.per_star ? 0 : (X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
         const double bf = a2[3 * k], bx = a2[3 * k + 1], by = a2[3 * k + 2];
@@ -465,7 +466,7 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
             if (qx >= hi_edge) atomicAdd(&pack_counts[k >> 10].y, 1);
         }
     }
-    if (X.on) peer_epoch_advance(X);
+    if (X.on && !S.per_star) peer_epoch_advance(X);
 }
 
 // (5) p -= h dphi/dq at the new q; (6) reflections
@@ -480,6 +481,80 @@ __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, cons
         if ((x < 0.0) || (x > P.Rg - 1.0)) px *= -1.0;
         if ((y < 0.0) || (y > P.C - 1.0)) py *= -1.0;
         p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
+    }
+}
+
+// Per-star stop rule (srhmc_big_step.fixed_point_mode = 1): nothing in steps (1)-(4) of a leapfrog step couples the stars any
+// more, so everything between two gradient evaluations is ONE per-star kernel and no iteration count crosses the GPUs:
+//   [FROM_EVAL: g = sum of the footprint partials, (5) last half kick and (6) reflections of the step that just ended]
+//   (1) p -= h dphi/dq, (2) p fixed point, (3) q fixed point -- each to the star's own convergence --,
+//   (4) p -= h dtau/dq at the new q, pair records of the new position, boundary-star counts for the ghost packing.
+// Same expressions, in the same order, as big_tail_kernel / big_kick1_kernel / big_pfix_qfix_kernel / big_qfix_kick_kernel.
+template <bool FROM_EVAL>
+__global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, double* g, const double* gpart,
+                                   int ntx, int* tcnt, PairRec* tlist, int* err, int2* pack_counts, double lo_edge, double hi_edge) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double sf = q[3 * k], sx = q[3 * k + 1], sy = q[3 * k + 2];
+        double gf, gx, gy;
+        if (FROM_EVAL && gpart) {
+            gsum_star(P, k, sf, sx, sy, gpart, gf, gx, gy);
+            g[3 * k] = gf; g[3 * k + 1] = gx; g[3 * k + 2] = gy;
+        } else {
+            gf = g[3 * k]; gx = g[3 * k + 1]; gy = g[3 * k + 2];
+        }
+        const Metric m0 = metric_of(P.F, sf, S.g_ff2);
+        const double dphi = dphi_f(P, m0, gf, sf);
+        double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
+        if (FROM_EVAL) {
+            pf = pf - S.h * dphi;
+            px -= S.h * gx;
+            py -= S.h * gy;
+            if (sf < P.F.f_lim) pf *= -1.0;
+            if ((sx < 0.0) || (sx > P.Rg - 1.0)) px *= -1.0;
+            if ((sy < 0.0) || (sy > P.C - 1.0)) py *= -1.0;
+        }
+        // (1), (2)
+        pf = pf - S.h * dphi;
+        px -= S.h * gx;
+        py -= S.h * gy;
+        {
+            const double rho = pf, kap = -m0.dHff / (m0.Hff * m0.Hff);
+            int c = 0;
+            while (c < S.counter_max) {
+                const double pn = rho - S.h * (((pf * pf) * kap) / 2.0);
+                const bool more = fabs(pf - pn) > S.delta;
+                pf = pn;
+                ++c;
+                if (!more) break;
+            }
+        }
+        // (3) q' = sigma + h (p/H(sigma) + p/H(q))
+        const double bf = pf / m0.Hff, bx = px / m0.Hxx, by = py / m0.Hxx;
+        double qf = sf, qx = sx, qy = sy;
+        {
+            int c = 0;
+            while (c < S.counter_max) {
+                const Metric m = metric_of(P.F, qf, S.g_ff2);
+                const double nf = sf + S.h * (bf + pf / m.Hff);
+                const double nx = sx + S.h * (bx + px / m.Hxx);
+                const double ny = sy + S.h * (by + py / m.Hxx);
+                const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
+                qf = nf; qx = nx; qy = ny;
+                ++c;
+                if (!(d > S.delta)) break;
+            }
+        }
+        q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
+        // (4)
+        const Metric m = metric_of(P.F, qf, S.g_ff2);
+        p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+        p[3 * k + 1] = px;
+        p[3 * k + 2] = py;
+        if (tcnt) bin_star(P, ntx, k, qf, qx, qy, true, tcnt, tlist, err);
+        if (pack_counts) {
+            if (qx < lo_edge) atomicAdd(&pack_counts[k >> 10].x, 1);
+            if (qx >= hi_edge) atomicAdd(&pack_counts[k >> 10].y, 1);
+        }
     }
 }
 
@@ -529,7 +604,7 @@ __global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const
         p[3 * k] = pf; p[3 * k + 1] = px; p[3 * k + 2] = py;
     }
     if (NEXT && local_max) atomicMax(cnt, local_max);
-    if (NEXT && X.prod) peer_max_epilogue(X, cnt);
+    if (NEXT && X.prod && !S.per_star) peer_max_epilogue(X, cnt);
 }
 
 // momentum refresh p = z sqrt(H) (sampler_RHMC.py:1021-1022) with device Philox keyed by the GLOBAL star id, or
@@ -1417,6 +1492,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
     const int n = b->n;
     BigStep S;
     S.h = s->dt / 2.0; S.delta = s->delta; S.g_ff2 = s->g_ff2; S.counter_max = s->counter_max;
+    S.per_star = s->fixed_point_mode != 0 ? 1 : 0;
     const int tb = 128, gs = std::max(1, std::min((n + tb - 1) / tb, 4 * b->sm_count));
     const size_t npix = (size_t)P.nrows * P.C;
     const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
@@ -1431,7 +1507,35 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
         X.prod = b->fuse_prod ? 1 : 0;
         X.epoch = b->xepoch.as<unsigned long long>(); X.ticket = b->xticket.as<unsigned int>(); X.err = b->err.as<int>();
     }
+    // per-star stop rule: the whole advance between two evaluations in one kernel (big_perstar_kernel)
+    auto launch_perstar = [&](bool from_eval, const double* gpart_in) -> int {
+        if (b->use_tiles && (b->own_binned || b->ghosts_binned)) {  // records nobody consumed
+            BCU(cudaMemsetAsync(b->tcnt.ptr, 0, (size_t)b->nty * b->ntx * 4, st));
+            b->ghosts_binned = false;
+        }
+        const bool count_here = peer_multi && b->fuse_prod;
+        if (count_here && b->pack_counted) BCU(cudaMemsetAsync(b->packcnt.ptr, 0, b->packcnt.cap, st));
+        const double reach_k = (double)(b->cfg.nrows_halo + P.rad + 1);
+        const double lo_edge_k = (b->rank > 0) ? (double)P.own_lo + reach_k : -1e300;
+        const double hi_edge_k = (b->rank < b->world - 1) ? (double)P.own_hi - reach_k : 1e300;
+        int* tc = b->use_tiles ? b->tcnt.as<int>() : nullptr;
+        PairRec* tl = b->use_tiles ? b->tlist.as<PairRec>() : nullptr;
+        int2* pc = count_here ? b->packcnt.as<int2>() : nullptr;
+        if (from_eval)
+            big_perstar_kernel<true><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart_in,
+                                                        b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k);
+        else
+            big_perstar_kernel<false><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), nullptr,
+                                                         b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k);
+        b->pack_counted = count_here;
+        b->own_binned = b->use_tiles;
+        b->launches += 1;
+        return 0;
+    };
     switch (phase) {
+        case SRHMC_BIG_PS_ADVANCE:
+            if (int rc = launch_perstar(false, nullptr)) return rc;
+            break;
         case SRHMC_BIG_PACK: {
             // boundary lists for the neighbours: everything that can touch their data rows
             const double reach = (double)(b->cfg.nrows_halo + P.rad + 1);
@@ -1475,10 +1579,13 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
         case SRHMC_BIG_EVAL_V:
         case SRHMC_BIG_EVAL_KICK2:
         case SRHMC_BIG_EVAL_V_KICK2:
-        case SRHMC_BIG_EVAL_KICK2_KICK1: {
+        case SRHMC_BIG_EVAL_KICK2_KICK1:
+        case SRHMC_BIG_EVAL_PS_ADVANCE: {
             const int want_V = (phase == SRHMC_BIG_EVAL_V || phase == SRHMC_BIG_EVAL_V_KICK2) ? 1 : 0;
-            // tail: 0 none, 1 the step's last half kick + reflections, 2 also the next step's first kick + p fixed point A
-            const int tail = phase == SRHMC_BIG_EVAL_KICK2_KICK1 ? 2 : ((phase == SRHMC_BIG_EVAL_KICK2 || phase == SRHMC_BIG_EVAL_V_KICK2) ? 1 : 0);
+            // tail: 0 none, 1 the step's last half kick + reflections, 2 also the next step's first kick + p fixed point A,
+            // 3 (per-star stop rule) the step's end and the whole advance of the next step in one kernel
+            const int tail = phase == SRHMC_BIG_EVAL_PS_ADVANCE ? 3 : (phase == SRHMC_BIG_EVAL_KICK2_KICK1 ? 2 :
+                             ((phase == SRHMC_BIG_EVAL_KICK2 || phase == SRHMC_BIG_EVAL_V_KICK2) ? 1 : 0));
             const double* ga = (b->world > 1 && b->rank > 0) ? b->recv.as<double>() + ((size_t)(b->rank - 1) * 2 + 1) * list : nullptr;
             const double* gb = (b->world > 1 && b->rank < b->world - 1) ? b->recv.as<double>() + ((size_t)(b->rank + 1) * 2 + 0) * list : nullptr;
             const double* gpart = nullptr;
@@ -1561,7 +1668,10 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             else if (tail == 2)
                 big_tail_kernel<true><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart,
                                                          b->a1.as<double>(), b->a2.as<double>(), cnt, X);
-            if (tail) b->launches += 1;
+            else if (tail == 3) {
+                if (int rc = launch_perstar(true, gpart)) return rc;
+            }
+            if (tail == 1 || tail == 2) b->launches += 1;
             break;
         }
         case SRHMC_BIG_RESET_ITER:
@@ -1574,7 +1684,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_PFIX_QFIX:
-            if (peer_multi && !b->fuse_max && !b->fuse_prod) {
+            if (peer_multi && !b->fuse_max && !b->fuse_prod && !S.per_star) {
                 big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
                 b->launches += 1;
@@ -1586,7 +1696,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             b->launches += 1;
             break;
         case SRHMC_BIG_QFIX_KICK: {
-            if (peer_multi && !b->fuse_max && !b->fuse_prod) {
+            if (peer_multi && !b->fuse_max && !b->fuse_prod && !S.per_star) {
                 big_xchg_small_kernel<<<1, 32, 0, st>>>(b->peers, b->rank, b->world, 0, 2, cnt, nullptr, nullptr,
                                                         b->xepoch.as<unsigned long long>(), b->err.as<int>());
                 b->launches += 1;

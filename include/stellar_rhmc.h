@@ -336,7 +336,10 @@ typedef enum srhmc_big_phase_id {
     /* fused forms (same arithmetic in the same order, fewer launches): */
     SRHMC_BIG_EVAL_KICK2 = 12,       /* EVAL then KICK2 */
     SRHMC_BIG_EVAL_V_KICK2 = 13,     /* EVAL_V then KICK2 */
-    SRHMC_BIG_EVAL_KICK2_KICK1 = 14  /* EVAL, KICK2 and the KICK1 of the following leapfrog step (same q, same gradient) */
+    SRHMC_BIG_EVAL_KICK2_KICK1 = 14, /* EVAL, KICK2 and the KICK1 of the following leapfrog step (same q, same gradient) */
+    /* per-star stop rule (srhmc_big_step.fixed_point_mode = 1): steps 1-4 of a7 couple no stars, so they are one kernel */
+    SRHMC_BIG_PS_ADVANCE = 15,       /* KICK1, both fixed points to each star's own convergence, p -= h dtau/dq, binning */
+    SRHMC_BIG_EVAL_PS_ADVANCE = 16   /* EVAL, KICK2 and the PS_ADVANCE of the following leapfrog step */
 } srhmc_big_phase_id;
 
 typedef struct srhmc_big_step {
@@ -344,7 +347,10 @@ typedef struct srhmc_big_step {
     int32_t counter_max, f_pos;
     int32_t iteration;       /* Metropolis iteration index (RNG counter, chain row); < 0: use the device-side counter,
                                 which ACCEPT advances -- lets one captured CUDA graph of an iteration be replayed */
-    int32_t reserved;
+    int32_t fixed_point_mode;/* 0: reference stop rule (sampler_RHMC.py:531-545: both implicit loops run until the slowest
+                                star of the WHOLE field has converged; tiled over GPUs that is two max all-reduces per
+                                leapfrog step); 1: per-star early exit, as srhmc_config.fixed_point_mode = 1 (results differ
+                                from the reference by less than `delta` per step; no iteration count crosses the GPUs) */
     uint64_t seed;
 } srhmc_big_step;
 

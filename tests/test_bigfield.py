@@ -130,7 +130,7 @@ def _consts(S):
                 V_prior_const=S.V_prior_const if S.V_prior_const is not None else 0.0)
 
 
-def _engine(S, q, world=1, rad=12, halo=20, D=None):
+def _engine(S, q, world=1, rad=12, halo=20, D=None, fixed_point_mode=0):
     import torch
 
     # one explicit side stream for the engine AND the LocalComm tensor ops (CUDA-graph capture needs a non-default one)
@@ -147,7 +147,7 @@ def _engine(S, q, world=1, rad=12, halo=20, D=None):
         s.set_data(S.D if D is None else D)
         s.set_stars(q.reshape(-1, 3))
         strips.append(s)
-    return bf.BigFieldRHMC(strips, bf.LocalComm() if world > 1 else bf.NoComm())
+    return bf.BigFieldRHMC(strips, bf.LocalComm() if world > 1 else bf.NoComm(), fixed_point_mode=fixed_point_mode)
 
 
 _STREAM = None
@@ -340,6 +340,49 @@ def test_bigfield_star_kernel_spot_check_against_patch_oracle(monkeypatch):
         grad = eng.stars(n)[2]
         _, gref = so.patch_eval(S, D, q0, 12)
         assert _grad_close(grad, gref, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("path", ["scatter", "tile"])
+def test_bigfield_per_star_stop_rule_matches_cta_kernel(world, path, monkeypatch):
+    """fixed_point_mode = 1 (every star's implicit loops stop at its own convergence; one merged per-star kernel between two
+    evaluations, no max all-reduce): three leapfrog steps of the 204-star field against the CTA-resident kernel in the same
+    mode, untiled and as two strips -- and within the fixed-point tolerance of the reference's stop rule."""
+    _set_path(monkeypatch, path)
+    from test_gpu_parity import make_ctx
+
+    g = golden("field_eval_204")
+    S = setup_from(g)
+    ref = {}
+    for mode in (0, 1):
+        with make_ctx(S, max_stars=204, patch_radius=12, fixed_point_mode=mode) as ctx:
+            ctx.set_data(S.D)
+            ref[mode] = ctx.step(g["q"][None], g["p"][None], 3, float(g["dt"]), g_ff2=S.g_ff2)
+    eng = _engine(S, g["q"], world=world, halo=14, fixed_point_mode=1)
+    for s in eng.strips:
+        s.set_momenta(g["p"].reshape(-1, 3)[s.ids])
+    eng.steps(3, float(g["dt"]), g_ff2=S.g_ff2)
+    q, p, _ = eng.stars(204)
+    assert relerr(q.ravel(), ref[1][0][0]) < 1e-10
+    assert _grad_close(p, ref[1][1][0], 1e-8)
+    # the two stop rules differ by what the extra iterations of an already converged star change: far below delta = 1e-6
+    assert 0 < relerr(ref[1][0][0], ref[0][0][0]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_bigfield_per_star_chain_tiled_equals_untiled(monkeypatch):
+    """Device-RNG chain in the per-star mode: a 4-strip tiling reproduces the untiled run (decisions, energies to 1e-10)."""
+    _set_path(monkeypatch, "tile")
+    S, D, q0 = _synthetic_field(256, 96, 700, 3)
+    outs = []
+    for world in (1, 4):
+        eng = _engine(S, q0.ravel(), world=world, D=D, halo=20, fixed_point_mode=1)
+        outs.append((eng.run(6, 5, 2e-2, f_pos=True, g_ff2=4.0, seed=11), eng.stars(700)[0]))
+    a, b = outs
+    assert np.array_equal(a[0]["A_chain"], b[0]["A_chain"]) and 0 < a[0]["A_chain"].sum()
+    assert relerr(b[0]["E_chain"], a[0]["E_chain"]) < 1e-10
+    assert relerr(b[1], a[1]) < 1e-9
 
 @pytest.mark.gpu
 def test_bigfield_tile_kernel_dense_list_chunks_and_auto_path(monkeypatch):
