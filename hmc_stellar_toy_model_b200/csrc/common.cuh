@@ -158,6 +158,53 @@ __device__ __forceinline__ double rcp_fast(double a) {
 }
 __device__ __forceinline__ float rcp_fast(float a) { return __frcp_rn(a); }
 
+// Division-free form of the reference metric (sampler_RHMC.py:229-292) for the per-star scalar code of the leapfrog step
+// (the FP64 divisions of metric_of are ~30 instructions and ~150 cycles each on a dependent path).  With
+//   c = (B/g0)/g_ff, u = f/g_ff2 + c, w = 1/(f + c), fh = max(f, f_low), v = 1/fh, t = 1/g1 + (B/g2) v :
+//   H_ff = 1/u,  H_ff' = -w^2,  H_ff'/H_ff = -u w^2,  -H_ff'/H_ff^2 = (u w)^2,
+//   1/H_xx = v t / g_xx,  H_xx'/H_xx = v (t + (B/g2) v) / t   (0 below the faint clamp).
+// Every reciprocal is rcp_fast (2^-60); metric_of stays the reference-order form for reported H, H' and the energies.
+struct MetricK {
+    double c, ig2, ig1, Bg2, igxx, f_low;
+};
+__device__ __forceinline__ MetricK make_metric_k(const FieldParams& P, double g_ff2) {
+    MetricK K;
+    K.c = (P.B / P.g0) / P.g_ff;
+    K.ig2 = 1.0 / g_ff2;
+    K.ig1 = 1.0 / P.g1;
+    K.Bg2 = P.B / P.g2;
+    K.igxx = 1.0 / P.g_xx;
+    K.f_low = P.f_low;
+    return K;
+}
+struct MetricFast {
+    double u;      // 1/H_ff
+    double kap;    // -H_ff'/H_ff^2
+    double ihxx;   // 1/H_xx
+    double tphi;   // (H_ff'/H_ff + 2 H_xx'/H_xx)/2
+};
+__device__ __forceinline__ MetricFast metric_fast(const MetricK& K, double f) {
+    MetricFast m;
+    const double u = fma(f, K.ig2, K.c);
+    const double w = rcp_fast(f + K.c);
+    const double uw = u * w;
+    const bool low = f < K.f_low;
+    const double v = rcp_fast(low ? K.f_low : f);
+    const double bv = K.Bg2 * v;
+    const double t = bv + K.ig1;
+    m.u = u;
+    m.kap = uw * uw;
+    m.ihxx = (v * t) * K.igxx;
+    const double dxx = low ? 0.0 : (v * (t + bv)) * rcp_fast(t);
+    m.tphi = fma(-0.5 * uw, w, dxx);
+    return m;
+}
+__device__ __forceinline__ double inv_hff_k(const MetricK& K, double f) { return fma(f, K.ig2, K.c); }
+__device__ __forceinline__ double inv_hxx_k(const MetricK& K, double f) {
+    const double v = rcp_fast(fmax(f, K.f_low));
+    return (v * fma(K.Bg2, v, K.ig1)) * K.igxx;
+}
+
 __device__ __forceinline__ double ipow(double b, int n) {  // b^n, small n >= 0
     double r = 1.0;
     while (n > 0) {

@@ -642,18 +642,22 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
     const double h = c.h;
     const int tid = threadIdx.x, nt = blockDim.x;
 
+    // The per-star scalar code runs on N of the CTA's 512 threads while the others wait: it is pure latency, so the metric is
+    // taken in its division-free form (metric_fast, common.cuh; 2^-60 reciprocals -- the iterates agree with the division
+    // forms to rounding and the fixed-point counts are unchanged).
+    const MetricK K = make_metric_k(P, c.g_ff2);
     // (1) p <- p - h dphi/dq(q); set up the p fixed point: a1[3k] = anchor rho_f, a2[3k] = -H_ff'/H_ff^2
     for (int k = tid; k < c.N; k += nt) {
-        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        const MetricFast m = metric_fast(K, c.q[3 * k]);
         double gf, gx, gy;
         total_grad(c, k, gf, gx, gy);
-        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        gf += m.tphi;
         const double pf = c.p[3 * k] - h * gf;
         c.p[3 * k] = pf;
         c.p[3 * k + 1] -= h * gx;
         c.p[3 * k + 2] -= h * gy;
         c.a1[3 * k] = pf;   // own slots only: the q fixed point below reuses a1 / a2 per component without a barrier
-        c.a2[3 * k] = -m.dHff / (m.Hff * m.Hff);
+        c.a2[3 * k] = m.kap;
     }
     // (2) p' = rho - h dtau/dq(q, p)  until max|p - p'| <= delta   (only flux slots move)
     // (3) q' = sigma + h (p/H(sigma) + p/H(q))  until max|q - q'| <= delta
@@ -707,19 +711,19 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
     }
     // a1 = sigma, a2 = p/H(sigma): a thread only touches the slots of its own stars
     for (int k = tid; k < c.N; k += nt) {
-        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        const double u0 = inv_hff_k(K, c.q[3 * k]), ih0 = inv_hxx_k(K, c.q[3 * k]);
         c.a1[3 * k] = c.q[3 * k];
         c.a1[3 * k + 1] = c.q[3 * k + 1];
         c.a1[3 * k + 2] = c.q[3 * k + 2];
-        c.a2[3 * k] = c.p[3 * k] / m.Hff;
-        c.a2[3 * k + 1] = c.p[3 * k + 1] / m.Hxx;
-        c.a2[3 * k + 2] = c.p[3 * k + 2] / m.Hxx;
+        c.a2[3 * k] = c.p[3 * k] * u0;
+        c.a2[3 * k + 1] = c.p[3 * k + 1] * ih0;
+        c.a2[3 * k + 2] = c.p[3 * k + 2] * ih0;
     }
     auto q_iter = [&](int k, double& qf, double& qx, double& qy) -> bool {
-        const Metric m = metric_of(P, qf, c.g_ff2);
-        const double nf = c.a1[3 * k] + h * (c.a2[3 * k] + c.p[3 * k] / m.Hff);
-        const double nx = c.a1[3 * k + 1] + h * (c.a2[3 * k + 1] + c.p[3 * k + 1] / m.Hxx);
-        const double ny = c.a1[3 * k + 2] + h * (c.a2[3 * k + 2] + c.p[3 * k + 2] / m.Hxx);
+        const double uq = inv_hff_k(K, qf), ihq = inv_hxx_k(K, qf);
+        const double nf = c.a1[3 * k] + h * (c.a2[3 * k] + c.p[3 * k] * uq);
+        const double nx = c.a1[3 * k + 1] + h * (c.a2[3 * k + 1] + c.p[3 * k + 1] * ihq);
+        const double ny = c.a1[3 * k + 2] + h * (c.a2[3 * k + 2] + c.p[3 * k + 2] * ihq);
         const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
         qf = nf;
         qx = nx;
@@ -761,9 +765,9 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
     }
     // (4) p <- p - h dtau/dq(q, p) at the new q
     for (int k = tid; k < c.N; k += nt) {
-        const Metric m = metric_of(P, c.q[3 * k], c.g_ff2);
+        const MetricFast m = metric_fast(K, c.q[3 * k]);
         const double pf = c.p[3 * k];
-        c.p[3 * k] = pf - h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+        c.p[3 * k] = pf - h * (((pf * pf) * m.kap) / 2.0);
     }
     __syncthreads();
     if (tid == 0) cmax[1] = 0;  // read by every thread before the barrier above; next used after several more
@@ -772,10 +776,10 @@ __device__ void rhmc_step(const Ctx<T>& c, double delta, int counter_max, bool w
     if (want_V) Vpix = v;
     for (int k = tid; k < c.N; k += nt) {
         const double f = c.q[3 * k], x = c.q[3 * k + 1], y = c.q[3 * k + 2];
-        const Metric m = metric_of(P, f, c.g_ff2);
+        const MetricFast m = metric_fast(K, f);
         double gf, gx, gy;
         total_grad(c, k, gf, gx, gy);
-        gf += ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+        gf += m.tphi;
         double pf = c.p[3 * k] - h * gf, px = c.p[3 * k + 1] - h * gx, py = c.p[3 * k + 2] - h * gy;
         // (6) reflections (sampler_RHMC.py:554-564); positions are not clamped
         if (f < P.f_lim) pf *= -1.0;
