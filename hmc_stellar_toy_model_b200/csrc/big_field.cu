@@ -361,12 +361,16 @@ struct BigStep {
     double h, delta, g_ff2;
     int counter_max;
     int per_star;   // srhmc_big_step.fixed_point_mode = 1: every star's fixed points stop at the star's own convergence
+    MetricK K;      // constants of the division-free metric (metric_fast, common.cuh), computed on the host
 };
 
-__device__ __forceinline__ double dphi_f(const BigParams& P, const Metric& m, double gpix_f, double f) {
+// The per-star kernels use the metric in its division-free form (metric_fast: rcp_fast reciprocals, 2^-60): an FP64 division
+// is ~30 instructions on a dependent path and these kernels are either latency-bound (a strip of a tiled field) or spend most
+// of their instructions dividing.  Same iterates to rounding, same fixed-point counts (tests/test_bigfield.py).
+__device__ __forceinline__ double dphi_f(const BigParams& P, const MetricFast& m, double gpix_f, double f) {
     double gf = gpix_f;
     if (P.use_prior) gf += P.F.alpha / f;
-    return gf + ((m.dHff / m.Hff) + (2.0 * m.dHxx / m.Hxx)) / 2.0;
+    return gf + m.tphi;
 }
 
 // (1) p -= h dphi/dq; (2) p fixed point, phase A: iterate to this star's own convergence, record the count
@@ -375,11 +379,11 @@ __global__ void big_kick1_kernel(const BigParams P, const BigStep S, int n, cons
     int local_max = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double f = q[3 * k];
-        const Metric m = metric_of(P.F, f, S.g_ff2);
+        const MetricFast m = metric_fast(S.K, f);
         double pf = p[3 * k] - S.h * dphi_f(P, m, g[3 * k], f);
         p[3 * k + 1] -= S.h * g[3 * k + 1];
         p[3 * k + 2] -= S.h * g[3 * k + 2];
-        const double rho = pf, kap = -m.dHff / (m.Hff * m.Hff);
+        const double rho = pf, kap = m.kap;
         a1[3 * k] = rho;      // anchor
         a2[3 * k] = kap;
         int c = 0;
@@ -411,15 +415,15 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
         // q' = sigma + h (p/H(sigma) + p/H(q))
         const double sf = q[3 * k], sx = q[3 * k + 1], sy = q[3 * k + 2];
         const double px = p[3 * k + 1], py = p[3 * k + 2];
-        const Metric m0 = metric_of(P.F, sf, S.g_ff2);
-        const double bf = pf / m0.Hff, bx = px / m0.Hxx, by = py / m0.Hxx;
+        const double u0 = inv_hff_k(S.K, sf), ih0 = inv_hxx_k(S.K, sf);
+        const double bf = pf * u0, bx = px * ih0, by = py * ih0;
         double qf = sf, qx = sx, qy = sy;
         int c = 0;
         while (c < S.counter_max) {
-            const Metric m = metric_of(P.F, qf, S.g_ff2);
-            const double nf = sf + S.h * (bf + pf / m.Hff);
-            const double nx = sx + S.h * (bx + px / m.Hxx);
-            const double ny = sy + S.h * (by + py / m.Hxx);
+            const double uq = inv_hff_k(S.K, qf), ihq = inv_hxx_k(S.K, qf);
+            const double nf = sf + S.h * (bf + pf * uq);
+            const double nx = sx + S.h * (bx + px * ihq);
+            const double ny = sy + S.h * (by + py * ihq);
             const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
             qf = nf; qx = nx; qy = ny;
             ++c;
@@ -451,14 +455,14 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
         const double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
         double qf = q[3 * k], qx = q[3 * k + 1], qy = q[3 * k + 2];
         for (int c = reinterpret_cast<const int*>(a2 + 3 * (size_t)n)[k]; c < target; ++c) {
-            const Metric m = metric_of(P.F, qf, S.g_ff2);
-            qf = sf + S.h * (bf + pf / m.Hff);
-            qx = sx + S.h * (bx + px / m.Hxx);
-            qy = sy + S.h * (by + py / m.Hxx);
+            const double uq = inv_hff_k(S.K, qf), ihq = inv_hxx_k(S.K, qf);
+            qf = sf + S.h * (bf + pf * uq);
+            qx = sx + S.h * (bx + px * ihq);
+            qy = sy + S.h * (by + py * ihq);
         }
         q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
-        const Metric m = metric_of(P.F, qf, S.g_ff2);
-        p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+        const MetricFast m = metric_fast(S.K, qf);
+        p[3 * k] = pf - S.h * (((pf * pf) * m.kap) / 2.0);
         if (tcnt) bin_star(P, ntx, k, qf, qx, qy, true, tcnt, tlist, err);
         // boundary-star counts per 1024-star chunk for the ordered ghost packing that follows (integer atomics: exact)
         if (pack_counts) {
@@ -473,7 +477,7 @@ __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, 
 __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, const double* q, double* p, const double* g) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double f = q[3 * k], x = q[3 * k + 1], y = q[3 * k + 2];
-        const Metric m = metric_of(P.F, f, S.g_ff2);
+        const MetricFast m = metric_fast(S.K, f);
         double pf = p[3 * k] - S.h * dphi_f(P, m, g[3 * k], f);
         double px = p[3 * k + 1] - S.h * g[3 * k + 1];
         double py = p[3 * k + 2] - S.h * g[3 * k + 2];
@@ -502,7 +506,7 @@ __global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, do
         } else {
             gf = g[3 * k]; gx = g[3 * k + 1]; gy = g[3 * k + 2];
         }
-        const Metric m0 = metric_of(P.F, sf, S.g_ff2);
+        const MetricFast m0 = metric_fast(S.K, sf);
         const double dphi = dphi_f(P, m0, gf, sf);
         double pf = p[3 * k], px = p[3 * k + 1], py = p[3 * k + 2];
         if (FROM_EVAL) {
@@ -518,7 +522,7 @@ __global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, do
         px -= S.h * gx;
         py -= S.h * gy;
         {
-            const double rho = pf, kap = -m0.dHff / (m0.Hff * m0.Hff);
+            const double rho = pf, kap = m0.kap;
             int c = 0;
             while (c < S.counter_max) {
                 const double pn = rho - S.h * (((pf * pf) * kap) / 2.0);
@@ -529,15 +533,15 @@ __global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, do
             }
         }
         // (3) q' = sigma + h (p/H(sigma) + p/H(q))
-        const double bf = pf / m0.Hff, bx = px / m0.Hxx, by = py / m0.Hxx;
+        const double bf = pf * m0.u, bx = px * m0.ihxx, by = py * m0.ihxx;
         double qf = sf, qx = sx, qy = sy;
         {
             int c = 0;
             while (c < S.counter_max) {
-                const Metric m = metric_of(P.F, qf, S.g_ff2);
-                const double nf = sf + S.h * (bf + pf / m.Hff);
-                const double nx = sx + S.h * (bx + px / m.Hxx);
-                const double ny = sy + S.h * (by + py / m.Hxx);
+                const double uq = inv_hff_k(S.K, qf), ihq = inv_hxx_k(S.K, qf);
+                const double nf = sf + S.h * (bf + pf * uq);
+                const double nx = sx + S.h * (bx + px * ihq);
+                const double ny = sy + S.h * (by + py * ihq);
                 const double d = fmax(fabs(qf - nf), fmax(fabs(qx - nx), fabs(qy - ny)));
                 qf = nf; qx = nx; qy = ny;
                 ++c;
@@ -546,8 +550,8 @@ __global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, do
         }
         q[3 * k] = qf; q[3 * k + 1] = qx; q[3 * k + 2] = qy;
         // (4)
-        const Metric m = metric_of(P.F, qf, S.g_ff2);
-        p[3 * k] = pf - S.h * (((pf * pf) * (-m.dHff / (m.Hff * m.Hff))) / 2.0);
+        const MetricFast m = metric_fast(S.K, qf);
+        p[3 * k] = pf - S.h * (((pf * pf) * m.kap) / 2.0);
         p[3 * k + 1] = px;
         p[3 * k + 2] = py;
         if (tcnt) bin_star(P, ntx, k, qf, qx, qy, true, tcnt, tlist, err);
@@ -575,7 +579,7 @@ __global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const
         } else {
             gf = g[3 * k]; gx = g[3 * k + 1]; gy = g[3 * k + 2];
         }
-        const Metric m = metric_of(P.F, f, S.g_ff2);
+        const MetricFast m = metric_fast(S.K, f);
         const double dphi = dphi_f(P, m, gf, f);
         double pf = p[3 * k] - S.h * dphi;
         double px = p[3 * k + 1] - S.h * gx;
@@ -587,7 +591,7 @@ __global__ void big_tail_kernel(const BigParams P, const BigStep S, int n, const
             pf = pf - S.h * dphi;
             px -= S.h * gx;
             py -= S.h * gy;
-            const double rho = pf, kap = -m.dHff / (m.Hff * m.Hff);
+            const double rho = pf, kap = m.kap;
             a1[3 * k] = rho;
             a2[3 * k] = kap;
             int c = 0;
@@ -1493,6 +1497,8 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
     BigStep S;
     S.h = s->dt / 2.0; S.delta = s->delta; S.g_ff2 = s->g_ff2; S.counter_max = s->counter_max;
     S.per_star = s->fixed_point_mode != 0 ? 1 : 0;
+    S.K.c = (P.F.B / P.F.g0) / P.F.g_ff; S.K.ig2 = 1.0 / s->g_ff2; S.K.ig1 = 1.0 / P.F.g1; S.K.Bg2 = P.F.B / P.F.g2;
+    S.K.igxx = 1.0 / P.F.g_xx; S.K.f_low = P.F.f_low;   // make_metric_k (common.cuh) on the host
     const int tb = 128, gs = std::max(1, std::min((n + tb - 1) / tb, 4 * b->sm_count));
     const size_t npix = (size_t)P.nrows * P.C;
     const size_t list = 1 + 3 * (size_t)std::max(1, b->cfg.max_ghosts);
