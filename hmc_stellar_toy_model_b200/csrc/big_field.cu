@@ -369,7 +369,7 @@ struct BigStep {
 // of their instructions dividing.  Same iterates to rounding, same fixed-point counts (tests/test_bigfield.py).
 __device__ __forceinline__ double dphi_f(const BigParams& P, const MetricFast& m, double gpix_f, double f) {
     double gf = gpix_f;
-    if (P.use_prior) gf += P.F.alpha / f;
+    if (P.use_prior) gf = fma(P.F.alpha, rcp_fast(f), gf);
     return gf + m.tphi;
 }
 

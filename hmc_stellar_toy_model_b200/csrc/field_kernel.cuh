@@ -562,7 +562,7 @@ __device__ __forceinline__ void total_grad(const Ctx<T>& c, int k, double& gf, d
     gf = c.g[3 * k];
     gx = c.g[3 * k + 1];
     gy = c.g[3 * k + 2];
-    if (P.use_prior) gf += P.alpha / c.q[3 * k];
+    if (P.use_prior) gf = fma(P.alpha, rcp_fast(c.q[3 * k]), gf);   // per-step path: no FP64 division (2^-60 reciprocal)
     if (P.use_Vc) {
         const double x = c.q[3 * k + 1], y = c.q[3 * k + 2];
         double sx = 0.0, sy = 0.0;
