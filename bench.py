@@ -259,6 +259,7 @@ class ClockSampler:
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+        time.sleep(0.3)   # nvidia-smi needs ~0.2 s before its first line: start it ahead of the timed region, not inside it
         return self
 
     def stop(self):
@@ -382,8 +383,10 @@ class Env:
 
 # ----------------------------------------------------------------------------------------------- independent chains / fields
 def bench_chains(env, wl, *, niter, steps, warmup, e2e_steps, want, precision, scaling, seed_base, field_id_base=0,
-                 device_data_seed=None, parallelism=""):
-    """C2 / C4: F independent fields per rank in one RHMCContext, one resident launch per step."""
+                 device_data_seed=None, parallelism="", min_seconds=0.0):
+    """C2 / C4: F independent fields per rank in one RHMCContext, one resident launch per step.
+    min_seconds (sub-records only): lengthen the timed region to at least this, so that the clock sampler (50 ms period) sees
+    it -- `steps` in the record is the number actually timed."""
     torch = env.torch
     from hmc_stellar_toy_model_b200 import RHMCContext, _capi
 
@@ -426,6 +429,9 @@ def bench_chains(env, wl, *, niter, steps, warmup, e2e_steps, want, precision, s
     for w in range(warmup):
         a, keep = make_args(100 + w)
         ctx.run_launch(a)
+    if min_seconds > 0 and warmup > 0:
+        t_step = env.max_over_ranks([ctx.last_kernel_ms()])[0]
+        steps = int(max(steps, min(64, np.ceil(1e3 * min_seconds / max(t_step, 1e-3)))))
     env.barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = ctx.launch_count
@@ -613,7 +619,7 @@ def tiled_parity_check(env, stream):
 
 
 def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_steps, comm_kind, with_parity, precision=64,
-                   replicas=False, label="c5_tiled_field", dt=None, fixed_point_mode=0):
+                   replicas=False, label="c5_tiled_field", dt=None, fixed_point_mode=0, min_seconds=0.0):
     """C5: ONE large field, row strips over the ranks (strong), or one rows x cols strip per rank (weak).
     replicas=True (C3): every rank runs its own copy of the whole field, no communication."""
     torch = env.torch
@@ -651,9 +657,17 @@ def bench_bigfield(env, *, rows, cols, nstars, weak, niter, steps, warmup, e2e_s
     pin_D = _capi.PinnedBuffer((strip.nrows, cols))
     pin_D.array[...] = strip.gen_mock_data(t["q_true"], seed=77, return_data=True)
     units = nst_g * (niter + 1) * run["nsteps"] * (n_ranks if replicas else 1)
+    t_step = 0.0
     for w in range(warmup):
         strip.set_stars(t["q0"])
+        torch.cuda.synchronize()
+        t0w = time.perf_counter()
         eng.run(niter, seed=1000, **run)
+        torch.cuda.synchronize()
+        t_step = time.perf_counter() - t0w
+    if min_seconds > 0 and warmup > 0:   # sub-records: a timed region the 50 ms clock sampler can see
+        t_step = env.max_over_ranks([t_step])[0]
+        steps = int(max(steps, min(400, np.ceil(min_seconds / max(t_step, 1e-6)))))
     env.barrier()
     sampler = ClockSampler(env.local).start() if env.rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -791,7 +805,7 @@ def run_ours(args):
             wl["name"] += "_fp32"
         return bench_chains(env, wl, niter=args.c4_niter, steps=args.sub_steps, warmup=3, e2e_steps=2, want=("E", "A"),
                             precision=args.precision if precision is None else precision, scaling="strong", seed_base=17,
-                            field_id_base=rank * per,
+                            field_id_base=rank * per, min_seconds=0.6 if which == "all" else 0.0,
                             device_data_seed=4, parallelism="%d independent fields split over %d GPU(s) (contiguous "
                             "blocks), no communication" % (per * world, world))
 
@@ -800,7 +814,8 @@ def run_ours(args):
                               steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
                               comm_kind=args.comm, with_parity=not weak and precision is None and not fixed_point_mode,
                               precision=args.precision if precision is None else precision,
-                              fixed_point_mode=fixed_point_mode or args.fixed_point_mode)
+                              fixed_point_mode=fixed_point_mode or args.fixed_point_mode,
+                              min_seconds=0.6 if which == "all" else 0.0)
 
     def c3():
         # BASELINE configs[2]: "RHMC-big-sim2/3/4 crowded field: hundreds to thousands of stars in one large image with the
@@ -808,7 +823,7 @@ def run_ours(args):
         return bench_bigfield(env, rows=256, cols=256, nstars=3277, weak=False, niter=args.c5_niter,
                               steps=max(10, args.sub_steps) if which == "all" else args.steps, warmup=3, e2e_steps=2,
                               comm_kind=args.comm, with_parity=False, precision=args.precision, replicas=True,
-                              label="c3_crowded_field")
+                              label="c3_crowded_field", min_seconds=0.6 if which == "all" else 0.0)
 
     if which == "c4":
         out = c4()
@@ -824,7 +839,7 @@ def run_ours(args):
         wl = workload_c2(args.chains_per_mag, 77 + rank)
         wl["name"] = "c2_one_star_32x32_fp32"
         return bench_chains(env, wl, niter=args.niter, steps=args.sub_steps, warmup=3, e2e_steps=2,
-                            want=("q", "p", "E", "V", "T", "A"), precision=32, scaling="weak", seed_base=0,
+                            want=("q", "p", "E", "V", "T", "A"), precision=32, scaling="weak", seed_base=0, min_seconds=0.6,
                             parallelism="independent chains sharded across %d GPU(s), no communication; FP32 pixel "
                             "arithmetic for the gradient-only evaluations, FP64 state and energies" % world)
 
