@@ -191,13 +191,24 @@ __global__ void big_gather_kernel(const BigParams P, const double* q, int n_own,
             const int irow = i0 + lane;
             const double dxl = ((double)irow + 0.5) - x;
             const double exl = (irow <= i1) ? exp(-(dxl * dxl) * P.inv2s2) : 0.0;
+            // the lane's column of the residual patch first, all loads in flight together (one L2 latency instead of one per
+            // row: this kernel runs one wave of warps on the small fields it serves, so its time IS that latency chain)
+            constexpr int kRows = 2 * kMaxRad + 1;
+            double rr[kRows];
+            const double* lp = L + (size_t)(i0 - P.row0) * P.C + min(j, j1);
+            const int nrow = i1 - i0 + 1;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) rr[r] = (r < nrow) ? __ldcg(lp + (size_t)r * P.C) : 0.0;
             double c0 = 0.0, c1 = 0.0;
-            for (int i = i0; i <= i1; ++i) {
-                const double ex = __shfl_sync(0xffffffffu, exl, i - i0);
-                const double dx = ((double)i + 0.5) - x;
-                const double rho = okc ? L[(size_t)(i - P.row0) * P.C + j] : 0.0;
-                c0 = fma(rho, ex, c0);
-                c1 = fma(rho, ex * dx, c1);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (r < nrow) {
+                    const double ex = __shfl_sync(0xffffffffu, exl, r);
+                    const double dx = ((double)(i0 + r) + 0.5) - x;
+                    const double rho = okc ? rr[r] : 0.0;
+                    c0 = fma(rho, ex, c0);
+                    c1 = fma(rho, ex * dx, c1);
+                }
             }
             sf = ey * c0;
             sx = ey * c1;
@@ -447,7 +458,11 @@ __global__ void big_pfix_qfix_kernel(const BigParams P, const BigStep S, int n, 
 // and -- tile path -- the pair records of the star's final position for the coming evaluation (bin_star, big_tile.cuh)
 __global__ void big_qfix_kick_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, const double* a1,
                                      const double* a2, const int* cnt_q, int ntx, int* tcnt, PairRec* tlist, int* err, const PeerX X,
-                                     int2* pack_counts, double lo_edge, double hi_edge) {
+                                     int2* pack_counts, double lo_edge, double hi_edge, double* Lfill, size_t npix) {
+    // star-parallel evaluation path: the model image of the COMING evaluation is reset to the background here (nobody reads
+    // it between the last gather and the next scatter), which saves that path a launch per leapfrog step
+    if (Lfill)
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) Lfill[i] = P.F.B;
     const int target = S.per_star ? 0 : (X.on ? peer_max_in_kernel(X, *cnt_q) : *cnt_q);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = a1[3 * k], sx = a1[3 * k + 1], sy = a1[3 * k + 2];
@@ -496,7 +511,10 @@ __global__ void big_kick2_kernel(const BigParams P, const BigStep S, int n, cons
 // Same expressions, in the same order, as big_tail_kernel / big_kick1_kernel / big_pfix_qfix_kernel / big_qfix_kick_kernel.
 template <bool FROM_EVAL>
 __global__ void big_perstar_kernel(const BigParams P, const BigStep S, int n, double* q, double* p, double* g, const double* gpart,
-                                   int ntx, int* tcnt, PairRec* tlist, int* err, int2* pack_counts, double lo_edge, double hi_edge) {
+                                   int ntx, int* tcnt, PairRec* tlist, int* err, int2* pack_counts, double lo_edge, double hi_edge,
+                                   double* Lfill, size_t npix) {
+    if (Lfill)   // as big_qfix_kick_kernel: background reset of the star-parallel path's model image
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) Lfill[i] = P.F.B;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const double sf = q[3 * k], sx = q[3 * k + 1], sy = q[3 * k + 2];
         double gf, gx, gy;
@@ -1018,6 +1036,7 @@ struct srhmc_big {
     CUtensorMap tmapD32{};
     bool tma = false;          // a tensor map over the data window exists: the tile kernels load their tile by TMA
     bool tile2 = false;        // persistent variant (big_tile2_kernel, SRHMC_TILE_V2=1) instead of one CTA per tile
+    bool L_filled = false;     // star-parallel path: the position-update kernel has already reset the model image
     int star_mode = -1;        // gradient-only FP64 evaluations by big_star_kernel: -1 = when the tile lists are short (sparse
                                // field), 0 = never, 1 = always (SRHMC_BIG_STAR)
     CUtensorMap tmapD{};
@@ -1527,12 +1546,14 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
         int* tc = b->use_tiles ? b->tcnt.as<int>() : nullptr;
         PairRec* tl = b->use_tiles ? b->tlist.as<PairRec>() : nullptr;
         int2* pc = count_here ? b->packcnt.as<int2>() : nullptr;
+        double* lf = (!b->use_tiles && n > 0) ? b->L.as<double>() : nullptr;
         if (from_eval)
             big_perstar_kernel<true><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), gpart_in,
-                                                        b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k);
+                                                        b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k, lf, npix);
         else
             big_perstar_kernel<false><<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->g.as<double>(), nullptr,
-                                                         b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k);
+                                                         b->ntx, tc, tl, b->err.as<int>(), pc, lo_edge_k, hi_edge_k, lf, npix);
+        b->L_filled = lf != nullptr;
         b->pack_counted = count_here;
         b->own_binned = b->use_tiles;
         b->launches += 1;
@@ -1657,7 +1678,11 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 gpart = b->gpart.as<double>();
             } else {
                 const int pg = (int)std::min<size_t>((npix + 255) / 256, (size_t)kVBlocks);
-                big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
+                if (!b->L_filled) {
+                    big_fill_kernel<<<pg, 256, 0, st>>>(b->L.as<double>(), npix, P.F.B);
+                    b->launches += 1;
+                }
+                b->L_filled = false;
                 const int total = n + 2 * std::max(1, b->cfg.max_ghosts);
                 const int sg = std::max(1, std::min((total * 32 + 255) / 256, 16 * b->sm_count));
                 big_scatter_kernel<<<sg, 256, 0, st>>>(P, b->q.as<double>(), n, ga, gb, b->L.as<double>(), b->err.as<int>());
@@ -1665,7 +1690,7 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
                 if (want_V) big_vsum_kernel<<<1, 256, 0, st>>>(b->vpart.as<double>(), pg, b->scalars.as<double>());
                 const int gg = std::max(1, std::min((n * 32 + 255) / 256, 16 * b->sm_count));
                 big_gather_kernel<<<gg, 256, 0, st>>>(P, b->q.as<double>(), n, b->L.as<double>(), b->g.as<double>());
-                b->launches += want_V ? 5 : 4;
+                b->launches += want_V ? 4 : 3;
                 if (tail == 2) BCU(cudaMemsetAsync(cnt, 0, 8, st));  // the tile kernel does this on the tile path
             }
             if (tail == 1)
@@ -1720,7 +1745,9 @@ int srhmc_big_phase(srhmc_big* b, int32_t phase, const srhmc_big_step* s) {
             big_qfix_kick_kernel<<<gs, tb, 0, st>>>(P, S, n, b->q.as<double>(), b->p.as<double>(), b->a1.as<double>(),
                                                     b->a2.as<double>(), cnt + 1, b->ntx, b->use_tiles ? b->tcnt.as<int>() : nullptr,
                                                     b->use_tiles ? b->tlist.as<PairRec>() : nullptr, b->err.as<int>(), X,
-                                                    count_here ? b->packcnt.as<int2>() : nullptr, lo_edge_k, hi_edge_k);
+                                                    count_here ? b->packcnt.as<int2>() : nullptr, lo_edge_k, hi_edge_k,
+                                                    (!b->use_tiles && n > 0) ? b->L.as<double>() : nullptr, npix);
+            b->L_filled = !b->use_tiles && n > 0;
             b->pack_counted = count_here;
             b->own_binned = b->use_tiles;
             b->launches += 1;
