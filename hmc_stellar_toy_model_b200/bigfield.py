@@ -28,6 +28,17 @@ PHASE = dict(PACK=0, EVAL=1, EVAL_V=2, KICK1=3, PFIX_QFIX=4, QFIX_KICK=5, KICK2=
 
 
 # ----------------------------------------------------------------------------------------------- host-side geometry
+def tile_order(q, cols, tile=64):
+    """Permutation that sorts stars [n,3] (f, x, y) by the 64x64 tile holding them (row-major over the tiles, original order
+    inside a tile)."""
+    q = np.asarray(q, dtype=np.float64).reshape(-1, 3)
+    if len(q) < 2:
+        return np.arange(len(q), dtype=np.int64)
+    ti = np.floor(q[:, 1]).astype(np.int64) // tile
+    tj = np.floor(q[:, 2]).astype(np.int64) // tile
+    return np.argsort(ti * (int(cols) // tile + 1) + tj, kind="stable").astype(np.int64)
+
+
 def strip_bounds(rows: int, world: int):
     """Owned row ranges [lo, hi) of `world` equal-height strips (the last one takes the remainder)."""
     base = rows // world
@@ -152,10 +163,7 @@ class BigFieldStrip:
         # stars are stored in 64x64-tile order (row-major over the tiles, stable inside a tile): consecutive warps of the
         # star-centric gradient kernel then read neighbouring patches (DRAM pages and L2 lines are shared instead of being
         # opened once per 200-byte row segment).  `ids` carries the permutation: every per-star array of the API is in this order.
-        if len(mine) > 1:
-            ti = np.floor(q_global[mine, 1]).astype(np.int64) // 64
-            tj = np.floor(q_global[mine, 2]).astype(np.int64) // 64
-            mine = mine[np.argsort(ti * (self.cols // 64 + 1) + tj, kind="stable")]
+        mine = mine[tile_order(q_global[mine], self.cols)]
         q = np.ascontiguousarray(q_global[mine])
         check(self._lib.srhmc_big_set_stars(self._h, _capi.dptr(q), mine.ctypes.data_as(C.POINTER(C.c_int64)), len(mine)))
         self.n, self.ids = len(mine), mine

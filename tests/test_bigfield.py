@@ -30,6 +30,19 @@ def test_strip_geometry():
         bf.strip_bounds(3, 8)
 
 
+def test_tile_order_is_a_stable_row_major_tile_sort():
+    """set_stars stores a strip's stars in 64x64-tile order (locality for the tile lists and footprint sums)."""
+    rng = np.random.RandomState(1)
+    q = np.stack([rng.uniform(1, 2, 500), rng.uniform(-3, 400, 500), rng.uniform(-2, 700, 500)], axis=1)
+    order = bf.tile_order(q, 700)
+    assert sorted(order.tolist()) == list(range(500))
+    key = (np.floor(q[order, 1]) // 64) * (700 // 64 + 1) + np.floor(q[order, 2]) // 64
+    assert np.all(np.diff(key) >= 0)
+    same = np.diff(key) == 0
+    assert np.all(np.diff(order)[same] > 0)          # stable inside a tile
+    assert bf.tile_order(q[:1], 700).tolist() == [0] and len(bf.tile_order(q[:0], 700)) == 0
+
+
 def test_ghost_lists_cover_every_star_that_can_touch_a_neighbour():
     rows, world, rad, halo = 256, 4, 12, 24
     rng = np.random.RandomState(1)
