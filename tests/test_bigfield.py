@@ -397,6 +397,30 @@ def test_bigfield_per_star_chain_tiled_equals_untiled(monkeypatch):
     assert relerr(b[0]["E_chain"], a[0]["E_chain"]) < 1e-10
     assert relerr(b[1], a[1]) < 1e-9
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bigfield_sparse_chain_star_kernel_tiled_equals_untiled(mode, monkeypatch):
+    """A sparse field (150 stars on 640x700: the automatic rule hands the gradient-only evaluations to the star-centric
+    kernel, the potential to the tile kernel) through whole Metropolis iterations, untiled and as three strips with ghosts, in
+    both stop-rule modes: same decisions, energies to 1e-10 -- and the same chain as with the tile kernel alone."""
+    monkeypatch.setenv("SRHMC_BIG_PATH", "tile")
+    S, D, q0 = _synthetic_field(640, 700, 150, 17)
+    outs = {}
+    for star, world in (("auto", 1), ("auto", 3), ("0", 1)):
+        if star == "auto":
+            monkeypatch.delenv("SRHMC_BIG_STAR", raising=False)
+        else:
+            monkeypatch.setenv("SRHMC_BIG_STAR", star)
+        eng = _engine(S, q0.ravel(), world=world, D=D, halo=20, fixed_point_mode=mode)
+        outs[(star, world)] = (eng.run(6, 5, 2e-2, f_pos=True, g_ff2=4.0, seed=11), eng.stars(150)[0])
+    a, b, c = outs[("auto", 1)], outs[("auto", 3)], outs[("0", 1)]
+    assert 0 < a[0]["A_chain"].sum()
+    for other in (b, c):
+        assert np.array_equal(a[0]["A_chain"], other[0]["A_chain"])
+        assert relerr(other[0]["E_chain"], a[0]["E_chain"]) < 1e-10
+        assert relerr(other[1], a[1]) < 1e-9
+
 @pytest.mark.gpu
 def test_bigfield_tile_kernel_dense_list_chunks_and_auto_path(monkeypatch):
     """1600x1600 field (625 tiles > 2 x SM count: the tile path is chosen automatically) and a clump of 300 stars in
