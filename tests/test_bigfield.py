@@ -338,6 +338,23 @@ def test_bigfield_star_kernel_equals_tile_kernel(rows, cols, n, world, monkeypat
 
 
 @pytest.mark.gpu
+def test_bigfield_star_kernel_wide_patch(monkeypatch):
+    """Patch radius 14 (29 x 29 patches: the 31-row instantiation of the star-centric kernel) against the tile kernel and the
+    patch oracle, untiled and as two strips."""
+    S, D, q0 = _synthetic_field(640, 700, 500, 8)
+    _, gref = so.patch_eval(S, D, q0, 14)
+    for world in (1, 2):
+        res = {}
+        for path in ("tile", "star"):
+            _set_path(monkeypatch, path)
+            eng = _engine(S, q0.ravel(), world=world, D=D, rad=14, halo=24)
+            eng.evaluate(want_V=False, g_ff2=4.0)
+            res[path] = eng.stars(500)[2]
+        assert _grad_close(res["star"], res["tile"], 1e-11)
+        assert _grad_close(res["star"], gref, 1e-10)
+
+
+@pytest.mark.gpu
 def test_bigfield_star_kernel_spot_check_against_patch_oracle(monkeypatch):
     """The star-centric kernel chosen by the automatic rule (very sparse 1600x1600 field: 400 stars on 625 tiles) against the
     NumPy patch oracle, and the same field with 3000 stars (tile kernel by the rule, star kernel forced)."""
