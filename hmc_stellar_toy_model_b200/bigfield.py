@@ -34,9 +34,13 @@ def tile_order(q, cols, tile=64):
     q = np.asarray(q, dtype=np.float64).reshape(-1, 3)
     if len(q) < 2:
         return np.arange(len(q), dtype=np.int64)
-    ti = np.floor(q[:, 1]).astype(np.int64) // tile
-    tj = np.floor(q[:, 2]).astype(np.int64) // tile
-    return np.argsort(ti * (int(cols) // tile + 1) + tj, kind="stable").astype(np.int64)
+    ti = np.floor(q[:, 1] * (1.0 / tile)).astype(np.int64)      # floor(x / tile) = floor(x) // tile
+    tj = np.floor(q[:, 2] * (1.0 / tile)).astype(np.int64)
+    key = ti * (int(cols) // tile + 1) + tj
+    key -= key.min()
+    if key.max() < 65536:
+        key = key.astype(np.uint16)   # NumPy's stable sort of 16-bit keys is a radix sort: ~4x faster on 1e5 stars
+    return np.argsort(key, kind="stable").astype(np.int64)
 
 
 def strip_bounds(rows: int, world: int):
@@ -163,8 +167,9 @@ class BigFieldStrip:
         # stars are stored in 64x64-tile order (row-major over the tiles, stable inside a tile): consecutive warps of the
         # star-centric gradient kernel then read neighbouring patches (DRAM pages and L2 lines are shared instead of being
         # opened once per 200-byte row segment).  `ids` carries the permutation: every per-star array of the API is in this order.
-        mine = mine[tile_order(q_global[mine], self.cols)]
-        q = np.ascontiguousarray(q_global[mine])
+        q = q_global if len(mine) == len(q_global) else q_global[mine]
+        order = tile_order(q, self.cols)
+        mine, q = mine[order], np.ascontiguousarray(q[order])
         check(self._lib.srhmc_big_set_stars(self._h, _capi.dptr(q), mine.ctypes.data_as(C.POINTER(C.c_int64)), len(mine)))
         self.n, self.ids = len(mine), mine
 
